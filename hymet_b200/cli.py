@@ -1,0 +1,150 @@
+"""`mash`-compatible command line: the process-level drop-in.
+
+HYMET only ever runs ``mash screen -p 8 -v 0.9 DB.msh dir/*.fna``
+(/root/reference/scripts/mash.sh:14; presence check run_hymet_cami.sh:72).  Put
+bin/mash first on PATH and the unmodified scripts keep working: same options
+(-p -v -i -w -h), same stdout TSV, same exit codes, progress on stderr (S20/S21).
+"""
+from __future__ import annotations
+
+import os
+import sys
+from typing import List, Optional
+
+USAGE = """
+Version: hymet-screen-b200 (mash screen drop-in, B200)
+
+Usage:
+
+  mash screen [options] <queries>.msh <mixture> [<mixture>] ...
+
+Description:
+
+  Determine how well query sequences are contained within a mixture of
+  sequences. The queries must be formatted as a single Mash sketch file (.msh).
+  The mixture files can be contigs or reads, in fasta or fastq, gzipped or not,
+  and "-" can be given for <mixture> to read from standard input. The output
+  fields are [identity, shared-hashes, median-multiplicity, p-value, query-ID,
+  query-comment], where median-multiplicity is computed for shared hashes.
+
+Options:
+
+  -h          Help
+  -p <int>    Host packer threads [1]
+  -w          Winner-takes-all strategy for identity estimates.
+  -i <num>    Minimum identity to report. Inclusive unless set to zero. -1 to
+              include all. [0]
+  -v <num>    Maximum p-value to report. (0-1) [1.0]
+"""
+
+
+def _err(msg: str) -> None:
+    sys.stderr.write("ERROR: %s\n" % msg)
+
+
+def screen_main(args: List[str], stdout=None) -> int:
+    stdout = stdout or sys.stdout
+    threads, wta, imin, pmax = 1, False, 0.0, 1.0
+    pos: List[str] = []
+    i = 0
+    try:
+        while i < len(args):
+            a = args[i]
+            if a == "-h":
+                stdout.write(USAGE)
+                return 0
+            if a == "-w":
+                wta = True
+            elif a in ("-p", "-i", "-v"):
+                if i + 1 >= len(args):
+                    _err("-%s requires an argument" % a[1])
+                    return 1
+                v = args[i + 1]
+                i += 1
+                if a == "-p":
+                    threads = int(v)
+                elif a == "-i":
+                    imin = float(v)
+                else:
+                    pmax = float(v)
+            elif a.startswith("-") and a != "-":
+                _err("Unrecognized option: %s" % a)
+                return 1
+            else:
+                pos.append(a)
+            i += 1
+    except ValueError:
+        _err("malformed numeric option value")
+        return 1
+    if len(pos) < 2:
+        stdout.write(USAGE)
+        return 0
+    db_path, inputs = pos[0], pos[1:]
+    if not db_path.endswith(".msh"):
+        _err("%s does not look like a sketch (.msh)" % db_path)
+        return 1
+    if threads < 1 or not (0.0 <= pmax <= 1.0) or imin > 1.0:
+        _err("option value out of range")
+        return 1
+
+    from . import screen as hs   # ctypes + numpy only: no torch import on the CLI path
+    from .tsv import screen_lines
+
+    device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
+    try:
+        sys.stderr.write("Loading %s...\n" % db_path)
+        db = hs.Database.load_msh(db_path, device)
+        sys.stderr.write("   %d distinct hashes.\n" % db.n_distinct)
+        scr = hs.Screen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
+        sys.stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
+        for p in inputs:
+            if p != "-" and not os.path.exists(p):
+                _err("could not open %s for reading." % p)
+                return 1
+            scr.feed_fasta(p, threads)
+        scr.flush()
+        st = scr.stats()
+        if st["n_records"] == 0:
+            _err("Did not find sequence records in inputs.")
+            return 1
+        sys.stderr.write("   Estimated distinct k-mers in mixture: %d\n" % st["set_size"])
+        if st["set_size"] == 0:
+            sys.stderr.write("WARNING: no valid k-mers in input.\n")
+        sys.stderr.write("Summing shared...\n")
+        if wta:
+            sys.stderr.write("Reallocating to winners...\n")
+        sys.stderr.write("Computing coverage medians...\n")
+        res = scr.finish(wta)
+        sys.stderr.write("Writing output...\n")
+        for ln in screen_lines(res.shared, db.sizes, res.median, res.identity, res.pvalue, db.names, db.comments,
+                               imin, pmax):
+            stdout.write(ln)
+        stdout.flush()
+        return 0
+    except hs.HsError as e:
+        _err(e.msg)
+        return 1
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    argv = sys.argv[1:] if argv is None else argv
+    if not argv or argv[0] in ("-h", "--help", "help"):
+        sys.stdout.write("mash (hymet-screen-b200): only the `screen` command is provided.\n" + USAGE)
+        return 0
+    if argv[0] == "--version":
+        sys.stdout.write("2.3-hymet-screen-b200\n")
+        return 0
+    if argv[0] != "screen":
+        # HYMET uses nothing else; hand over to a real mash when one exists further down PATH
+        me = os.path.realpath(sys.argv[0])
+        for d in os.environ.get("PATH", "").split(os.pathsep):
+            cand = os.path.join(d, "mash")
+            if os.path.isfile(cand) and os.access(cand, os.X_OK) and os.path.realpath(cand) != me:
+                os.execv(cand, [cand] + argv)
+        sys.stderr.write("mash (hymet-screen-b200): command '%s' is not provided by this drop-in\n" % argv[0])
+        return 2
+    return screen_main(argv[1:])
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,1074 @@
+// abi.cu -- the C ABI of libhymet_screen.so (include/hymet_screen.h): handle
+// lifetimes, HBM layout, stream orchestration.  All arithmetic of the hot path runs
+// in the kernels of screen_kernels.cu; the only host arithmetic here is control
+// logic (thresholds, S10's one-line set-size formula, merging <= G*s mixture hashes).
+// There is deliberately no CPU implementation of any kernel in this library.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/hymet_screen.h"
+#include "fasta_pack.h"
+#include "kmer_core.cuh"
+#include "msh_capnp.h"
+#include "screen_kernels.h"
+
+#define HS_API extern "C" __attribute__((visibility("default")))
+
+using namespace hs;
+
+namespace {
+
+thread_local std::string g_err;
+int g_device = -1;
+int g_sm = 0;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) return fail(HS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define NEED_DEVICE()                                                                                      \
+    do {                                                                                                   \
+        if (g_device < 0) return fail(HS_ENODEV, "hs_init() has not bound an sm_100 device (no CPU fallback)"); \
+        CU(cudaSetDevice(g_device));                                                                       \
+    } while (0)
+
+double now_s()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+uint64_t tiles_for(uint64_t n_bases) { return ((n_bases + 31) / 32 + kTileWords - 1) / kTileWords; }
+
+// ---- device arena for query chunks ------------------------------------------
+struct Arena {
+    struct Slab { char *p; size_t cap, used; };
+    std::vector<Slab> slabs;
+    size_t slab_bytes = (size_t)256 << 20;
+    size_t total = 0;
+    cudaError_t alloc(size_t n, void **out)
+    {
+        n = (n + 255) & ~(size_t)255;
+        if (slabs.empty() || slabs.back().used + n > slabs.back().cap) {
+            Slab s{nullptr, std::max(n, slab_bytes), 0};
+            cudaError_t e = cudaMalloc((void **)&s.p, s.cap);
+            if (e != cudaSuccess) return e;
+            slabs.push_back(s);
+            total += s.cap;
+        }
+        *out = slabs.back().p + slabs.back().used;
+        slabs.back().used += n;
+        return cudaSuccess;
+    }
+    void reset()
+    {   // keep the first slab for reuse, drop the rest
+        for (size_t i = 1; i < slabs.size(); i++) { cudaFree(slabs[i].p); total -= slabs[i].cap; }
+        if (slabs.size() > 1) slabs.resize(1);
+        if (!slabs.empty()) slabs[0].used = 0;
+    }
+    void release()
+    {
+        for (auto &s : slabs) cudaFree(s.p);
+        slabs.clear();
+        total = 0;
+    }
+};
+
+struct Chunk {
+    const uint64_t *d_seq;
+    const uint32_t *d_inv;
+    uint64_t n_bases;
+};
+
+// ---- mixture bottom-s engine (K3 control logic) --------------------------------
+// ctl words on the device: [0] distinct count, [1] overflow, [2] has_max, [3] n_out, [4] n_unique
+struct MixEngine {
+    uint32_t s = 0, cap = 0, cand_cap = 0;
+    uint64_t *d_set[2] = {nullptr, nullptr};
+    int cur = 0;
+    uint32_t *d_ctl = nullptr;
+    uint32_t *h_ctl = nullptr;  // pinned
+    uint64_t *d_cand = nullptr, *d_scratch = nullptr;
+    uint64_t tau = ~0ull;
+    bool dirty = false;    // the set lost elements (overflow): must be rebuilt by re-hashing
+    bool touched = false;  // launches since the last check
+    bool auto_tau = true;  // first pass: lower tau per launch so expected offers stay <= cap/8
+    uint32_t passes = 1;
+
+    int init(uint32_t s_)
+    {
+        s = s_ ? s_ : 1;
+        cap = 1u << 20;
+        while ((uint64_t)cap < 64ull * s) cap <<= 1;
+        cand_cap = 8192;
+        while (cand_cap < 4 * s) cand_cap <<= 1;
+        for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&d_set[i], (size_t)cap * 8));
+        CU(cudaMalloc((void **)&d_ctl, 8 * sizeof(uint32_t)));
+        CU(cudaHostAlloc((void **)&h_ctl, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
+        CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
+        return HS_OK;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < 2; i++) cudaFree(d_set[i]);
+        cudaFree(d_ctl); cudaFree(d_cand); cudaFree(d_scratch);
+        if (h_ctl) cudaFreeHost(h_ctl);
+    }
+    size_t bytes() const { return (size_t)cap * 16 + (size_t)cand_cap * 16; }
+    int reset(cudaStream_t st, uint64_t new_tau = ~0ull)
+    {
+        CU(cudaMemsetAsync(d_set[cur], 0xFF, (size_t)cap * 8, st));
+        CU(cudaMemsetAsync(d_ctl, 0, 8 * sizeof(uint32_t), st));
+        tau = new_tau; dirty = false; touched = false;
+        auto_tau = new_tau == ~0ull;  // a re-offer pass runs at the tau the finaliser chose
+        return HS_OK;
+    }
+    // threshold for a launch over n positions: expected offers <= cap/8
+    void before_launch(uint64_t n)
+    {
+        const uint64_t budget = cap / 8;
+        if (auto_tau && n > budget) {
+            const uint64_t t = (~0ull / n) * budget;
+            if (t < tau) tau = t;
+        }
+        touched = true;
+    }
+    MixView view() const
+    {
+        MixView v;
+        v.set = d_set[cur]; v.mask = cap - 1; v.limit = cap / 2; v.tau = tau;
+        v.count = d_ctl; v.overflow = d_ctl + 1; v.has_max = d_ctl + 2;
+        return v;
+    }
+    // Between launches: keep the set sparse by lowering tau (exact: dropped values
+    // are larger than >= s kept ones, so they can never be among the s smallest).
+    int check(cudaStream_t st)
+    {
+        if (!touched) return HS_OK;
+        CU(cudaMemcpyAsync(h_ctl, d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        touched = false;
+        if (h_ctl[1]) { dirty = true; return HS_OK; }
+        while (h_ctl[0] > cap / 4 && (tau >> 2) > 0) {
+            const uint64_t nt = tau >> 2;
+            const int other = cur ^ 1;
+            CU(cudaMemsetAsync(d_set[other], 0xFF, (size_t)cap * 8, st));
+            CU(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t), st));
+            CU(launch_mix_rebuild(d_set[cur], cap, nt, d_set[other], d_ctl, st));
+            CU(cudaMemcpyAsync(h_ctl, d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            cur = other; tau = nt;
+        }
+        return HS_OK;
+    }
+};
+
+}  // namespace
+
+// =============================================================================
+// handles
+// =============================================================================
+struct hs_msh { MshData d; };
+
+struct hs_db {
+    uint32_t k = 0, s = 0, seed = 42;
+    bool use64 = true;
+    uint64_t n_refs = 0, n_entries = 0, n_distinct = 0, max_key = 0;
+    std::vector<std::string> names, comments;
+    std::vector<uint64_t> lengths, offsets;
+    uint64_t *d_keys = nullptr;
+    uint32_t *d_vals = nullptr;
+    uint32_t n_buckets = 0, special = kNoEntry;
+    uint32_t *d_canon = nullptr;
+    uint64_t *d_offsets = nullptr, *d_lengths = nullptr;
+    uint64_t device_bytes = 0;
+    double t_parse = 0, t_build = 0;
+    TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special}; }
+};
+
+struct Staging {
+    uint64_t *seq = nullptr;
+    uint32_t *inv = nullptr;
+    uint64_t cap_words = 0;
+    cudaEvent_t free_ev = nullptr;
+};
+
+struct hs_screen {
+    hs_db *db = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint32_t *d_counts = nullptr;
+    unsigned long long *d_stats = nullptr;
+    MixEngine mix;
+    std::vector<uint64_t> mixture;  // settled s smallest distinct hashes, ascending
+    bool flushed = false;
+    uint32_t *d_shared = nullptr, *d_median = nullptr;
+    double *d_identity = nullptr, *d_pvalue = nullptr;
+    unsigned long long *d_best_score = nullptr, *d_best_len = nullptr;
+    uint32_t *d_winner = nullptr;
+    Arena arena;
+    std::vector<Chunk> chunks;
+    std::vector<Staging> staging;
+    std::mutex mu;  // serialises arena + launches when packer threads feed concurrently
+    bool filter = true;
+    uint64_t chunk_text = (uint64_t)16 << 20;
+    hs_stats_t st;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    cudaEvent_t red0 = nullptr, red1 = nullptr;
+};
+
+namespace {
+
+int db_build(hs_db *db, const uint64_t *hashes)
+{
+    const double t0 = now_s();
+    const uint64_t E = db->n_entries, N = db->n_refs;
+    if (E > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "more than 2^32 stored hashes");
+    if (db->k == 0 || db->k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
+    uint64_t nb = (E * 3 + 3) / 4;  // 4 slots per bucket -> load factor <= 1/3
+    if (nb < 16) nb = 16;
+    db->n_buckets = (uint32_t)nb;
+    db->max_key = 0;
+    for (uint64_t i = 0; i < N; i++)
+        if (db->offsets[i + 1] > db->offsets[i]) db->max_key = std::max(db->max_key, hashes[db->offsets[i + 1] - 1]);
+    for (uint64_t i = 0; i < N; i++)  // ascending order is part of the format; verify instead of trusting
+        for (uint64_t e = db->offsets[i] + 1; e < db->offsets[i + 1]; e++)
+            if (hashes[e] <= hashes[e - 1]) return fail(HS_EFORMAT, "sketch hashes are not strictly ascending");
+
+    uint64_t *d_hashes = nullptr;
+    uint32_t *d_flags = nullptr;
+    unsigned long long *d_nd = nullptr;
+    CU(cudaMalloc((void **)&db->d_keys, nb * 32));
+    CU(cudaMalloc((void **)&db->d_vals, nb * 16));
+    CU(cudaMalloc((void **)&db->d_canon, std::max<uint64_t>(E, 1) * 4));
+    CU(cudaMalloc((void **)&db->d_offsets, (N + 1) * 8));
+    CU(cudaMalloc((void **)&db->d_lengths, std::max<uint64_t>(N, 1) * 8));
+    CU(cudaMalloc((void **)&d_hashes, std::max<uint64_t>(E, 1) * 8));
+    CU(cudaMalloc((void **)&d_flags, 2 * sizeof(uint32_t)));
+    CU(cudaMalloc((void **)&d_nd, sizeof(unsigned long long)));
+    db->device_bytes = nb * 48 + E * 4 + (N + 1) * 8 + N * 8;
+    CU(cudaMemset(db->d_keys, 0xFF, nb * 32));
+    CU(cudaMemset(db->d_vals, 0xFF, nb * 16));
+    CU(cudaMemset(d_flags, 0xFF, sizeof(uint32_t)));      // [0] special = kNoEntry
+    CU(cudaMemset(d_flags + 1, 0, sizeof(uint32_t)));     // [1] fail
+    CU(cudaMemset(d_nd, 0, sizeof(unsigned long long)));
+    if (E) CU(cudaMemcpy(d_hashes, hashes, E * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->d_offsets, db->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
+    if (N) CU(cudaMemcpy(db->d_lengths, db->lengths.data(), N * 8, cudaMemcpyHostToDevice));
+    CU(launch_table_insert(db->d_keys, db->d_vals, db->n_buckets, d_hashes, E, d_flags, nullptr, d_flags + 1, 0));
+    uint32_t flags[2];
+    CU(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags[1]) return fail(HS_ECUDA, "hash table build failed (table full)");
+    db->special = flags[0];
+    if (db->special != kNoEntry) db->max_key = ~0ull;
+    CU(launch_table_canon(db->view(), d_hashes, E, db->d_canon, d_nd, 0));
+    unsigned long long nd = 0;
+    CU(cudaMemcpy(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost));
+    db->n_distinct = nd;
+    cudaFree(d_hashes); cudaFree(d_flags); cudaFree(d_nd);
+    db->t_build = now_s() - t0;
+    return HS_OK;
+}
+
+void fill_info(const hs_db *db, hs_db_info_t *o)
+{
+    memset(o, 0, sizeof *o);
+    o->k = db->k; o->s = db->s; o->seed = db->seed; o->use64 = db->use64;
+    o->n_refs = db->n_refs; o->n_entries = db->n_entries; o->n_distinct = db->n_distinct;
+    o->n_buckets = db->n_buckets; o->max_key = db->max_key; o->device_bytes = db->device_bytes;
+    o->t_parse_s = db->t_parse; o->t_build_s = db->t_build;
+}
+
+StreamArgs base_args(const Chunk &c, uint32_t k, uint32_t seed, bool use64)
+{
+    StreamArgs a;
+    memset(&a, 0, sizeof a);
+    a.seq = c.d_seq; a.inv = c.d_inv; a.n_bases = c.n_bases;
+    a.n_tiles = (uint32_t)tiles_for(c.n_bases);
+    a.k = (int)k; a.seed = seed; a.use64 = use64;
+    return a;
+}
+
+// launch the streaming kernel for one chunk (caller holds s->mu)
+int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix)
+{
+    if (!c.n_bases) return HS_OK;
+    if (tiles_for(c.n_bases) > 0xFFFFFFFFull) return fail(HS_EINVAL, "chunk too large");
+    if (mix) {
+        int rc = s->mix.check(s->stream);
+        if (rc) return rc;
+        s->mix.before_launch(c.n_bases);
+    }
+    StreamArgs a = base_args(c, s->db->k, s->db->seed, s->db->use64);
+    a.do_count = count; a.do_filter = s->filter; a.do_mix = mix;
+    a.tab = s->db->view(); a.counts = s->d_counts; a.mix = s->mix.view();
+    a.stats = count ? s->d_stats : s->d_stats + ST_COUNT;  // re-offer passes must not double count
+    if (s->ev_used == s->ev_pool.size()) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+        s->ev_pool.emplace_back(e0, e1);
+    }
+    auto &ev = s->ev_pool[s->ev_used++];
+    CU(cudaEventRecord(ev.first, s->stream));
+    CU(launch_stream(a, g_sm, s->stream));
+    CU(cudaEventRecord(ev.second, s->stream));
+    s->st.n_launches++;
+    s->st.n_positions += c.n_bases;
+    return HS_OK;
+}
+
+int screen_zero(hs_screen *s)
+{
+    CU(cudaMemsetAsync(s->d_counts, 0, std::max<uint64_t>(s->db->n_entries, 1) * 4, s->stream));
+    CU(cudaMemsetAsync(s->d_stats, 0, 2 * ST_COUNT * sizeof(unsigned long long), s->stream));
+    int rc = s->mix.reset(s->stream);
+    if (rc) return rc;
+    s->mix.passes = 1;
+    s->mixture.clear();
+    s->flushed = false;
+    s->chunks.clear();
+    s->arena.reset();
+    s->ev_used = 0;
+    memset(&s->st, 0, sizeof s->st);
+    return HS_OK;
+}
+
+// Settle the s smallest distinct hashes of everything streamed so far (K3).
+// rehash(tau) re-offers every resident chunk to a fresh set when the set lost
+// elements (overflow) or tau was lowered further than the data supports.
+template <class Rehash>
+int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint32_t &n_launches, Rehash &&rehash)
+{
+    for (int round = 0; round < 40; round++) {
+        int rc = m.check(st);
+        if (rc) return rc;
+        if (m.dirty) {  // overflow: too many distinct values below tau -> lower it and re-offer
+            const uint64_t nt = m.tau >> 4;
+            rc = m.reset(st, nt ? nt : 1);
+            if (rc) return rc;
+            m.passes++;
+            rc = rehash();
+            if (rc) return rc;
+            continue;
+        }
+        // distinct values <= tau (older, larger ones may linger from before tau dropped)
+        uint64_t thr = m.tau;
+        uint32_t M = 0;
+        for (int iter = 0; iter < 64; iter++) {
+            CU(cudaMemsetAsync(m.d_ctl + 3, 0, sizeof(uint32_t), st));
+            CU(launch_mix_collect(m.d_set[m.cur], m.cap, thr, m.d_cand, m.cand_cap, m.d_ctl + 3, st));
+            n_launches++;
+            CU(cudaMemcpyAsync(m.h_ctl, m.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            M = m.h_ctl[3];
+            if (M <= m.cand_cap && (M >= m.s || thr == m.tau)) break;
+            if (M > m.cand_cap) {
+                // aim for ~1.5 s candidates assuming hashes are uniform below thr
+                const long double f = ((long double)m.s * 1.5L + 64.0L) / (long double)M;
+                thr = (uint64_t)((long double)thr * (f < 0.9L ? f : 0.9L));
+            } else {
+                thr = (thr > m.tau / 2) ? m.tau : thr * 2;
+            }
+        }
+        if (M > m.cand_cap) return fail(HS_ECUDA, "mixture candidate selection did not converge");
+        if (M < m.s && m.tau != ~0ull) {
+            // complete below tau but fewer than s distinct values there (very repetitive
+            // input): raise tau and re-offer everything
+            const uint64_t nt = (m.tau > (~0ull >> 4)) ? ~0ull : (m.tau << 4);
+            rc = m.reset(st, nt);
+            if (rc) return rc;
+            m.passes++;
+            rc = rehash();
+            if (rc) return rc;
+            continue;
+        }
+        out.clear();
+        if (M) {
+            CU(launch_sort_unique(m.d_cand, M, m.d_scratch, m.d_ctl + 4, st));
+            n_launches++;
+            CU(cudaMemcpyAsync(m.h_ctl, m.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            const uint32_t nu = std::min(m.h_ctl[4], m.s);
+            out.resize(nu);
+            CU(cudaMemcpy(out.data(), m.d_cand, (size_t)nu * 8, cudaMemcpyDeviceToHost));
+        }
+        if (m.h_ctl[2] && out.size() < m.s) out.push_back(~0ull);  // hash == 2^64-1 present
+        return HS_OK;
+    }
+    return fail(HS_ECUDA, "mixture threshold search did not settle");
+}
+
+uint64_t set_size_of(const std::vector<uint64_t> &mix, bool use64)
+{   // S10: (uint64) (2^W * |M| / max(M)), W = 64 or 32, in double
+    if (mix.empty()) return 0;
+    const double est = pow(2.0, use64 ? 64.0 : 32.0) * (double)mix.size() / (double)mix.back();
+    if (!(est < 18446744073709551615.0)) return ~0ull;
+    return (uint64_t)est;
+}
+
+int collect_stream_ms(hs_screen *s)
+{
+    float total = 0;
+    for (size_t i = 0; i < s->ev_used; i++) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->ev_pool[i].first, s->ev_pool[i].second));
+        total += ms;
+    }
+    s->st.ms_stream = total;
+    return HS_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+// library
+// =============================================================================
+HS_API const char *hs_version(void) { return "hymet-screen-b200 0.1 (sm_100a)"; }
+HS_API const char *hs_last_error(void) { return g_err.c_str(); }
+HS_API int hs_sm_count(void) { return g_sm; }
+
+HS_API int hs_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(HS_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count is 0") +
+                                   " (this library has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(HS_EINVAL, "device ordinal out of range");
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(HS_ENODEV, std::string("device ") + p.name + " is sm_" + std::to_string(p.major) + std::to_string(p.minor) +
+                                   "; this build carries sm_100a code only");
+    CU(cudaSetDevice(device));
+    g_device = device;
+    g_sm = p.multiProcessorCount;
+    return HS_OK;
+}
+
+// =============================================================================
+// .msh on the host
+// =============================================================================
+HS_API int hs_msh_open(const char *path, hs_msh **out)
+{
+    if (!path || !out) return fail(HS_EINVAL, "null argument");
+    auto *m = new hs_msh();
+    std::string err;
+    int rc = msh_read(path, m->d, err);
+    if (rc) { delete m; return fail(rc, err); }
+    *out = m;
+    return HS_OK;
+}
+HS_API int hs_msh_info(const hs_msh *m, hs_db_info_t *info)
+{
+    if (!m || !info) return fail(HS_EINVAL, "null argument");
+    memset(info, 0, sizeof *info);
+    info->k = m->d.k; info->s = m->d.s; info->seed = m->d.seed; info->use64 = m->d.use64;
+    info->n_refs = m->d.offsets.size() - 1; info->n_entries = m->d.hashes.size();
+    info->t_parse_s = m->d.t_parse_s;
+    for (uint64_t h : m->d.hashes) info->max_key = std::max(info->max_key, h);
+    return HS_OK;
+}
+HS_API int hs_msh_ref(const hs_msh *m, uint64_t i, const char **name, const char **comment, uint64_t *length,
+                      uint64_t *n_hashes, const uint64_t **hashes)
+{
+    if (!m || i + 1 >= m->d.offsets.size()) return fail(HS_EINVAL, "reference index out of range");
+    if (name) *name = m->d.names[i].c_str();
+    if (comment) *comment = m->d.comments[i].c_str();
+    if (length) *length = m->d.lengths[i];
+    if (n_hashes) *n_hashes = m->d.offsets[i + 1] - m->d.offsets[i];
+    if (hashes) *hashes = m->d.hashes.data() + m->d.offsets[i];
+    return HS_OK;
+}
+HS_API void hs_msh_free(hs_msh *m) { delete m; }
+
+// =============================================================================
+// database on the GPU
+// =============================================================================
+HS_API int hs_db_from_msh(const hs_msh *m, hs_db **out)
+{
+    if (!m || !out) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    auto *db = new hs_db();
+    db->k = m->d.k; db->s = m->d.s; db->seed = m->d.seed; db->use64 = m->d.use64;
+    db->n_refs = m->d.offsets.size() - 1; db->n_entries = m->d.hashes.size();
+    db->names = m->d.names; db->comments = m->d.comments; db->lengths = m->d.lengths; db->offsets = m->d.offsets;
+    db->t_parse = m->d.t_parse_s;
+    int rc = db_build(db, m->d.hashes.data());
+    if (rc) { hs_db_free(db); return rc; }
+    *out = db;
+    return HS_OK;
+}
+
+HS_API int hs_db_load_msh(const char *path, hs_db **out)
+{
+    hs_msh *m = nullptr;
+    int rc = hs_msh_open(path, &m);
+    if (rc) return rc;
+    rc = hs_db_from_msh(m, out);
+    hs_msh_free(m);
+    return rc;
+}
+
+HS_API int hs_db_from_arrays(uint32_t k, uint32_t s, uint32_t seed, uint64_t n_refs, const uint64_t *offsets,
+                             const uint64_t *hashes, const uint64_t *lengths, hs_db **out)
+{
+    if (!offsets || !out || (!hashes && offsets[n_refs])) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    auto *db = new hs_db();
+    db->k = k; db->s = s; db->seed = seed;
+    db->use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
+    db->n_refs = n_refs; db->n_entries = offsets[n_refs];
+    db->offsets.assign(offsets, offsets + n_refs + 1);
+    if (lengths) db->lengths.assign(lengths, lengths + n_refs); else db->lengths.assign(n_refs, 0);
+    db->names.assign(n_refs, std::string()); db->comments.assign(n_refs, std::string());
+    int rc = db_build(db, hashes);
+    if (rc) { hs_db_free(db); return rc; }
+    *out = db;
+    return HS_OK;
+}
+
+HS_API int hs_db_info(const hs_db *db, hs_db_info_t *info)
+{
+    if (!db || !info) return fail(HS_EINVAL, "null argument");
+    fill_info(db, info);
+    return HS_OK;
+}
+HS_API int hs_db_ref(const hs_db *db, uint64_t i, const char **name, const char **comment, uint64_t *length,
+                     uint64_t *n_hashes)
+{
+    if (!db || i >= db->n_refs) return fail(HS_EINVAL, "reference index out of range");
+    if (name) *name = db->names[i].c_str();
+    if (comment) *comment = db->comments[i].c_str();
+    if (length) *length = db->lengths[i];
+    if (n_hashes) *n_hashes = db->offsets[i + 1] - db->offsets[i];
+    return HS_OK;
+}
+HS_API void hs_db_free(hs_db *db)
+{
+    if (!db) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    cudaFree(db->d_keys); cudaFree(db->d_vals); cudaFree(db->d_canon); cudaFree(db->d_offsets); cudaFree(db->d_lengths);
+    delete db;
+}
+
+// =============================================================================
+// screen
+// =============================================================================
+HS_API int hs_screen_new(hs_db *db, hs_screen **out)
+{
+    if (!db || !out) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    auto *s = new hs_screen();
+    s->db = db;
+    const uint64_t N = std::max<uint64_t>(db->n_refs, 1), E = std::max<uint64_t>(db->n_entries, 1);
+    auto bail = [&](int rc) { hs_screen_free(s); return rc; };
+#define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(HS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); return bail(HS_ECUDA); } } while (0)
+    CUB(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    CUB(cudaMalloc((void **)&s->d_counts, E * 4));
+    CUB(cudaMalloc((void **)&s->d_stats, 2 * ST_COUNT * sizeof(unsigned long long)));
+    CUB(cudaMalloc((void **)&s->d_shared, N * 4));
+    CUB(cudaMalloc((void **)&s->d_median, N * 4));
+    CUB(cudaMalloc((void **)&s->d_identity, N * 8));
+    CUB(cudaMalloc((void **)&s->d_pvalue, N * 8));
+    CUB(cudaEventCreate(&s->red0));
+    CUB(cudaEventCreate(&s->red1));
+#undef CUB
+    int rc = s->mix.init(db->s);
+    if (rc) return bail(rc);
+    rc = screen_zero(s);
+    if (rc) return bail(rc);
+    *out = s;
+    return HS_OK;
+}
+
+HS_API int hs_screen_set_stream(hs_screen *s, void *cuda_stream)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    NEED_DEVICE();
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+    if (cuda_stream) {
+        s->stream = (cudaStream_t)cuda_stream;
+    } else {
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        s->own_stream = true;
+    }
+    return HS_OK;
+}
+
+HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
+{
+    if (!s || !key) return fail(HS_EINVAL, "null argument");
+    if (!strcmp(key, "filter")) s->filter = value != 0;
+    else if (!strcmp(key, "chunk_bases")) s->chunk_text = value > 4096 ? (uint64_t)value : 4096;
+    else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
+    else return fail(HS_EINVAL, std::string("unknown option ") + key);
+    return HS_OK;
+}
+
+HS_API uint64_t hs_packed_words(uint64_t n_bases) { return tiles_for(n_bases) * kTileWords; }
+
+HS_API int hs_pack_text(const char *text, size_t n, uint64_t *seq2, uint32_t *inv, uint64_t cap_words,
+                        uint64_t *n_bases, hs_stats_t *stats)
+{
+    if ((!text && n) || !seq2 || !inv || !n_bases) return fail(HS_EINVAL, "null argument");
+    if (cap_words < pack_words_bound(n)) return fail(HS_EINVAL, "capacity below hs pack bound (n/32 + 4 words)");
+    PackStats ps;
+    pack_text_span(text, n, seq2, inv, &ps);
+    *n_bases = ps.n_positions;
+    if (stats) { memset(stats, 0, sizeof *stats); stats->n_bases = ps.n_seq_bases; stats->n_records = ps.n_records; stats->n_positions = ps.n_positions; }
+    return HS_OK;
+}
+
+namespace {
+
+// copy a packed host chunk into the arena (padding flagged invalid) and launch
+int feed_host_chunk(hs_screen *s, const uint64_t *seq, const uint32_t *inv, uint64_t n_bases, cudaEvent_t done_ev)
+{
+    if (!n_bases) return HS_OK;
+    const uint64_t words = (n_bases + 31) / 32, alloc = hs_packed_words(n_bases);
+    void *dseq = nullptr, *dinv = nullptr;
+    CU(s->arena.alloc(alloc * 8, &dseq));
+    CU(s->arena.alloc(alloc * 4, &dinv));
+    CU(cudaMemcpyAsync(dseq, seq, words * 8, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaMemcpyAsync(dinv, inv, words * 4, cudaMemcpyHostToDevice, s->stream));
+    if (alloc > words) {
+        CU(cudaMemsetAsync((char *)dseq + words * 8, 0, (alloc - words) * 8, s->stream));
+        CU(cudaMemsetAsync((char *)dinv + words * 4, 0xFF, (alloc - words) * 4, s->stream));
+    }
+    if (done_ev) CU(cudaEventRecord(done_ev, s->stream));
+    s->st.h2d_bytes += words * 12;
+    Chunk c{(const uint64_t *)dseq, (const uint32_t *)dinv, n_bases};
+    s->chunks.push_back(c);
+    return launch_chunk(s, c, true, true);
+}
+
+int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
+{
+    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    const int parts = (int)std::min<uint64_t>(1u << 20, n / s->chunk_text + 1);
+    auto spans = split_records(text, n, parts, 1 << 16);
+    if ((int)spans.size() < threads) threads = (int)spans.size();
+    if (threads < 1) return HS_OK;
+    // two staging buffers per packer thread (pinned), reused through events
+    const size_t need = (size_t)threads * 2;
+    while (s->staging.size() < need) {
+        Staging g;
+        CU(cudaEventCreateWithFlags(&g.free_ev, cudaEventDisableTiming));
+        s->staging.push_back(g);
+    }
+    std::atomic<size_t> next{0};
+    std::atomic<int> rc_all{HS_OK};
+    std::string err_all;
+    std::mutex err_mu;
+    auto worker = [&](int t) {
+        cudaSetDevice(g_device);
+        int flip = 0;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= spans.size() || rc_all.load() != HS_OK) break;
+            Staging &g = s->staging[(size_t)t * 2 + (flip ^= 1)];
+            const size_t len = spans[i].second - spans[i].first;
+            const uint64_t bound = pack_words_bound(len);
+            int rc = HS_OK;
+            if (g.cap_words < bound) {
+                if (g.seq) { cudaEventSynchronize(g.free_ev); cudaFreeHost(g.seq); cudaFreeHost(g.inv); g.seq = nullptr; g.inv = nullptr; }
+                g.cap_words = bound + bound / 8;
+                if (cudaHostAlloc((void **)&g.seq, g.cap_words * 8, cudaHostAllocDefault) != cudaSuccess ||
+                    cudaHostAlloc((void **)&g.inv, g.cap_words * 4, cudaHostAllocDefault) != cudaSuccess) {
+                    g.cap_words = 0;
+                    rc = fail(HS_ENOMEM, "pinned staging allocation failed");
+                }
+            } else {
+                cudaEventSynchronize(g.free_ev);  // previous H2D from this buffer has finished
+            }
+            PackStats ps;
+            if (rc == HS_OK) {
+                pack_text_span(text + spans[i].first, len, g.seq, g.inv, &ps);
+                std::lock_guard<std::mutex> lk(s->mu);
+                s->st.n_bases += ps.n_seq_bases;
+                s->st.n_records += ps.n_records;
+                rc = feed_host_chunk(s, g.seq, g.inv, ps.n_positions, g.free_ev);
+            }
+            if (rc != HS_OK) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (rc_all.load() == HS_OK) { rc_all = rc; err_all = g_err; }
+                break;
+            }
+        }
+    };
+    if (threads == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+        for (auto &th : pool) th.join();
+    }
+    if (rc_all != HS_OK) return fail(rc_all, err_all);
+    return HS_OK;
+}
+
+}  // namespace
+
+HS_API int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads)
+{
+    if (!s || (!text && n)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    return feed_text_impl(s, text, n, host_threads);
+}
+
+HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads)
+{
+    if (!s || !path) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    std::vector<char> buf;
+    std::string err;
+    if (!slurp_file(path, buf, err)) return fail(HS_EIO, err);
+    return feed_text_impl(s, buf.data(), buf.size(), host_threads);
+}
+
+HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases)
+{
+    if (!s || ((!seq2 || !inv) && n_bases)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->st.n_bases += n_bases;
+    return feed_host_chunk(s, seq2, inv, n_bases, nullptr);
+}
+
+HS_API int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const void *d_inv, uint64_t n_bases)
+{
+    if (!s || ((!d_seq2 || !d_inv) && n_bases)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (((uintptr_t)d_seq2 & 15) || ((uintptr_t)d_inv & 15)) return fail(HS_EINVAL, "packed device buffers must be 16-byte aligned");
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->st.n_bases += n_bases;
+    Chunk c{(const uint64_t *)d_seq2, (const uint32_t *)d_inv, n_bases};
+    s->chunks.push_back(c);
+    return launch_chunk(s, c, true, true);
+}
+
+HS_API int hs_screen_flush(hs_screen *s)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    NEED_DEVICE();
+    if (s->flushed) return HS_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaEventRecord(s->red0, s->stream));
+    int rc = mix_finalize(s->mix, s->stream, s->mixture, s->st.n_launches, [&]() -> int {
+        for (const Chunk &c : s->chunks) {
+            int r = launch_chunk(s, c, false, true);
+            if (r) return r;
+            s->st.n_positions -= c.n_bases;  // a mixture-only second pass is not new input
+        }
+        return HS_OK;
+    });
+    if (rc) return rc;
+    CU(cudaEventRecord(s->red1, s->stream));
+    unsigned long long h[ST_COUNT];
+    CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->st.n_valid_kmers = h[ST_VALID]; s->st.n_probes = h[ST_PROBES]; s->st.n_bucket_reads = h[ST_BUCKETS];
+    s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
+    s->st.n_mix_passes = s->mix.passes;
+    s->st.n_mixture = s->mixture.size();
+    s->st.set_size = set_size_of(s->mixture, s->db->use64);
+    rc = collect_stream_ms(s);
+    if (rc) return rc;
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
+    s->st.ms_reduce = ms;
+    s->flushed = true;
+    return HS_OK;
+}
+
+HS_API int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n)
+{
+    if (!s || !d_counts || !n) return fail(HS_EINVAL, "null argument");
+    *d_counts = s->d_counts;
+    *n = s->db->n_entries;
+    return HS_OK;
+}
+
+HS_API int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes, uint32_t *n)
+{
+    if (!s || !n) return fail(HS_EINVAL, "null argument");
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    *n = (uint32_t)s->mixture.size();
+    if (hashes) memcpy(hashes, s->mixture.data(), s->mixture.size() * 8);
+    return HS_OK;
+}
+
+HS_API int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n)
+{
+    if (!s || (!hashes && n)) return fail(HS_EINVAL, "null argument");
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    // union of per-rank bottom-s sets, keep the s smallest (<= G*s values: control-plane work)
+    s->mixture.insert(s->mixture.end(), hashes, hashes + n);
+    std::sort(s->mixture.begin(), s->mixture.end());
+    s->mixture.erase(std::unique(s->mixture.begin(), s->mixture.end()), s->mixture.end());
+    if (s->mixture.size() > s->db->s) s->mixture.resize(s->db->s);
+    s->st.n_mixture = s->mixture.size();
+    s->st.set_size = set_size_of(s->mixture, s->db->use64);
+    return HS_OK;
+}
+
+HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *median, double *identity,
+                            double *pvalue, hs_stats_t *stats)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    NEED_DEVICE();
+    int rc = hs_screen_flush(s);
+    if (rc) return rc;
+    hs_db *db = s->db;
+    const uint64_t N = db->n_refs, E = db->n_entries;
+    CU(cudaEventRecord(s->red0, s->stream));
+    CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
+    s->st.n_launches++;
+    if (wta && E) {
+        if (!s->d_winner) {
+            CU(cudaMalloc((void **)&s->d_best_score, E * 8));
+            CU(cudaMalloc((void **)&s->d_best_len, E * 8));
+            CU(cudaMalloc((void **)&s->d_winner, E * 4));
+        }
+        CU(launch_winner(db->d_offsets, N, db->d_canon, s->d_counts, s->d_shared, db->d_lengths, s->d_best_score,
+                         s->d_best_len, s->d_winner, E, g_sm, s->stream));
+        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, s->d_winner, s->d_shared, s->d_median, g_sm,
+                                s->stream));
+        s->st.n_launches += 4;
+    }
+    CU(launch_stats(db->k, s->st.set_size, N, s->d_shared, nullptr, db->d_offsets, nullptr, s->d_identity, s->d_pvalue,
+                    s->stream));
+    s->st.n_launches++;
+    CU(cudaEventRecord(s->red1, s->stream));
+    std::vector<uint32_t> sh(N);
+    if (N) {
+        CU(cudaMemcpyAsync(sh.data(), s->d_shared, N * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (median) CU(cudaMemcpyAsync(median, s->d_median, N * 4, cudaMemcpyDeviceToHost, s->stream));
+        if (identity) CU(cudaMemcpyAsync(identity, s->d_identity, N * 8, cudaMemcpyDeviceToHost, s->stream));
+        if (pvalue) CU(cudaMemcpyAsync(pvalue, s->d_pvalue, N * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    if (shared) for (uint64_t i = 0; i < N; i++) shared[i] = sh[i];
+    s->st.d2h_bytes += N * (4 + (median ? 4 : 0) + (identity ? 8 : 0) + (pvalue ? 8 : 0));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
+    s->st.ms_reduce += ms;
+    if (stats) *stats = s->st;
+    return HS_OK;
+}
+
+HS_API int hs_screen_reset(hs_screen *s)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    NEED_DEVICE();
+    CU(cudaStreamSynchronize(s->stream));
+    return screen_zero(s);
+}
+
+HS_API int hs_screen_stats(hs_screen *s, hs_stats_t *stats)
+{
+    if (!s || !stats) return fail(HS_EINVAL, "null argument");
+    *stats = s->st;
+    return HS_OK;
+}
+
+HS_API void hs_screen_free(hs_screen *s)
+{
+    if (!s) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_counts); cudaFree(s->d_stats); cudaFree(s->d_shared); cudaFree(s->d_median);
+    cudaFree(s->d_identity); cudaFree(s->d_pvalue); cudaFree(s->d_best_score); cudaFree(s->d_best_len); cudaFree(s->d_winner);
+    s->mix.destroy();
+    s->arena.release();
+    for (auto &g : s->staging) {
+        if (g.seq) cudaFreeHost(g.seq);
+        if (g.inv) cudaFreeHost(g.inv);
+        if (g.free_ev) cudaEventDestroy(g.free_ev);
+    }
+    for (auto &e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (s->red0) cudaEventDestroy(s->red0);
+    if (s->red1) cudaEventDestroy(s->red1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+// =============================================================================
+// single stages
+// =============================================================================
+HS_API int hs_hash_packed(uint32_t k, uint32_t seed, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases,
+                          uint64_t *out_hash, uint8_t *out_valid)
+{
+    if (!seq2 || !inv || !out_hash || !out_valid) return fail(HS_EINVAL, "null argument");
+    if (k == 0 || k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
+    NEED_DEVICE();
+    if (!n_bases) return HS_OK;
+    const uint64_t words = (n_bases + 31) / 32, alloc = hs_packed_words(n_bases);
+    uint64_t *dseq = nullptr, *dh = nullptr;
+    uint32_t *dinv = nullptr;
+    uint8_t *dv = nullptr;
+    unsigned long long *dst = nullptr;
+    CU(cudaMalloc((void **)&dseq, alloc * 8));
+    CU(cudaMalloc((void **)&dinv, alloc * 4));
+    CU(cudaMalloc((void **)&dh, n_bases * 8));
+    CU(cudaMalloc((void **)&dv, n_bases));
+    CU(cudaMalloc((void **)&dst, ST_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemset(dseq, 0, alloc * 8));
+    CU(cudaMemset(dinv, 0xFF, alloc * 4));
+    CU(cudaMemset(dh, 0, n_bases * 8));
+    CU(cudaMemset(dv, 0, n_bases));
+    CU(cudaMemset(dst, 0, ST_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemcpy(dseq, seq2, words * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dinv, inv, words * 4, cudaMemcpyHostToDevice));
+    Chunk c{dseq, dinv, n_bases};
+    StreamArgs a = base_args(c, k, seed, pow(4.0, (double)k) > pow(2.0, 32.0));
+    a.emit_hash = dh; a.emit_valid = dv; a.stats = dst;
+    CU(launch_stream(a, g_sm, 0));
+    CU(cudaMemcpy(out_hash, dh, n_bases * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_valid, dv, n_bases, cudaMemcpyDeviceToHost));
+    cudaFree(dseq); cudaFree(dinv); cudaFree(dh); cudaFree(dv); cudaFree(dst);
+    return HS_OK;
+}
+
+HS_API int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *out_entry)
+{
+    if (!db || (!hashes && n) || (!out_entry && n)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!n) return HS_OK;
+    uint64_t *dh = nullptr;
+    uint32_t *de = nullptr;
+    unsigned long long *dst = nullptr;
+    CU(cudaMalloc((void **)&dh, n * 8));
+    CU(cudaMalloc((void **)&de, n * 4));
+    CU(cudaMalloc((void **)&dst, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(dst, 0, 2 * sizeof(unsigned long long)));
+    CU(cudaMemcpy(dh, hashes, n * 8, cudaMemcpyHostToDevice));
+    CU(launch_probe(db->view(), dh, n, de, dst, g_sm, 0));
+    CU(cudaMemcpy(out_entry, de, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dh); cudaFree(de); cudaFree(dst);
+    return HS_OK;
+}
+
+HS_API int hs_db_probe_device(hs_db *db, const void *d_hashes, uint64_t n, uint64_t *n_hits, uint64_t *n_bucket_reads,
+                              float *ms)
+{
+    if (!db || (!d_hashes && n)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    unsigned long long *dst = nullptr, h[2] = {0, 0};
+    cudaEvent_t e0, e1;
+    CU(cudaMalloc((void **)&dst, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(dst, 0, 2 * sizeof(unsigned long long)));
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, 0));
+    CU(launch_probe(db->view(), (const uint64_t *)d_hashes, n, nullptr, dst, g_sm, 0));
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, e0, e1));
+    CU(cudaMemcpy(h, dst, sizeof h, cudaMemcpyDeviceToHost));
+    if (n_hits) *n_hits = h[0];
+    if (n_bucket_reads) *n_bucket_reads = h[1];
+    if (ms) *ms = t;
+    cudaFree(dst); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return HS_OK;
+}
+
+HS_API int hs_db_entry_ids(hs_db *db, uint32_t *out)
+{
+    if (!db || !out) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (db->n_entries) CU(cudaMemcpy(out, db->d_canon, db->n_entries * 4, cudaMemcpyDeviceToHost));
+    return HS_OK;
+}
+
+HS_API int hs_stat_batch(uint32_t k, uint64_t set_size, uint64_t n, const uint64_t *shared, const uint64_t *size,
+                         double *identity, double *pvalue)
+{
+    if ((!shared || !size || !identity || !pvalue) && n) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!n) return HS_OK;
+    uint64_t *dx = nullptr, *dn = nullptr;
+    double *di = nullptr, *dp = nullptr;
+    CU(cudaMalloc((void **)&dx, n * 8)); CU(cudaMalloc((void **)&dn, n * 8));
+    CU(cudaMalloc((void **)&di, n * 8)); CU(cudaMalloc((void **)&dp, n * 8));
+    CU(cudaMemcpy(dx, shared, n * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dn, size, n * 8, cudaMemcpyHostToDevice));
+    CU(launch_stats(k, set_size, n, nullptr, dx, nullptr, dn, di, dp, 0));
+    CU(cudaMemcpy(identity, di, n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pvalue, dp, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dn); cudaFree(di); cudaFree(dp);
+    return HS_OK;
+}
+
+HS_API int hs_sketch_text(uint32_t k, uint32_t s_, uint32_t seed, const char *text, size_t n, uint64_t *out_hashes,
+                          uint32_t *n_out, uint64_t *length)
+{
+    if ((!text && n) || !out_hashes || !n_out) return fail(HS_EINVAL, "null argument");
+    if (k == 0 || k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
+    NEED_DEVICE();
+    std::vector<uint64_t> seq(pack_words_bound(n));
+    std::vector<uint32_t> inv(pack_words_bound(n));
+    PackStats ps;
+    pack_text_span(text, n, seq.data(), inv.data(), &ps);
+    if (length) *length = ps.n_seq_bases;
+    *n_out = 0;
+    if (!ps.n_positions) return HS_OK;
+    const uint64_t words = (ps.n_positions + 31) / 32, alloc = hs_packed_words(ps.n_positions);
+    uint64_t *dseq = nullptr;
+    uint32_t *dinv = nullptr;
+    unsigned long long *dst = nullptr;
+    CU(cudaMalloc((void **)&dseq, alloc * 8));
+    CU(cudaMalloc((void **)&dinv, alloc * 4));
+    CU(cudaMalloc((void **)&dst, ST_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemset(dseq, 0, alloc * 8));
+    CU(cudaMemset(dinv, 0xFF, alloc * 4));
+    CU(cudaMemset(dst, 0, ST_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemcpy(dseq, seq.data(), words * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dinv, inv.data(), words * 4, cudaMemcpyHostToDevice));
+    MixEngine mix;
+    int rc = mix.init(s_);
+    if (rc) return rc;
+    rc = mix.reset(0);
+    Chunk c{dseq, dinv, ps.n_positions};
+    const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
+    auto offer = [&]() -> int {
+        mix.before_launch(c.n_bases);
+        StreamArgs a = base_args(c, k, seed, use64);
+        a.do_mix = 1; a.mix = mix.view(); a.stats = dst;
+        CU(launch_stream(a, g_sm, 0));
+        return HS_OK;
+    };
+    std::vector<uint64_t> out;
+    uint32_t launches = 0;
+    if (rc == HS_OK) rc = offer();
+    if (rc == HS_OK) rc = mix_finalize(mix, 0, out, launches, offer);
+    mix.destroy();
+    cudaFree(dseq); cudaFree(dinv); cudaFree(dst);
+    if (rc) return rc;
+    *n_out = (uint32_t)out.size();
+    memcpy(out_hashes, out.data(), out.size() * 8);
+    return HS_OK;
+}

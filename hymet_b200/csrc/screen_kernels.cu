@@ -1,0 +1,668 @@
+// screen_kernels.cu -- hand-written sm_100a kernels for the `mash screen` hot path.
+//
+// Path replaced: the streaming loop of `mash screen` (hashSequence + getHash +
+// MinHashHeap::tryInsert + hashCounts[key]++), its "Summing shared" / "-w" /
+// median / identity / p-value stages, and the hash-table build, i.e. SURVEY.md 8a
+// rows a5, a7-a15, for the invocation at /root/reference/scripts/mash.sh:14.
+//
+//   k_stream        K1+K2(+K3 insert): rolling canonical k-mer -> MurmurHash3 ->
+//                   range pre-filter -> 32-byte bucket probe -> warp-aggregated count.
+//                   Persistent CTAs; packed tiles arrive through the TMA engine
+//                   (1-D cp.async.bulk + mbarrier, double buffered).
+//   k_table_insert / k_table_canon   GPU build of the key table (row a5)
+//   k_probe         K2 alone (parity + HBM roofline of the random probes)
+//   k_mix_*         K3: mixture bottom-s set maintenance
+//   k_sort_unique   K3: final ordering of the <= few-thousand candidates
+//   k_sketch_reduce K4: shared count + median multiplicity per sketch
+//   k_winner        K5: -w reassignment
+//   k_stats         K6: identity + binomial upper tail
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kmer_core.cuh"
+#include "screen_kernels.h"
+
+namespace hs {
+
+// ---------------------------------------------------------------------------
+// PTX: mbarrier + bulk async copy global -> shared (TMA engine; SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    uint32_t ok;
+    const long long t0 = clock64();
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+        // a tile that never lands means a broken launch contract: fail loudly, never hang the GPU
+        if (!ok && clock64() - t0 > 4000000000ll) __trap();
+    } while (!ok);
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// table lookup (shared by k_stream, k_table_canon, k_probe)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t table_find(const TableView &t, uint64_t h, uint32_t &n_reads)
+{
+    if (h == kEmptyKey) return t.special;
+    uint32_t b = bucket_of(h, t.n_buckets);
+    for (uint32_t tries = 0; tries < t.n_buckets; tries++) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)b * kBucketSlots);
+        const ulonglong2 k01 = __ldg(p), k23 = __ldg(p + 1);  // one 32-byte sector
+        n_reads++;
+        if (k01.x == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 0);
+        if (k01.y == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 1);
+        if (k23.x == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 2);
+        if (k23.y == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 3);
+        if (k01.x == kEmptyKey || k01.y == kEmptyKey || k23.x == kEmptyKey || k23.y == kEmptyKey) return kNoEntry;
+        b = (b + 1 == t.n_buckets) ? 0u : b + 1;
+    }
+    return kNoEntry;
+}
+
+__device__ __forceinline__ void mix_insert(const MixView &m, uint64_t h)
+{
+    if (h == kEmptyKey) { atomicExch(m.has_max, 1u); return; }
+    uint32_t slot = mixset_slot(h, m.mask);
+    for (uint32_t tries = 0; tries <= m.mask; tries++) {
+        unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(m.set + slot));
+        if (cur == h) return;
+        if (cur == kEmptyKey) {
+            if (__ldcg(m.count) >= m.limit) { atomicExch(m.overflow, 1u); return; }
+            cur = atomicCAS(reinterpret_cast<unsigned long long *>(m.set + slot), (unsigned long long)kEmptyKey,
+                            (unsigned long long)h);
+            if (cur == kEmptyKey) { atomicAdd(m.count, 1u); return; }
+            if (cur == h) return;
+        }
+        slot = (slot + 1) & m.mask;
+    }
+    atomicExch(m.overflow, 1u);
+}
+
+// ---------------------------------------------------------------------------
+// K1 + K2 (+ K3 insert): the streaming kernel
+// ---------------------------------------------------------------------------
+struct __align__(16) TileBuf {
+    uint64_t seq[kTileWords + 2];  // [1] = halo word, [2..] = the tile
+    uint32_t inv[kTileWords + 4];  // [3] = halo word, [4..] = the tile
+};
+static_assert(sizeof(TileBuf) % 16 == 0, "tile buffers must keep 16-byte alignment");
+
+// 256 x 4-base ASCII expansions, replicated per bank (entry b of lane l at [b*32+l])
+// so that 32 lanes with 32 different indices never conflict.
+struct SmemLut {
+    const uint32_t *lane_base;
+    __device__ __forceinline__ uint32_t operator()(uint32_t b) const { return lane_base[b * 32]; }
+};
+
+template <int KT>
+__global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
+{
+    __shared__ TileBuf buf[2];
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ uint32_t lut[256 * 32];
+
+    const int k = KT ? KT : a.k;
+    const bool use64 = KT ? (KT > 16) : (a.use64 != 0);
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = ascii4(i >> 5);
+    __syncthreads();
+    const SmemLut L{lut + lane};
+
+    auto issue = [&](uint32_t tile, uint32_t b) {
+        // tile 0 has no halo (positions before the chunk do not exist)
+        const uint32_t sw = tile ? 2u : 0u, iw = tile ? 4u : 0u;
+        const uint32_t sbytes = (kTileWords + sw) * 8u, ibytes = (kTileWords + iw) * 4u;
+        mbar_expect_tx(&bar[b], sbytes + ibytes);
+        bulk_g2s(&buf[b].seq[2 - sw], a.seq + (size_t)tile * kTileWords - sw, sbytes, &bar[b]);
+        bulk_g2s(&buf[b].inv[4 - iw], a.inv + (size_t)tile * kTileWords - iw, ibytes, &bar[b]);
+    };
+
+    uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
+    uint32_t tile = blockIdx.x, it = 0;
+    if (tid == 0 && tile < a.n_tiles) issue(tile, 0);
+
+    for (; tile < a.n_tiles; tile += gridDim.x, it++) {
+        const uint32_t b = it & 1u, phase = (it >> 1) & 1u;
+        const uint32_t next = tile + gridDim.x;
+        if (tid == 0 && next < a.n_tiles) issue(next, b ^ 1u);
+        mbar_wait(&bar[b], phase);
+        uint64_t cur = buf[b].seq[tid + 2], prev = buf[b].seq[tid + 1];
+        uint32_t icur = buf[b].inv[tid + 4], iprev = buf[b].inv[tid + 3];
+        __syncthreads();  // every thread holds its words: buf[b] may be refilled
+
+        if (tile == 0 && tid == 0) { prev = 0; iprev = ~0u; }
+        const uint64_t pos0 = ((uint64_t)tile * kTileWords + tid) * kBasesPerWord;
+        if (pos0 + kBasesPerWord > a.n_bases) {
+            const uint32_t nv = pos0 >= a.n_bases ? 0u : (uint32_t)(a.n_bases - pos0);
+            icur |= nv ? ((1u << (32 - nv)) - 1u) : ~0u;
+        }
+        if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
+
+        for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, [&](int j, uint64_t h) {
+            n_valid++;
+            if (a.emit_hash) {
+                a.emit_hash[pos0 + j] = h;
+                a.emit_valid[pos0 + j] = 1;
+            }
+            if (a.do_mix && h <= a.mix.tau) {
+                n_mix++;
+                mix_insert(a.mix, h);
+            }
+            if (a.do_count && (!a.do_filter || h <= a.tab.max_key)) {
+                n_probe++;
+                const uint32_t id = table_find(a.tab, h, n_reads);
+                if (id != kNoEntry) {
+                    // warp-aggregated count: lanes that hit the same key add once
+                    const uint32_t peers = __match_any_sync(__activemask(), id);
+                    if ((uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(a.counts + id, (uint32_t)__popc(peers));
+                    n_hits++;
+                }
+            }
+        });
+    }
+
+    n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);
+    n_hits = warp_sum(n_hits); n_mix = warp_sum(n_mix);
+    if (lane == 0) {
+        if (n_valid) atomicAdd(a.stats + ST_VALID, (unsigned long long)n_valid);
+        if (n_probe) atomicAdd(a.stats + ST_PROBES, (unsigned long long)n_probe);
+        if (n_reads) atomicAdd(a.stats + ST_BUCKETS, (unsigned long long)n_reads);
+        if (n_hits) atomicAdd(a.stats + ST_HITS, (unsigned long long)n_hits);
+        if (n_mix) atomicAdd(a.stats + ST_MIXINS, (unsigned long long)n_mix);
+    }
+}
+
+template <int KT>
+static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream_t st)
+{
+    static int occ = 0;
+    if (!occ) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT>, kCtaThreads, 0);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+    }
+    uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (!grid) return cudaSuccess;
+    k_stream<KT><<<grid, kCtaThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st)
+{
+    switch (a.k) {
+    case 21: return launch_stream_t<21>(a, sm_count, st);
+    case 31: return launch_stream_t<31>(a, sm_count, st);
+    case 16: return launch_stream_t<16>(a, sm_count, st);
+    default: return launch_stream_t<0>(a, sm_count, st);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Table build (row a5) and standalone probe (K2)
+// ---------------------------------------------------------------------------
+__global__ void k_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
+                               uint64_t n, uint32_t *special, uint32_t *fail)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = hashes[e];
+        if (h == kEmptyKey) { atomicMin(special, (uint32_t)e); continue; }
+        uint32_t b = bucket_of(h, n_buckets);
+        bool done = false;
+        for (uint32_t tries = 0; tries < n_buckets && !done; tries++) {
+#pragma unroll
+            for (int s = 0; s < kBucketSlots && !done; s++) {
+                const size_t slot = (size_t)b * kBucketSlots + s;
+                unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(keys + slot));
+                if (cur == kEmptyKey) {
+                    cur = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot), (unsigned long long)kEmptyKey,
+                                    (unsigned long long)h);
+                    if (cur == kEmptyKey) cur = h;
+                }
+                if (cur == h) {
+                    // canonical id of a key = smallest entry index holding it: identical on
+                    // every GPU whatever the insertion order, so counts[] all-reduce cleanly
+                    atomicMin(vals + slot, (uint32_t)e);
+                    done = true;
+                }
+            }
+            b = (b + 1 == n_buckets) ? 0u : b + 1;
+        }
+        if (!done) atomicExch(fail, 1u);
+    }
+}
+
+__global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_t n, uint32_t *canon,
+                              unsigned long long *n_distinct)
+{
+    uint32_t local = 0, dummy = 0;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = table_find(t, hashes[e], dummy);
+        canon[e] = id;
+        local += id == (uint32_t)e;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_distinct, (unsigned long long)local);
+}
+
+__global__ void __launch_bounds__(256) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
+                                               uint32_t *out_entry, unsigned long long *stats)
+{
+    uint32_t hits = 0, reads = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t id = table_find(t, __ldg(hashes + i), reads);
+        if (out_entry) out_entry[i] = id;
+        hits += id != kNoEntry;
+    }
+    hits = warp_sum(hits); reads = warp_sum(reads);
+    if ((threadIdx.x & 31) == 0) {
+        if (hits) atomicAdd(stats + 0, (unsigned long long)hits);
+        if (reads) atomicAdd(stats + 1, (unsigned long long)reads);
+    }
+}
+
+static inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap)
+{
+    uint64_t g = (n + threads - 1) / threads;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (uint32_t)g;
+}
+
+cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
+                                uint64_t n_entries, uint32_t *special, unsigned long long *, uint32_t *fail,
+                                cudaStream_t st)
+{
+    if (!n_entries) return cudaSuccess;
+    k_table_insert<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(keys, vals, n_buckets, hashes, n_entries,
+                                                                      special, fail);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint64_t n_entries, uint32_t *canon,
+                               unsigned long long *n_distinct, cudaStream_t st)
+{
+    if (!n_entries) return cudaSuccess;
+    k_table_canon<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(t, hashes, n_entries, canon, n_distinct);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n, uint32_t *out_entry,
+                         unsigned long long *stats, int sm_count, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    k_probe<<<grid_for(n, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K3: mixture bottom-s set
+// ---------------------------------------------------------------------------
+__global__ void k_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
+                              uint32_t *n_out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const uint64_t v = set[i];
+        if (v != kEmptyKey && v <= thr) {
+            const uint32_t p = atomicAdd(n_out, 1u);
+            if (p < out_cap) out[p] = v;
+        }
+    }
+}
+
+__global__ void k_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count)
+{
+    const uint32_t mask = cap - 1;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        const uint64_t v = src[i];
+        if (v == kEmptyKey || v > thr) continue;
+        uint32_t slot = mixset_slot(v, mask);
+        for (;;) {
+            const unsigned long long cur = atomicCAS(reinterpret_cast<unsigned long long *>(dst + slot),
+                                                     (unsigned long long)kEmptyKey, (unsigned long long)v);
+            if (cur == kEmptyKey) { atomicAdd(count, 1u); break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
+                               uint32_t *n_out, cudaStream_t st)
+{
+    k_mix_collect<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(set, cap, thr, out, out_cap, n_out);
+    return cudaGetLastError();
+}
+cudaError_t launch_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count,
+                               cudaStream_t st)
+{
+    k_mix_rebuild<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(src, cap, thr, dst, count);
+    return cudaGetLastError();
+}
+
+// Single-CTA bitonic sort + unique.  work = shared memory (n_pad <= kSortSmemMax) or a
+// global scratch buffer.  Padding value kEmptyKey sorts last and is never a real key.
+constexpr uint32_t kSortSmemMax = 8192;
+
+__device__ void bitonic_sort_block(uint64_t *w, uint32_t n_pad)
+{
+    for (uint32_t kk = 2; kk <= n_pad; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const uint64_t x = w[i], y = w[p];
+                    const bool up = (i & kk) == 0;
+                    if ((x > y) == up) { w[i] = y; w[p] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_sort_unique(uint64_t *data, uint32_t n, uint32_t n_pad, uint64_t *scratch,
+                                                      uint32_t *n_unique)
+{
+    extern __shared__ uint64_t sm[];
+    __shared__ uint32_t warp_tot[32];
+    uint64_t *w = scratch ? scratch : sm;
+    for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) w[i] = i < n ? data[i] : kEmptyKey;
+    __syncthreads();
+    bitonic_sort_block(w, n_pad);
+    // unique: each thread owns a contiguous run of the sorted array
+    const uint32_t per = (n_pad + blockDim.x - 1) / blockDim.x;
+    const uint32_t beg = threadIdx.x * per, end = min(beg + per, n_pad);
+    uint32_t cnt = 0;
+    for (uint32_t i = beg; i < end; i++) cnt += (w[i] != kEmptyKey) && (i == 0 || w[i] != w[i - 1]);
+    // exclusive scan of cnt over the block
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t v = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0u, s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += t;
+        }
+        warp_tot[lane] = s - v;  // exclusive
+        if (lane == 31) *n_unique = s;
+    }
+    __syncthreads();
+    uint32_t pos = warp_tot[wid] + inc - cnt;
+    for (uint32_t i = beg; i < end; i++)
+        if ((w[i] != kEmptyKey) && (i == 0 || w[i] != w[i - 1])) data[pos++] = w[i];
+}
+
+cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st)
+{
+    uint32_t n_pad = 2;
+    while (n_pad < n) n_pad <<= 1;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_sort_unique, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(kSortSmemMax * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const bool in_smem = n_pad <= kSortSmemMax;
+    k_sort_unique<<<1, 1024, in_smem ? n_pad * sizeof(uint64_t) : 0, st>>>(data, n, n_pad, in_smem ? nullptr : scratch,
+                                                                          n_unique);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K4: per-sketch shared count + median multiplicity (rows a11, a13)
+// ---------------------------------------------------------------------------
+constexpr int kReduceThreads = 128;
+constexpr uint32_t kReduceCache = 10240;  // counts of one sketch kept in shared memory (40 KB)
+
+__device__ __forceinline__ uint32_t block_sum128(uint32_t v, uint32_t *red)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(kReduceThreads) k_sketch_reduce(const uint64_t *offsets, uint64_t n_refs,
+                                                                  const uint32_t *canon, const uint32_t *counts,
+                                                                  const uint32_t *winner, uint32_t *shared_out,
+                                                                  uint32_t *median_out)
+{
+    __shared__ uint32_t cache[kReduceCache];
+    __shared__ uint32_t red[4], redmax[4];
+    for (uint64_t i = blockIdx.x; i < n_refs; i += gridDim.x) {
+        const uint64_t beg = offsets[i], end = offsets[i + 1];
+        const bool cached = end - beg <= kReduceCache;
+        auto value = [&](uint64_t e) -> uint32_t {
+            const uint32_t id = canon[e];
+            uint32_t c = counts[id];
+            if (winner && c && winner[id] != (uint32_t)i) c = 0;
+            return c;
+        };
+        uint32_t cnt = 0, mx = 0;
+        for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
+            const uint32_t c = value(e);
+            if (cached) cache[e - beg] = c;
+            cnt += c != 0;
+            mx = max(mx, c);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0) redmax[threadIdx.x >> 5] = mx;
+        const uint32_t S = block_sum128(cnt, red);  // barriers inside also publish cache[] and redmax[]
+        if (S == 0) {
+            if (threadIdx.x == 0) { shared_out[i] = 0; median_out[i] = 0; }
+            __syncthreads();
+            continue;
+        }
+        mx = max(max(redmax[0], redmax[1]), max(redmax[2], redmax[3]));
+        // S12: sorted_depths[S/2] by MSB-first radix selection over the non-zero counts
+        uint32_t kk = S / 2, prefix = 0;
+        for (int bit = 31 - __clz(mx); bit >= 0; bit--) {
+            const uint32_t himask = ~((2u << bit) - 1u);
+            uint32_t z = 0;
+            for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
+                const uint32_t c = cached ? cache[e - beg] : value(e);
+                z += (c != 0) && ((c & himask) == prefix) && !((c >> bit) & 1u);
+            }
+            z = block_sum128(z, red);
+            if (kk >= z) { kk -= z; prefix |= 1u << bit; }
+        }
+        if (threadIdx.x == 0) { shared_out[i] = S; median_out[i] = prefix; }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_sketch_reduce(const uint64_t *offsets, uint64_t n_refs, const uint32_t *canon,
+                                 const uint32_t *counts, const uint32_t *winner, uint32_t *shared, uint32_t *median,
+                                 int sm_count, cudaStream_t st)
+{
+    if (!n_refs) return cudaSuccess;
+    const uint32_t grid = (uint32_t)((n_refs < (uint64_t)sm_count * 16) ? n_refs : (uint64_t)sm_count * 16);
+    k_sketch_reduce<<<grid, kReduceThreads, 0, st>>>(offsets, n_refs, canon, counts, winner, shared, median);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K5: winner-take-all (row a12, rule S17).  Three max-reductions per present key:
+// best score, then longest genome among those, then highest sketch index.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kReduceThreads) k_winner(const uint64_t *offsets, uint64_t n_refs,
+                                                           const uint32_t *canon, const uint32_t *counts,
+                                                           const uint32_t *shared, const uint64_t *lengths,
+                                                           unsigned long long *best_score,
+                                                           unsigned long long *best_len, uint32_t *winner, int pass)
+{
+    for (uint64_t i = blockIdx.x; i < n_refs; i += gridDim.x) {
+        const uint64_t beg = offsets[i], end = offsets[i + 1];
+        const uint32_t sh = shared[i];
+        if (!sh) continue;  // no present key can belong to a sketch without hits
+        const uint64_t size = end - beg;
+        // score order == identity order (S13): identity is monotone in shared/size
+        const double jac = sh == size ? 1.0 : (double)sh / (double)size;
+        const unsigned long long sbits = (unsigned long long)__double_as_longlong(jac);
+        const unsigned long long len = lengths[i];
+        for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
+            const uint32_t id = canon[e];
+            if (!counts[id]) continue;
+            if (pass == 0) {
+                atomicMax(best_score + id, sbits);
+            } else if (pass == 1) {
+                if (best_score[id] == sbits) atomicMax(best_len + id, len);
+            } else {
+                if (best_score[id] == sbits && best_len[id] == len) atomicMax(winner + id, (uint32_t)i);
+            }
+        }
+    }
+}
+
+cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32_t *canon, const uint32_t *counts,
+                          const uint32_t *shared, const uint64_t *lengths, unsigned long long *best_score,
+                          unsigned long long *best_len, uint32_t *winner, uint64_t n_entries, int sm_count,
+                          cudaStream_t st)
+{
+    if (!n_refs) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(best_score, 0, n_entries * 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(best_len, 0, n_entries * 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(winner, 0, n_entries * 4, st)) != cudaSuccess) return e;
+    const uint32_t grid = (uint32_t)((n_refs < (uint64_t)sm_count * 16) ? n_refs : (uint64_t)sm_count * 16);
+    for (int pass = 0; pass < 3; pass++) {
+        k_winner<<<grid, kReduceThreads, 0, st>>>(offsets, n_refs, canon, counts, shared, lengths, best_score,
+                                                  best_len, winner, pass);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------
+// K6: identity (S13) and p-value (S14) in double precision
+// ---------------------------------------------------------------------------
+// P[Binomial(n, r) >= x], summed term by term from the term at x.  The leading term
+// C(n,x) r^x (1-r)^(n-x) is built as a running product with an explicit binary
+// exponent, so nothing large is ever exponentiated: relative error ~ sqrt(x) ulp.
+__device__ double binom_upper_tail(uint64_t x, uint64_t n, double r)
+{
+    if (x == 0) return 1.0;
+    if (x > n) return 0.0;
+    if (!(r > 0.0)) return 0.0;
+    if (r >= 1.0) return 1.0;
+    const double q = 1.0 - r;
+    const bool upper = (double)x > (double)n * r;  // sum the smaller side
+    const uint64_t j0 = upper ? x : x - 1;         // first term of the side we sum
+    // t(j0) = prod_{i=1..j0} ((n-j0+i)/i * r) * q^(n-j0)
+    double mant = 1.0;
+    long long ex = 0;
+    for (uint64_t i = 1; i <= j0; i++) {
+        mant *= ((double)(n - j0 + i) / (double)i) * r;
+        if (mant < 1e-250 || mant > 1e250) {
+            int e2;
+            mant = frexp(mant, &e2);
+            ex += e2;
+        }
+    }
+    {
+        const double e2 = (double)(n - j0) * log2(q);
+        const double fl = floor(e2);
+        mant *= exp2(e2 - fl);
+        ex += (long long)fl;
+    }
+    // geometric-like continuation
+    double sum = 1.0, term = 1.0;
+    if (upper) {
+        const double rq = r / q;
+        for (uint64_t j = j0; j < n; j++) {
+            term *= ((double)(n - j) / (double)(j + 1)) * rq;
+            sum += term;
+            if (term < sum * 1e-18) break;
+        }
+    } else {
+        const double qr = q / r;
+        for (uint64_t j = j0; j > 0; j--) {
+            term *= ((double)j / (double)(n - j + 1)) * qr;
+            sum += term;
+            if (term < sum * 1e-18) break;
+        }
+    }
+    int e2;
+    mant = frexp(mant * sum, &e2);
+    ex += e2;
+    const double side = ex < -1100 ? 0.0 : ldexp(mant, (int)ex);
+    return upper ? side : 1.0 - side;
+}
+
+__global__ void k_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
+                        const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes, double *identity,
+                        double *pvalue)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t x = shared32 ? (uint64_t)shared32[i] : shared64[i];
+    const uint64_t size = offsets ? offsets[i + 1] - offsets[i] : sizes[i];
+    double id;
+    if (x == size) id = 1.0;
+    else if (x == 0) id = 0.0;
+    else id = pow((double)x / (double)size, 1.0 / (double)k);
+    identity[i] = id;
+    const double kmer_space = ldexp(1.0, 2 * (int)k);  // 4^k
+    const double r = 1.0 / (1.0 + kmer_space / (double)set_size);
+    pvalue[i] = binom_upper_tail(x, size, r);
+}
+
+cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
+                         const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes,
+                         double *identity, double *pvalue, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    k_stats<<<(uint32_t)((n + 127) / 128), 128, 0, st>>>(k, set_size, n, shared32, shared64, offsets, sizes, identity,
+                                                        pvalue);
+    return cudaGetLastError();
+}
+
+}  // namespace hs

@@ -1,0 +1,88 @@
+// screen_kernels.h -- launch interface of the hand-written sm_100a kernels.
+// Internal to libhymet_screen.so (the public surface is include/hymet_screen.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hs {
+
+constexpr int kTileWords = 256;    // one CTA pass = 256 words = 8192 bases
+constexpr int kCtaThreads = 256;
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
+
+// counters accumulated by the streaming kernel (device, 64-bit each)
+enum StatSlot { ST_VALID = 0, ST_PROBES, ST_BUCKETS, ST_HITS, ST_MIXINS, ST_COUNT };
+
+struct TableView {
+    const uint64_t *keys;   // n_buckets * 4, kEmptyKey = free
+    const uint32_t *vals;   // n_buckets * 4, canonical entry id of the key
+    uint32_t n_buckets;
+    uint64_t max_key;       // largest stored key (range pre-filter)
+    uint32_t special;       // canonical entry id of key == kEmptyKey, or kNoEntry
+};
+
+struct MixView {
+    uint64_t *set;          // open addressing, capacity mask+1, kEmptyKey = free
+    uint32_t mask;
+    uint32_t limit;         // max distinct before `overflow` is raised
+    uint64_t tau;           // accept h <= tau
+    uint32_t *count;        // distinct inserted
+    uint32_t *overflow;
+    uint32_t *has_max;      // key == kEmptyKey seen (only possible when tau == max)
+};
+
+struct StreamArgs {
+    const uint64_t *seq;    // packed words (16-byte aligned), n_tiles * kTileWords allocated
+    const uint32_t *inv;
+    uint64_t n_bases;       // positions >= n_bases are invalid whatever inv says
+    uint32_t n_tiles;
+    int k;
+    uint32_t seed;
+    int use64;
+    int do_count;           // probe + count
+    int do_filter;          // skip probes for h > max_key
+    int do_mix;             // offer hashes <= tau to the mixture set
+    TableView tab;
+    uint32_t *counts;       // per canonical entry id
+    MixView mix;
+    unsigned long long *stats;  // ST_COUNT slots
+    uint64_t *emit_hash;    // optional: per position hash (K1 parity), n_bases entries
+    uint8_t *emit_valid;
+};
+
+// ---- streaming (K1+K2+K3 insert) -------------------------------------------
+cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st);
+
+// ---- database build (row a5) -------------------------------------------------
+cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
+                                uint64_t n_entries, uint32_t *special, unsigned long long *max_key,
+                                uint32_t *fail, cudaStream_t st);
+cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint64_t n_entries, uint32_t *canon,
+                               unsigned long long *n_distinct, cudaStream_t st);
+// standalone probe (K2): out_entry may be NULL; stats[0]=hits, stats[1]=bucket reads
+cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n, uint32_t *out_entry,
+                         unsigned long long *stats, int sm_count, cudaStream_t st);
+
+// ---- mixture bottom-s (K3) ---------------------------------------------------
+// copy keys <= thr from the set into out (append with atomic cursor); counts all <= thr
+cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
+                               uint32_t *n_out, cudaStream_t st);
+// rebuild: insert every key <= thr of `src` into (empty) `dst`
+cudaError_t launch_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count,
+                               cudaStream_t st);
+// sort ascending + unique in place (n <= cap_pow2 handled by padding); *n_unique out
+cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st);
+
+// ---- per-sketch reduction (K4), winner-take-all (K5), statistics (K6) ---------
+cudaError_t launch_sketch_reduce(const uint64_t *offsets, uint64_t n_refs, const uint32_t *canon,
+                                 const uint32_t *counts, const uint32_t *winner /*nullable*/, uint32_t *shared,
+                                 uint32_t *median, int sm_count, cudaStream_t st);
+cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32_t *canon, const uint32_t *counts,
+                          const uint32_t *shared, const uint64_t *lengths, unsigned long long *best_score,
+                          unsigned long long *best_len, uint32_t *winner, uint64_t n_entries, int sm_count,
+                          cudaStream_t st);
+cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
+                         const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes,
+                         double *identity, double *pvalue, cudaStream_t st);
+
+}  // namespace hs

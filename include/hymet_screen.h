@@ -1,0 +1,175 @@
+/*
+ * hymet_screen.h -- C ABI of libhymet_screen.so: the B200-native `mash screen`.
+ *
+ * What it replaces.  HYMET's candidate selection calls an external process,
+ *     mash screen -p 8 -v 0.9 "$MASH_SCREEN" "$INPUT_DIR"/ *.fna > "$SCREEN_TAB"
+ * (/root/reference/scripts/mash.sh:14; three times per run from
+ * /root/reference/run_hymet_cami.sh:85-96 and main.pl:94-104).  The reference
+ * has no FFI for this path -- the process boundary is the interface -- so the
+ * drop-in has two layers:
+ *   1. bin/mash (Python) keeps the CLI and the TSV byte-for-byte, and
+ *   2. this header is what that shim binds with ctypes.  Each entry point is
+ *      annotated with the step of `mash screen` it stands for (SURVEY.md 8a
+ *      rows a4..a16; Mash's own source is third-party and not under
+ *      /root/reference, so rows cite the survey's restated rules S1..S22).
+ *
+ * Conventions: plain C, no C++/torch types; every function returns HS_OK (0) or
+ * a negative HS_E* code and leaves a message for hs_last_error() (thread local).
+ * The caller allocates every output array.  There is no CPU fallback: without an
+ * sm_100 device hs_init() fails and every device entry point returns HS_ENODEV.
+ * One hs_screen is one query stream; handles are not re-entrant.
+ */
+#ifndef HYMET_SCREEN_H
+#define HYMET_SCREEN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_OK 0
+#define HS_EINVAL (-1)       /* bad argument */
+#define HS_ENODEV (-2)       /* no sm_100 (B200) device / hs_init not called */
+#define HS_ECUDA (-3)        /* CUDA runtime error (message has the detail) */
+#define HS_EIO (-4)          /* could not open / read an input */
+#define HS_EFORMAT (-5)      /* malformed .msh */
+#define HS_ENOMEM (-6)
+#define HS_EUNSUPPORTED (-7) /* S22: protein / noncanonical / preserveCase sketches, k > 32 */
+#define HS_ENOSEQ (-8)       /* S6: "Did not find sequence records in inputs" */
+#define HS_ESTATE (-9)       /* call order violated */
+
+typedef struct hs_msh hs_msh;       /* a parsed .msh on the host */
+typedef struct hs_db hs_db;         /* a sketch database resident on one GPU */
+typedef struct hs_screen hs_screen; /* one screen (query stream) against a db */
+
+typedef struct {
+    uint32_t k, s, seed, use64;   /* from the sketch file, never from the CLI (Appendix A) */
+    uint64_t n_refs, n_entries;   /* N sketches, E stored hashes */
+    uint64_t n_distinct;          /* D distinct hashes (device dbs only, else 0) */
+    uint64_t n_buckets;           /* hash-table buckets of 4 keys (device dbs only) */
+    uint64_t max_key;             /* largest stored hash: exact range pre-filter */
+    uint64_t device_bytes;        /* HBM held by the db */
+    double t_parse_s, t_build_s;  /* .msh parse / GPU table build, seconds */
+} hs_db_info_t;
+
+typedef struct {
+    uint64_t n_bases;        /* characters inside sequence records ("query bases", the Mbp of Mbp/s) */
+    uint64_t n_records;
+    uint64_t n_positions;    /* packed positions streamed (bases + record separators + padding) */
+    uint64_t n_valid_kmers;  /* K: k-mers hashed (S4) */
+    uint64_t n_probes;       /* P: table probes issued (<= K when the range pre-filter is on) */
+    uint64_t n_bucket_reads; /* 32-byte bucket sectors read by those probes */
+    uint64_t n_hits;         /* H: probes that found a key (count updates) */
+    uint64_t n_mix_inserts;  /* hashes offered to the mixture bottom-s set */
+    uint64_t set_size;       /* S10, printed by mash as "Estimated distinct k-mers in mixture" */
+    uint64_t n_mixture;      /* |M| <= s (S9) */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t n_launches;     /* kernels launched for this screen so far */
+    uint32_t n_mix_passes;   /* hashing passes needed for the mixture set (1 unless re-thresholded) */
+    float ms_stream;         /* device time of the k-mer/probe kernels (CUDA events) */
+    float ms_reduce;         /* device time of mixture finalise + per-sketch reduction */
+} hs_stats_t;
+
+/* ---- library ------------------------------------------------------------ */
+const char *hs_version(void);
+const char *hs_last_error(void);
+/* Bind this thread/process to CUDA device `device` (ordinal).  Fails with HS_ENODEV
+ * unless the device is compute capability 10.x. */
+int hs_init(int device);
+/* Number of SMs of the bound device (148 on B200); 0 before hs_init. */
+int hs_sm_count(void);
+
+/* ---- .msh on the host (row a4: Sketch::initFromFiles) --------------------- */
+int hs_msh_open(const char *path, hs_msh **out);
+int hs_msh_info(const hs_msh *m, hs_db_info_t *info);
+/* name/comment stay owned by the hs_msh; hashes -> pointer to n_hashes ascending
+ * 64-bit values (32-bit sketches are widened). length = S18. */
+int hs_msh_ref(const hs_msh *m, uint64_t i, const char **name, const char **comment, uint64_t *length,
+               uint64_t *n_hashes, const uint64_t **hashes);
+void hs_msh_free(hs_msh *m);
+
+/* ---- database on the GPU (row a5: the "Loading..." hash-table build) ------- */
+int hs_db_from_msh(const hs_msh *m, hs_db **out);
+int hs_db_load_msh(const char *path, hs_db **out); /* open + from_msh */
+/* Build from flat host arrays: offsets[n_refs+1], hashes[offsets[n_refs]] ascending per
+ * reference, lengths[n_refs] (may be NULL -> 0).  Names are empty. */
+int hs_db_from_arrays(uint32_t k, uint32_t s, uint32_t seed, uint64_t n_refs, const uint64_t *offsets,
+                      const uint64_t *hashes, const uint64_t *lengths, hs_db **out);
+int hs_db_info(const hs_db *db, hs_db_info_t *info);
+int hs_db_ref(const hs_db *db, uint64_t i, const char **name, const char **comment, uint64_t *length,
+              uint64_t *n_hashes);
+void hs_db_free(hs_db *db);
+
+/* ---- one screen ---------------------------------------------------------- */
+int hs_screen_new(hs_db *db, hs_screen **out);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = library's own). */
+int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
+/* Options: "filter" 1/0 = skip probes for hashes above the db's largest key (exact;
+ * default 1); "keep_query" 1/0 = keep packed chunks in HBM until finish (default 1,
+ * needed if the mixture threshold must be revisited); "chunk_bases" = host packer
+ * chunk size. */
+int hs_screen_set_option(hs_screen *s, const char *key, int64_t value);
+
+/* rows a6/a7: stream FASTA/FASTQ (plain or gzip; "-" = stdin).  The host packs into
+ * pinned 2-bit buffers with `host_threads` threads while the GPU consumes. */
+int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads);
+/* Same, text already in host memory. */
+int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads);
+/* Pre-packed HOST buffers (layout: hs_packed_words()).  n_bases positions. */
+int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases);
+/* Pre-packed DEVICE buffers, used in place (must stay alive until finish; allocation
+ * must hold hs_packed_words(n_bases) words of each array). */
+int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const void *d_inv, uint64_t n_bases);
+/* Words each packed array must hold for n_bases positions (tile padding included). */
+uint64_t hs_packed_words(uint64_t n_bases);
+/* Host packer alone (no GPU): text -> seq2/inv with capacity cap_words each; returns
+ * positions in *n_bases.  stats may be NULL. */
+int hs_pack_text(const char *text, size_t n, uint64_t *seq2, uint32_t *inv, uint64_t cap_words,
+                 uint64_t *n_bases, hs_stats_t *stats);
+
+/* rows a8-a10 complete: wait for the stream, settle the local mixture bottom-s. */
+int hs_screen_flush(hs_screen *s);
+
+/* Multi-GPU seam: after flush, counts[] (uint32, one per stored hash
+ * entry id; device pointer) may be summed across ranks in place, and every rank's local
+ * mixture hashes merged into every other rank, before finish. */
+int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n);
+int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);
+int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n);
+
+/* rows a11-a15: shared, median multiplicity, identity, p-value for every sketch, in
+ * sketch order.  winner_take_all = mash's -w (S17).  Arrays have n_refs elements. */
+int hs_screen_finish(hs_screen *s, int winner_take_all, uint64_t *shared, uint32_t *median,
+                     double *identity, double *pvalue, hs_stats_t *stats);
+/* Forget the query (counts, mixture, stats) so the handle can screen another one. */
+int hs_screen_reset(hs_screen *s);
+int hs_screen_stats(hs_screen *s, hs_stats_t *stats);
+void hs_screen_free(hs_screen *s);
+
+/* ---- single stages, for parity tests and per-kernel measurement ------------ */
+/* K1 alone (row a7/a8): hash every k-mer of a packed host buffer.  out_hash/out_valid
+ * have n_bases elements, indexed by the position of the k-mer's LAST base. */
+int hs_hash_packed(uint32_t k, uint32_t seed, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases,
+                   uint64_t *out_hash, uint8_t *out_valid);
+/* K2 alone (row a10): probe n host hashes; out_entry[i] = canonical entry id of the
+ * key (index into the db's flat hash array of its first occurrence) or 0xFFFFFFFF. */
+int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *out_entry);
+/* K2 alone on DEVICE hashes, timed: increments nothing, returns hits and device ms. */
+int hs_db_probe_device(hs_db *db, const void *d_hashes, uint64_t n, uint64_t *n_hits,
+                       uint64_t *n_bucket_reads, float *ms);
+/* canonical entry id of every stored entry (n_entries values). */
+int hs_db_entry_ids(hs_db *db, uint32_t *out);
+/* K6 alone (rows a14/a15). */
+int hs_stat_batch(uint32_t k, uint64_t set_size, uint64_t n, const uint64_t *shared, const uint64_t *size,
+                  double *identity, double *pvalue);
+/* `mash sketch` of one genome held as FASTA text: s smallest distinct hashes
+ * (reuses K1 + the mixture bottom-s machinery). */
+int hs_sketch_text(uint32_t k, uint32_t s, uint32_t seed, const char *text, size_t n, uint64_t *out_hashes,
+                   uint32_t *n_out, uint64_t *length);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYMET_SCREEN_H */

@@ -209,11 +209,11 @@ static int parse_text(seqset_t *ss, const char *t, uint64_t n)
             while (j < n && t[j] != '\n') j++;
             uint64_t L = j - i;
             if (ss_reserve(ss, L)) return -1;
-            for (uint64_t q = 0; q < L; q++) {
-                char c = t[i + q];
-                if (c == '\r' || c == ' ' || c == '\t') continue;
-                ss->seq[ss->nseq++] = c;
-            }
+            /* kseq semantics: keep every byte of the line (blanks included: they are
+             * simply non-alphabet characters), drop only one trailing '\r' */
+            if (L && t[i + L - 1] == '\r') L--;
+            memcpy(ss->seq + ss->nseq, t + i, L);
+            ss->nseq += L;
             i = j + 1;
         }
         const uint64_t len = ss->nseq - off;

@@ -83,13 +83,15 @@ def kmer_hashes(seq: str, k: int, seed: int = 42) -> List[Tuple[int, int]]:
 
 def parse_fasta(text: str) -> List[Tuple[str, str]]:
     recs, name, buf = [], None, []
-    for line in text.splitlines():
+    for line in text.split("\n"):
+        if line.endswith("\r"):
+            line = line[:-1]
         if line.startswith(">"):
             if name is not None:
                 recs.append((name, "".join(buf)))
             name, buf = line[1:], []
         elif name is not None:
-            buf.append(line.strip())
+            buf.append(line)  # kseq keeps every byte of a sequence line
     if name is not None:
         recs.append((name, "".join(buf)))
     return recs

@@ -1,0 +1,372 @@
+"""CUDA path vs the CPU oracle, through the C ABI (needs a B200: `pytest -m gpu`).
+
+Bit-exact: k-mer hashes, table membership, per-hash counts, shared counts, median
+multiplicities, winner-take-all assignment, mixture bottom-s, set size.
+Floating point: identity and p-value within 1e-12 relative (north_star).
+"""
+import json
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from hymet_b200 import msh as mshfmt
+from hymet_b200 import screen as hs
+from hymet_b200 import synth
+from hymet_b200.tsv import screen_lines
+from oracle import py_micro_oracle as po
+from tests import _oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RTOL = 1e-12  # north_star tolerance for identity / p-value
+
+
+def rel_close(a, b, rtol=RTOL):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return np.all(np.abs(a - b) <= rtol * np.abs(b))
+
+
+def build_db(genomes, k, s, seed=42):
+    """Sketch genomes with the ORACLE (checker side) -> flat arrays."""
+    hs_list, lens = [], []
+    for g in genomes:
+        h, ln = orc.sketch_text(synth.to_fasta([g], "g"), k, s, seed)
+        hs_list.append(h); lens.append(ln)
+    offsets = np.concatenate([[0], np.cumsum([len(h) for h in hs_list])]).astype(np.uint64)
+    hashes = np.concatenate(hs_list) if hs_list else np.zeros(0, np.uint64)
+    return offsets, hashes, np.array(lens, np.uint64)
+
+
+def compare_screen(db_gpu, db_orc, fasta: bytes, wta: bool, threads=2, feed="text", probe_filter=True):
+    scr = hs.Screen(db_gpu, probe_filter=probe_filter)
+    if feed == "text":
+        scr.feed_text(fasta, threads)
+    else:
+        seq, inv, n, _ = hs.pack_text(fasta)
+        scr.feed_packed(seq, inv, n)
+    res = scr.finish(wta)
+    want = db_orc.screen_text(fasta, threads=2, wta=wta)
+    assert res.shared.tolist() == want.shared.tolist()
+    assert res.median.tolist() == want.median.tolist()
+    assert res.set_size == want.set_size
+    assert scr.mixture().tolist() == want.mixture.tolist()
+    assert res.stats["n_valid_kmers"] == want.n_kmers
+    assert rel_close(res.identity, want.identity)
+    assert rel_close(res.pvalue, want.pvalue)
+    scr.close()
+    return res, want
+
+
+# ---------------------------------------------------------------- K1 ----------
+@pytest.mark.parametrize("k", [7, 15, 16, 17, 21, 27, 31, 32])
+def test_k1_hashes_every_kmer(k):
+    rng = random.Random(k)
+    text = ""
+    for r in range(9):
+        L = rng.choice([0, 5, k - 1, k, k + 1, 300, 8191, 8193, 20000])
+        s = "".join(rng.choice("ACGTacgtNRY") if rng.random() < 0.01 else rng.choice("ACGT") for _ in range(L))
+        text += ">r%d\n%s\n" % (r, s)
+    seq, inv, n, st = hs.pack_text(text.encode())
+    h, v = hs.hash_packed(k, 42, seq, inv, n)
+    # oracle: per record, window start i <-> packed position of last base
+    pos = 0
+    want_h = np.zeros(n, np.uint64); want_v = np.zeros(n, bool)
+    for _, s in po.parse_fasta(text):
+        pos += 1  # separator
+        oh, ov = orc.hash_sequence(s.encode(), k)
+        for i in np.nonzero(ov)[0]:
+            want_h[pos + i + k - 1] = oh[i]; want_v[pos + i + k - 1] = True
+        pos += len(s)
+    assert pos == n
+    assert np.array_equal(v, want_v)
+    assert np.array_equal(h[v], want_h[want_v])
+
+
+def test_k1_golden_murmur_vectors(golden_dir):
+    # every ACGT-only golden string of length <= 32 hashed as a (forward-canonical or not) k-mer
+    for vec in json.load(open(os.path.join(golden_dir, "murmur_kat.json"))):
+        data = bytes.fromhex(vec["hex"])
+        if vec["seed"] != 42 or not (1 <= len(data) <= 32) or any(c not in b"ACGT" for c in data):
+            continue
+        k = len(data)
+        rc = data.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+        if data > rc:
+            continue  # the k-mer hashed by mash is the canonical one
+        seq, inv, n, _ = hs.pack_text(b">x\n" + data + b"\n")
+        h, v = hs.hash_packed(k, 42, seq, inv, n)
+        assert v.sum() == 1
+        want = int(vec["h1"], 16)
+        assert int(h[v][0]) == (want if k > 16 else want & 0xFFFFFFFF)
+
+
+def test_k1_empty_and_padding():
+    seq, inv, n, _ = hs.pack_text(b"")
+    assert n == 0
+    seq, inv, n, _ = hs.pack_text(b">a\n" + b"N" * 100 + b"\n")
+    h, v = hs.hash_packed(21, 42, seq, inv, n)
+    assert not v.any()
+
+
+# ---------------------------------------------------------------- K2 ----------
+def test_k2_probe_membership_and_canonical_ids():
+    rng = np.random.default_rng(5)
+    n_refs, s = 300, 200
+    pool = rng.integers(0, 2 ** 62, size=20000, dtype=np.uint64)
+    pool[0] = 0; pool[1] = np.uint64(2 ** 64 - 1); pool[2] = np.uint64(2 ** 64 - 2)
+    sk = [np.unique(rng.choice(pool, size=s, replace=False)) for _ in range(n_refs)]
+    sk[0] = np.unique(np.concatenate([sk[0], pool[:3]]))
+    offsets = np.concatenate([[0], np.cumsum([len(x) for x in sk])]).astype(np.uint64)
+    hashes = np.concatenate(sk)
+    db = hs.Database.from_arrays(21, s, 42, offsets, hashes, np.ones(n_refs, np.uint64))
+    first = {}
+    for e, h in enumerate(hashes.tolist()):
+        first.setdefault(h, e)
+    assert db.n_distinct == len(first)
+    assert db.entry_ids().tolist() == [first[h] for h in hashes.tolist()]
+    q = np.concatenate([pool, rng.integers(0, 2 ** 64, size=50000, dtype=np.uint64)])
+    got = db.probe(q)
+    want = np.array([first.get(h, 0xFFFFFFFF) for h in q.tolist()], np.uint32)
+    assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- K6 ----------
+def test_k6_identity_pvalue_golden(golden_dir):
+    vecs = json.load(open(os.path.join(golden_dir, "pvalue_kat.json")))
+    for key in sorted({(v["k"], v["set_size"]) for v in vecs}):
+        grp = [v for v in vecs if (v["k"], v["set_size"]) == key]
+        ident, pv = hs.stat_batch(key[0], key[1], [v["x"] for v in grp], [v["n"] for v in grp])
+        for v, i_, p_ in zip(grp, ident, pv):
+            want_p, want_i = float(v["p"]), float(v["identity"])
+            assert abs(i_ - want_i) <= RTOL * want_i, v
+            if want_p < 1e-300:
+                assert p_ == pytest.approx(want_p, rel=1e-6, abs=1e-320), v
+            else:
+                assert abs(p_ - want_p) <= RTOL * want_p, (v, p_)
+
+
+def test_k6_matches_oracle_dense_grid():
+    rng = np.random.default_rng(11)
+    for k, ss in [(21, 10 ** 9), (21, 3 * 10 ** 6), (31, 10 ** 10), (16, 10 ** 6), (11, 5 * 10 ** 5)]:
+        n = rng.choice([1000, 1000, 5000, 10000, 437], size=400).astype(np.uint64)
+        x = (rng.random(400) ** 2 * n).astype(np.uint64)
+        x[:20] = 0; x[20:40] = n[20:40]
+        ident, pv = hs.stat_batch(k, ss, x, n)
+        L = orc.lib()
+        for i in range(400):
+            wi = L.orc_identity(int(x[i]), int(n[i]), k)
+            wp = L.orc_pvalue(int(x[i]), ss, 4.0 ** k, int(n[i]))
+            assert abs(ident[i] - wi) <= RTOL * wi
+            if wp < 1e-300:
+                assert pv[i] < 1e-299
+            else:
+                assert abs(pv[i] - wp) <= RTOL * wp, (k, ss, int(x[i]), int(n[i]), pv[i], wp)
+
+
+# ------------------------------------------------------- mixture / sketch -------
+@pytest.mark.parametrize("k,s", [(21, 1000), (16, 500), (31, 64)])
+def test_gpu_sketch_equals_oracle_sketch(k, s):
+    rng = np.random.default_rng(k)
+    g = synth.random_genome(rng, 300_000, n_frac=0.001)
+    fa = synth.to_fasta([g[:120_000], g[120_000:]], "chr")
+    got, ln = hs.sketch_text(fa, k, s)
+    want, wln = orc.sketch_text(fa, k, s)
+    assert ln == wln == 300_000
+    assert got.tolist() == want.tolist()
+
+
+def test_mixture_fewer_than_s_and_repetitive():
+    # S9: fewer than s distinct k-mers -> all of them; heavy duplication -> re-thresholding path
+    unit = synth.random_genome(np.random.default_rng(1), 700)
+    fa = synth.to_fasta([unit] * 3, "dup")
+    got, _ = hs.sketch_text(fa, 21, 1000)
+    want, _ = orc.sketch_text(fa, 21, 1000)
+    assert len(want) == 680 and got.tolist() == want.tolist()
+    big = synth.to_fasta([np.tile(synth.random_genome(np.random.default_rng(2), 5000), 400)], "rep", width=0)
+    got, _ = hs.sketch_text(big, 21, 1000)   # 2 Mbp but only ~5000 distinct k-mers
+    want, _ = orc.sketch_text(big, 21, 1000)
+    assert got.tolist() == want.tolist()
+
+
+# ---------------------------------------------------------------- full screen ---
+def golden_db(g):
+    hsl = [np.array([int(h) for h in r["hashes"]], np.uint64) for r in g["db"]]
+    offsets = np.concatenate([[0], np.cumsum([len(h) for h in hsl])]).astype(np.uint64)
+    return offsets, np.concatenate(hsl), np.array([r["length"] for r in g["db"]], np.uint64)
+
+
+@pytest.mark.parametrize("mode", ["plain", "wta"])
+def test_screen_small_golden(golden_dir, mode):
+    g = json.load(open(os.path.join(golden_dir, "screen_small.json")))
+    offsets, hashes, lengths = golden_db(g)
+    db = hs.Database.from_arrays(g["k"], g["s"], g["seed"], offsets, hashes, lengths)
+    scr = hs.Screen(db)
+    scr.feed_text(g["fasta"].encode(), 1)
+    res = scr.finish(mode == "wta")
+    want = g["results"][mode]
+    assert res.shared.tolist() == want["shared"]
+    assert res.median.tolist() == want["median"]
+    assert res.set_size == want["set_size"]
+    assert [str(int(h)) for h in scr.mixture()] == want["mixture"]
+    assert rel_close(res.identity, want["identity"])
+    assert rel_close(res.pvalue, want["pvalue"])
+
+
+@pytest.fixture(scope="module")
+def c1_case():
+    """Config 1 shape, scaled to seconds of oracle time: 200 genomes x 50 kb, k=21 s=1000,
+    2 Mbp of contigs cut from 20 of them at m in {0, 0.01, 0.05}."""
+    rng = np.random.default_rng(1)
+    genomes = [synth.random_genome(rng, 50_000, n_frac=0.001) for _ in range(200)]
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    contigs = []
+    for m in (0.0, 0.01, 0.05):
+        contigs += synth.cut_contigs(rng, genomes[:20], 700_000, m, median=6000.0)
+    fasta = synth.to_fasta(contigs, "contig", lower_frac=0.05, rng=rng)
+    return offsets, hashes, lengths, fasta
+
+
+@pytest.mark.parametrize("wta", [False, True])
+@pytest.mark.parametrize("feed", ["text", "packed"])
+def test_screen_c1_shape(c1_case, wta, feed):
+    offsets, hashes, lengths, fasta = c1_case
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    res, want = compare_screen(db, odb, fasta, wta, threads=3, feed=feed)
+    assert int(res.shared.sum()) > 10_000  # the case really exercises hits
+
+
+def test_filter_off_is_identical_and_probes_everything(c1_case):
+    offsets, hashes, lengths, fasta = c1_case
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    on, _ = compare_screen(db, odb, fasta, False, probe_filter=True)
+    off, _ = compare_screen(db, odb, fasta, False, probe_filter=False)
+    assert off.stats["n_probes"] == off.stats["n_valid_kmers"]
+    assert on.stats["n_probes"] <= off.stats["n_probes"]
+    assert on.stats["n_hits"] == off.stats["n_hits"]
+
+
+@pytest.mark.parametrize("k,s", [(16, 400), (31, 1000), (21, 5000)])
+def test_screen_other_k_and_s(k, s):
+    rng = np.random.default_rng(100 + k)
+    genomes = [synth.random_genome(rng, 40_000) for _ in range(30)]
+    offsets, hashes, lengths = build_db(genomes, k, s)
+    fasta = synth.to_fasta(synth.cut_contigs(rng, genomes[:10], 400_000, 0.02, median=5000.0), "c")
+    db = hs.Database.from_arrays(k, s, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(k, s, 42, offsets, hashes, lengths)
+    compare_screen(db, odb, fasta, False)
+    compare_screen(db, odb, fasta, True)
+
+
+def test_wta_clusters_with_ties():
+    """Config 4 shape: clusters of near-identical references (1-5 % divergence), equal-length
+    members (exact (score, length) ties -> highest index) and length-perturbed ones."""
+    rng = np.random.default_rng(4)
+    genomes = []
+    for c in range(12):
+        anc = synth.random_genome(rng, 60_000)
+        for m in range(6):
+            g = synth.mutate(anc, float(rng.uniform(0.01, 0.05)), rng)
+            genomes.append(g if m < 2 else g[:60_000 - int(rng.integers(1, 999))])
+        genomes.append(genomes[-1].copy())  # exact duplicate sketch: full tie
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    fasta = synth.to_fasta(synth.cut_contigs(rng, genomes[::7], 600_000, 0.0, median=8000.0), "c")
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    plain, _ = compare_screen(db, odb, fasta, False)
+    wta, _ = compare_screen(db, odb, fasta, True)
+    assert wta.shared.sum() < plain.shared.sum()          # reassignment removed shared credit
+    dup = [i for i in range(len(genomes)) if i % 7 == 6]
+    assert all(wta.shared[i - 1] == 0 or wta.shared[i] >= wta.shared[i - 1] for i in dup)
+
+
+def test_reset_and_chunked_feeds_agree(c1_case):
+    offsets, hashes, lengths, fasta = c1_case
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    scr = hs.Screen(db)
+    scr.set_option("chunk_bases", 70_000)   # many small chunks, several packer threads
+    scr.feed_text(fasta, 4)
+    a = scr.finish(False)
+    scr.reset()
+    half = fasta.rfind(b"\n>", 0, len(fasta) // 2) + 1
+    scr.feed_text(fasta[:half], 1); scr.feed_text(fasta[half:], 2)
+    b = scr.finish(False)
+    assert a.shared.tolist() == b.shared.tolist() and a.median.tolist() == b.median.tolist()
+    assert a.set_size == b.set_size
+    # idempotence of multiplicity: the same query twice doubles every median, keeps shared
+    scr.reset()
+    scr.feed_text(fasta, 2); scr.feed_text(fasta, 2)
+    c = scr.finish(False)
+    assert c.shared.tolist() == a.shared.tolist()
+    assert c.median.tolist() == (2 * a.median).tolist()
+
+
+# ---------------------------------------------------------------- drop-in -------
+def write_db(tmp_path, genomes, k, s, **kw):
+    offsets, hashes, lengths = build_db(genomes, k, s)
+    db = mshfmt.SketchDB(k=k, s=s, names=[synth.gcf_name(i) for i in range(len(genomes))],
+                         comments=["synthetic genome %d" % i for i in range(len(genomes))],
+                         lengths=lengths, offsets=offsets, hashes=hashes)
+    p = str(tmp_path / "db.msh")
+    mshfmt.write_msh(p, db, **kw)
+    return p
+
+
+def test_cli_tsv_byte_identical_to_oracle_cli(tmp_path):
+    rng = np.random.default_rng(8)
+    genomes = [synth.random_genome(rng, 30_000) for _ in range(40)]
+    dbp = write_db(tmp_path, genomes, 21, 1000, seg_cap_words=1 << 13, double_far_refs=[3])
+    fa1, fa2 = str(tmp_path / "a.fna"), str(tmp_path / "b.fna.gz")
+    open(fa1, "wb").write(synth.to_fasta(synth.cut_contigs(rng, genomes[:8], 200_000, 0.01, median=4000.0), "a"))
+    import gzip
+    gzip.open(fa2, "wb").write(synth.to_fasta(synth.cut_contigs(rng, genomes[5:12], 150_000, 0.03, median=4000.0), "b"))
+    orc.build()
+    for extra in ([], ["-w"], ["-i", "0.8"], ["-i", "-1", "-v", "0.9"]):
+        args = ["screen", "-p", "4"] + extra + [dbp, fa1, fa2]
+        got = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash")] + args, capture_output=True)
+        want = subprocess.run([orc.BIN] + args, capture_output=True)
+        assert got.returncode == 0 and want.returncode == 0, got.stderr.decode()
+        assert got.stdout == want.stdout
+        assert len(got.stdout.splitlines()) > 5
+    # S21: errors
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", dbp, str(tmp_path / "none.fna")],
+                       capture_output=True)
+    assert r.returncode == 1 and b"ERROR" in r.stderr and r.stdout == b""
+
+
+def test_unmodified_mash_sh_pipeline(tmp_path):
+    """The reference's own scripts/mash.sh (restated inline, the GPU box has no
+    /root/reference) with our `mash` first on PATH: all five outputs equal the ones
+    produced with the oracle CLI as `mash`."""
+    mash_sh = """#!/bin/bash
+INPUT_DIR="$1"; MASH_SCREEN="$2"; SCREEN_TAB="$3"; FILTERED_SCREEN="$4"; SORTED_SCREEN="$5"
+TOP_HITS="$6"; SELECTED_GENOMES="$7"; INITIAL_THRESHOLD="$8"
+mash screen -p 8 -v 0.9 "$MASH_SCREEN" "$INPUT_DIR"/*.fna > "$SCREEN_TAB"
+sort -u -k5,5 "$SCREEN_TAB" > "$FILTERED_SCREEN"
+sort -gr "$FILTERED_SCREEN" > "$SORTED_SCREEN"
+best=$INITIAL_THRESHOLD
+awk -v threshold="$best" '$1 > threshold' "$SORTED_SCREEN" > "$TOP_HITS"
+cut -f5 "$TOP_HITS" > "$SELECTED_GENOMES"
+"""
+    rng = np.random.default_rng(9)
+    genomes = [synth.random_genome(rng, 30_000) for _ in range(30)]
+    dbp = write_db(tmp_path, genomes, 21, 1000)
+    indir = tmp_path / "input"; indir.mkdir()
+    (indir / "sample_0.fna").write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[:6], 150_000, 0.01, median=4000.0), "s"))
+    sh = tmp_path / "mash.sh"; sh.write_text(mash_sh)
+    orc.build()
+    outs = {}
+    for tag, mash_exe in (("gpu", os.path.join(ROOT, "bin", "mash")), ("oracle", orc.BIN)):
+        bindir = tmp_path / ("bin_" + tag); bindir.mkdir()
+        os.symlink(mash_exe, bindir / "mash")
+        od = tmp_path / ("out_" + tag); od.mkdir()
+        files = [str(od / f) for f in ("screen.tab", "filtered.tab", "sorted.tab", "top_hits.tab", "selected.txt")]
+        env = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ["PATH"], LC_ALL="C")
+        subprocess.run(["bash", str(sh), str(indir), dbp] + files + ["0.9"], check=True, env=env)
+        outs[tag] = [open(f, "rb").read() for f in files]
+    assert outs["gpu"] == outs["oracle"]
+    assert len(outs["gpu"][4].splitlines()) >= 3

@@ -130,12 +130,12 @@ struct MixEngine {
         if (h_ctl) cudaFreeHost(h_ctl);
     }
     size_t bytes() const { return (size_t)cap * 16 + (size_t)cand_cap * 16; }
-    int reset(cudaStream_t st, uint64_t new_tau = ~0ull)
+    int reset(cudaStream_t st, uint64_t new_tau = ~0ull, bool automatic = true)
     {
         CU(cudaMemsetAsync(d_set[cur], 0xFF, (size_t)cap * 8, st));
         CU(cudaMemsetAsync(d_ctl, 0, 8 * sizeof(uint32_t), st));
         tau = new_tau; dirty = false; touched = false;
-        auto_tau = new_tau == ~0ull;  // a re-offer pass runs at the tau the finaliser chose
+        auto_tau = automatic;  // a re-offer pass runs at exactly the tau the finaliser chose
         return HS_OK;
     }
     // threshold for a launch over n positions: expected offers <= cap/8
@@ -360,7 +360,7 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
         if (rc) return rc;
         if (m.dirty) {  // overflow: too many distinct values below tau -> lower it and re-offer
             const uint64_t nt = m.tau >> 4;
-            rc = m.reset(st, nt ? nt : 1);
+            rc = m.reset(st, nt ? nt : 1, false);
             if (rc) return rc;
             m.passes++;
             rc = rehash();
@@ -391,7 +391,7 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
             // complete below tau but fewer than s distinct values there (very repetitive
             // input): raise tau and re-offer everything
             const uint64_t nt = (m.tau > (~0ull >> 4)) ? ~0ull : (m.tau << 4);
-            rc = m.reset(st, nt);
+            rc = m.reset(st, nt, false);
             if (rc) return rc;
             m.passes++;
             rc = rehash();

@@ -1023,6 +1023,59 @@ HS_API int hs_stat_batch(uint32_t k, uint64_t set_size, uint64_t n, const uint64
     return HS_OK;
 }
 
+namespace {
+// bottom-s of one packed device-resident stream (shared by the two sketch entry points)
+int sketch_device(uint32_t k, uint32_t s_, uint32_t seed, const uint64_t *dseq, const uint32_t *dinv, uint64_t n_bases,
+                  uint64_t *out_hashes, uint32_t *n_out)
+{
+    unsigned long long *dst = nullptr;
+    CU(cudaMalloc((void **)&dst, ST_COUNT * sizeof(unsigned long long)));
+    CU(cudaMemset(dst, 0, ST_COUNT * sizeof(unsigned long long)));
+    MixEngine mix;
+    int rc = mix.init(s_);
+    if (rc == HS_OK) rc = mix.reset(0);
+    Chunk c{dseq, dinv, n_bases};
+    const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
+    auto offer = [&]() -> int {
+        mix.before_launch(c.n_bases);
+        StreamArgs a = base_args(c, k, seed, use64);
+        a.do_mix = 1; a.mix = mix.view(); a.stats = dst;
+        CU(launch_stream(a, g_sm, 0));
+        return HS_OK;
+    };
+    std::vector<uint64_t> out;
+    uint32_t launches = 0;
+    if (rc == HS_OK) rc = offer();
+    if (rc == HS_OK) rc = mix_finalize(mix, 0, out, launches, offer);
+    mix.destroy();
+    cudaFree(dst);
+    if (rc) return rc;
+    *n_out = (uint32_t)out.size();
+    memcpy(out_hashes, out.data(), out.size() * 8);
+    return HS_OK;
+}
+}  // namespace
+
+HS_API int hs_sketch_packed_device(uint32_t k, uint32_t s_, uint32_t seed, const void *d_seq2, const void *d_inv,
+                                   uint64_t n_bases, uint64_t *out_hashes, uint32_t *n_out)
+{
+    if (!out_hashes || !n_out || ((!d_seq2 || !d_inv) && n_bases)) return fail(HS_EINVAL, "null argument");
+    if (k == 0 || k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
+    NEED_DEVICE();
+    *n_out = 0;
+    if (!n_bases) return HS_OK;
+    return sketch_device(k, s_, seed, (const uint64_t *)d_seq2, (const uint32_t *)d_inv, n_bases, out_hashes, n_out);
+}
+
+HS_API int hs_pack_codes_device(const void *d_codes, uint64_t n, void *d_seq2, void *d_inv, void *cuda_stream)
+{
+    if ((!d_codes && n) || !d_seq2 || !d_inv) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    CU(launch_pack_codes((const uint8_t *)d_codes, n, (uint64_t *)d_seq2, (uint32_t *)d_inv, hs_packed_words(n),
+                         (cudaStream_t)cuda_stream));
+    return HS_OK;
+}
+
 HS_API int hs_sketch_text(uint32_t k, uint32_t s_, uint32_t seed, const char *text, size_t n, uint64_t *out_hashes,
                           uint32_t *n_out, uint64_t *length)
 {
@@ -1048,27 +1101,7 @@ HS_API int hs_sketch_text(uint32_t k, uint32_t s_, uint32_t seed, const char *te
     CU(cudaMemset(dst, 0, ST_COUNT * sizeof(unsigned long long)));
     CU(cudaMemcpy(dseq, seq.data(), words * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dinv, inv.data(), words * 4, cudaMemcpyHostToDevice));
-    MixEngine mix;
-    int rc = mix.init(s_);
-    if (rc) return rc;
-    rc = mix.reset(0);
-    Chunk c{dseq, dinv, ps.n_positions};
-    const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
-    auto offer = [&]() -> int {
-        mix.before_launch(c.n_bases);
-        StreamArgs a = base_args(c, k, seed, use64);
-        a.do_mix = 1; a.mix = mix.view(); a.stats = dst;
-        CU(launch_stream(a, g_sm, 0));
-        return HS_OK;
-    };
-    std::vector<uint64_t> out;
-    uint32_t launches = 0;
-    if (rc == HS_OK) rc = offer();
-    if (rc == HS_OK) rc = mix_finalize(mix, 0, out, launches, offer);
-    mix.destroy();
+    int rc = sketch_device(k, s_, seed, dseq, dinv, ps.n_positions, out_hashes, n_out);
     cudaFree(dseq); cudaFree(dinv); cudaFree(dst);
-    if (rc) return rc;
-    *n_out = (uint32_t)out.size();
-    memcpy(out_hashes, out.data(), out.size() * 8);
-    return HS_OK;
+    return rc;
 }

@@ -665,4 +665,50 @@ cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Device-side packer: one thread builds one 64-bit word from 32 base codes
+// (two 128-bit loads), flags codes > 3 and everything past n as invalid.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv,
+                                                    uint64_t n_words)
+{
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p0 = w * 32;
+        uint64_t acc = 0;
+        uint32_t bad = 0;
+        if (p0 + 32 <= n && ((uintptr_t)(codes + p0) & 15) == 0) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(codes + p0));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(codes + p0) + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = (v[i] >> (8 * j)) & 0xFFu;
+                    acc = (acc << 2) | (c & 3u);
+                    bad = (bad << 1) | (c > 3u);
+                }
+            }
+        } else {
+            for (int j = 0; j < 32; j++) {
+                const uint64_t p = p0 + j;
+                const uint32_t c = p < n ? codes[p] : 4u;
+                acc = (acc << 2) | (c & 3u);
+                bad = (bad << 1) | (c > 3u);
+            }
+        }
+        seq[w] = acc;
+        inv[w] = bad;
+    }
+}
+
+cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t n_words_alloc,
+                              cudaStream_t st)
+{
+    if (!n_words_alloc) return cudaSuccess;
+    k_pack_codes<<<grid_for(n_words_alloc, 256, 148 * 16), 256, 0, st>>>(codes, n, seq, inv, n_words_alloc);
+    return cudaGetLastError();
+}
+
 }  // namespace hs

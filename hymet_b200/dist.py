@@ -1,0 +1,128 @@
+"""Multi-GPU screen: one process per GPU, query sharded, sketch table replicated.
+
+SURVEY.md 8e / BASELINE north_star: k-mers are independent, so each rank streams its
+own shard of the contigs against a full copy of the table (sketch DBs fit 180 GB HBM
+many times over).  The only cross-rank state is
+  * counts[E]  -- per-hash multiplicities, summed with ONE NCCL all-reduce over NVLink
+                  (uint32 sums are order independent => bit-exact), and
+  * the mixture bottom-s set -- each rank's s smallest distinct hashes, all-gathered
+                  (s*8 bytes per rank) and merged.
+Everything after that (per-sketch reduction, -w, statistics) runs replicated.
+
+torch.distributed is plumbing only (rendezvous + NCCL/gloo collectives).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import screen as hs
+
+
+class _DevMem:
+    """Expose a raw device allocation of the library to torch (no copy)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def counts_tensor(scr: hs.Screen, device: int) -> torch.Tensor:
+    """counts[E] of a flushed screen as an int32 CUDA tensor aliasing the library's buffer
+    (two's-complement sums equal uint32 sums mod 2^32, which is S8's wrap rule)."""
+    ptr, n = scr.counts_devptr()
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int32, device=f"cuda:{device}")
+    return torch.as_tensor(_DevMem(ptr, n, "<i4"), device=f"cuda:{device}")
+
+
+def record_aligned_range(buf, rank: int, world: int) -> Tuple[int, int]:
+    """Byte range of FASTA text `buf` owned by `rank`: cut at the first line starting
+    with '>' at or after rank*n/world, so no record (hence no k-mer) spans two shards."""
+    n = len(buf)
+    if n and bytes(buf[:1]) == b"@":      # FASTQ ('@' also appears in quality lines): not splittable
+        return (0, n) if rank == 0 else (n, n)
+
+    def cut(i: int) -> int:
+        if i <= 0:
+            return 0
+        if i >= n:
+            return n
+        j = buf.find(b"\n>", i - 1)
+        return n if j < 0 else j + 1
+
+    return cut(rank * n // world), cut((rank + 1) * n // world)
+
+
+def merge_bottom_s(parts, s: int) -> np.ndarray:
+    """Union of per-rank bottom-s sets -> the global s smallest distinct hashes (S9)."""
+    allh = np.concatenate([np.asarray(p, np.uint64) for p in parts]) if len(parts) else np.zeros(0, np.uint64)
+    return np.unique(allh)[:s]
+
+
+def all_gather_mixture(local: np.ndarray, s: int, device: Optional[torch.device] = None, group=None):
+    """Every rank's local mixture hashes (<= s each), as a list of uint64 arrays."""
+    world = dist.get_world_size(group)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    buf = torch.zeros(s + 1, dtype=torch.int64, device=device)
+    buf[0] = len(local)
+    if len(local):
+        buf[1:1 + len(local)] = torch.from_numpy(np.asarray(local, np.uint64).view(np.int64).copy()).to(device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    parts = []
+    for t in out:
+        t = t.cpu().numpy()
+        parts.append(t[1:1 + int(t[0])].view(np.uint64))
+    return parts
+
+
+def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's environment; initialises the process group."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+class DistributedScreen:
+    """hs.Screen whose finish() first exchanges counts and mixture with the other ranks."""
+
+    def __init__(self, db: hs.Database, device: int, **kw):
+        self.db, self.device = db, device
+        self.scr = hs.Screen(db, **kw)
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+
+    def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
+        return getattr(self.scr, name)
+
+    def exchange(self):
+        self.scr.flush()
+        if self.world == 1:
+            return
+        t = counts_tensor(self.scr, self.device)
+        torch.cuda.current_stream().synchronize()
+        if t.numel():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)          # the one NCCL all-reduce of the path
+        parts = all_gather_mixture(self.scr.mixture(), self.db.s)
+        me = dist.get_rank()
+        for r, p in enumerate(parts):
+            if r != me and len(p):
+                self.scr.merge_mixture(p)
+        torch.cuda.current_stream().synchronize()
+
+    def finish(self, wta: bool = False) -> hs.ScreenResult:
+        self.exchange()
+        return self.scr.finish(wta)

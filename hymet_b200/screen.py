@@ -271,6 +271,20 @@ def sketch_text(text: bytes, k: int, s: int, seed: int = 42, device: int = 0):
     return out[:n.value].copy(), int(ln.value)
 
 
+def sketch_packed_device(d_seq_ptr: int, d_inv_ptr: int, n_bases: int, k: int, s: int, seed: int = 42):
+    out = np.zeros(max(s, 1), np.uint64)
+    n = C.c_uint32()
+    check(_abi.load().hs_sketch_packed_device(k, s, seed, C.c_void_p(d_seq_ptr), C.c_void_p(d_inv_ptr), n_bases,
+                                              _ptr(out, C.c_uint64), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def pack_codes_device(d_codes_ptr: int, n: int, d_seq_ptr: int, d_inv_ptr: int, stream_ptr: int = 0):
+    """uint8 base codes in HBM -> packed words in HBM (both caller-allocated)."""
+    check(_abi.load().hs_pack_codes_device(C.c_void_p(d_codes_ptr), n, C.c_void_p(d_seq_ptr), C.c_void_p(d_inv_ptr),
+                                           C.c_void_p(stream_ptr) if stream_ptr else None))
+
+
 def read_msh_host(path: str):
     """The product's C++ .msh parser alone (no GPU): dict of arrays."""
     L = _abi.load()

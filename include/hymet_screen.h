@@ -169,6 +169,14 @@ int hs_stat_batch(uint32_t k, uint64_t set_size, uint64_t n, const uint64_t *sha
 int hs_sketch_text(uint32_t k, uint32_t s, uint32_t seed, const char *text, size_t n, uint64_t *out_hashes,
                    uint32_t *n_out, uint64_t *length);
 
+/* Same, for a genome already packed in DEVICE memory (hs_packed_words() layout). */
+int hs_sketch_packed_device(uint32_t k, uint32_t s, uint32_t seed, const void *d_seq2, const void *d_inv,
+                            uint64_t n_bases, uint64_t *out_hashes, uint32_t *n_out);
+/* Device-side packer: n base codes (uint8: 0..3 = A,C,G,T, anything else = invalid position)
+ * in DEVICE memory -> packed DEVICE arrays of hs_packed_words(n) words (padding flagged
+ * invalid).  Runs on `cuda_stream` (NULL = default stream) and returns without syncing. */
+int hs_pack_codes_device(const void *d_codes, uint64_t n, void *d_seq2, void *d_inv, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,88 @@
+"""Multi-GPU host logic on CPU: query sharding + the two exchanges, world_size 2, gloo.
+The all-reduce and all-gather are exercised for real (gloo); the per-rank screens are
+played by the oracle so that rank-sharded + exchanged == single-process, bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hymet_b200 import dist as hd
+from hymet_b200 import synth
+from tests import _oracle as orc
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _case():
+    rng = np.random.default_rng(21)
+    genomes = [synth.random_genome(rng, 20_000) for _ in range(12)]
+    sk = [orc.sketch_text(synth.to_fasta([g], "g"), 21, 200)[0] for g in genomes]
+    offsets = np.concatenate([[0], np.cumsum([len(x) for x in sk])]).astype(np.uint64)
+    fasta = synth.to_fasta(synth.cut_contigs(rng, genomes[:5], 150_000, 0.01, median=3000.0), "c")
+    return offsets, np.concatenate(sk), np.full(12, 20_000, np.uint64), fasta
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = hd.init_from_env("gloo")
+    offsets, hashes, lengths, fasta = _case()
+    db = orc.OracleDB.from_arrays(21, 200, 42, offsets, hashes, lengths)
+    b, e = hd.record_aligned_range(fasta, r, w)
+    local = db.screen_text(fasta[b:e]) if e > b else None
+    counts = torch.from_numpy((local.counts_per_entry if local is not None else np.zeros(len(hashes), np.uint32))
+                              .view(np.int32).copy())
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    parts = hd.all_gather_mixture(local.mixture if local is not None else np.zeros(0, np.uint64), 200)
+    merged = hd.merge_bottom_s(parts, 200)
+    q.put((r, (b, e), counts.numpy().view(np.uint32).copy(), merged))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_counts_and_mixture_equal_single_process():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    offsets, hashes, lengths, fasta = _case()
+    whole = orc.OracleDB.from_arrays(21, 200, 42, offsets, hashes, lengths).screen_text(fasta)
+    ranges = sorted(g[1] for g in got)
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(fasta) and ranges[0][1] == ranges[1][0]
+    for _, _, counts, merged in got:
+        assert np.array_equal(counts, whole.counts_per_entry)      # all-reduce(sum) == unsharded counts
+        assert np.array_equal(merged, whole.mixture)               # merged bottom-s == unsharded bottom-s
+    assert orc.lib().orc_set_size(got[0][3].ctypes.data_as(orc.C.POINTER(orc.C.c_uint64)), len(got[0][3]), 1) == whole.set_size
+
+
+def test_record_aligned_ranges_cover_without_splitting_records():
+    rng = np.random.default_rng(5)
+    fasta = synth.to_fasta([synth.random_genome(rng, int(n)) for n in rng.integers(10, 4000, size=37)], "r")
+    for world in (1, 2, 3, 8, 64):
+        rs = [hd.record_aligned_range(fasta, r, world) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == len(fasta)
+        assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+        assert all(b == e or fasta[b:b + 1] == b">" for b, e in rs)
+    fq = b"@r1\nACGT\n+\n!!!!\n@r2\nGGCC\n+\n@@@@\n"
+    assert hd.record_aligned_range(fq, 0, 2) == (0, len(fq)) and hd.record_aligned_range(fq, 1, 2) == (len(fq), len(fq))
+
+
+def test_merge_bottom_s():
+    a = np.array([1, 5, 9], np.uint64); b = np.array([2, 5, 7, 11], np.uint64)
+    assert hd.merge_bottom_s([a, b], 4).tolist() == [1, 2, 5, 7]
+    assert hd.merge_bottom_s([a, np.zeros(0, np.uint64)], 10).tolist() == [1, 5, 9]

@@ -229,6 +229,8 @@ def run_b200(args):
             time.sleep(0.25)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         stats = []
+        if sample_clocks:
+            torch.cuda.profiler.start()   # `ncu --profile-from-start off` sees only the timed region
         t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(steps):
@@ -236,6 +238,8 @@ def run_b200(args):
             stats.append(res.stats)
         e1.record(stream)
         barrier()
+        if sample_clocks:
+            torch.cuda.profiler.stop()
         wall = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)

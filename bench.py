@@ -169,7 +169,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -373,15 +373,27 @@ def run_b200(args):
                                 "table_build_s": t_table, "parity_on_sample": "bit-exact" if ok else "MISMATCH",
                                 "sample_shared_hashes": int(r.shared.sum())}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     scr.scr.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_OUT = None
+
+
+def emit(line) -> None:
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
     args = parse_args()
+    # libraries (NCCL's version banner) write to fd 1; the contract is ONE JSON line on stdout
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

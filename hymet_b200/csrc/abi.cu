@@ -302,6 +302,7 @@ StreamArgs base_args(const Chunk &c, uint32_t k, uint32_t seed, bool use64)
     a.seq = c.d_seq; a.inv = c.d_inv; a.n_bases = c.n_bases;
     a.n_tiles = (uint32_t)tiles_for(c.n_bases);
     a.k = (int)k; a.seed = seed; a.use64 = use64;
+    a.pw = make_pow2();
     return a;
 }
 

@@ -44,6 +44,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
     uint32_t ok;
@@ -124,11 +128,30 @@ struct SmemLut {
     __device__ __forceinline__ uint32_t operator()(uint32_t b) const { return lane_base[b * 32]; }
 };
 
+// Fast-path table: entry b = letters of the byte whose FIRST base is in the top two bits.
+// Addressed as lane_base + b*128 with the multiply done on the FMA pipe (Pow2::v[7]).
+struct SmemLutMsb {
+    uint32_t lane_base;  // shared-window byte address of lut[lane]
+    __device__ __forceinline__ uint32_t operator()(uint32_t word, int idx, const Pow2 &P) const
+    {
+        const uint32_t b = __byte_perm(word, 0u, 0x4440u | (uint32_t)idx);  // byte `idx`, zero extended
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(lane_base + b * P.v[7]));
+        return v;
+    }
+};
+
 template <int KT>
 __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
 {
-    __shared__ TileBuf buf[2];
-    __shared__ __align__(8) uint64_t bar[2];
+    constexpr bool kFast = KT >= 18;  // 64-bit-hash regime, k known at compile time
+    // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
+    // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
+    // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
+    // apart (ncu r01: 12 % of warp time sat in __syncthreads with the 2-stage version).
+    constexpr uint32_t kStages = 3, kPrefetch = 1;
+    __shared__ TileBuf buf[kStages];
+    __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
     __shared__ uint32_t lut[256 * 32];
 
     const int k = KT ? KT : a.k;
@@ -136,36 +159,49 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (uint32_t i = 0; i < kStages; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kCtaThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = ascii4(i >> 5);
+    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = kFast ? ascii4_msb(i >> 5) : ascii4(i >> 5);
     __syncthreads();
     const SmemLut L{lut + lane};
+    const SmemLutMsb LF{smem_u32(lut + lane)};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
         const uint32_t sw = tile ? 2u : 0u, iw = tile ? 4u : 0u;
         const uint32_t sbytes = (kTileWords + sw) * 8u, ibytes = (kTileWords + iw) * 4u;
-        mbar_expect_tx(&bar[b], sbytes + ibytes);
-        bulk_g2s(&buf[b].seq[2 - sw], a.seq + (size_t)tile * kTileWords - sw, sbytes, &bar[b]);
-        bulk_g2s(&buf[b].inv[4 - iw], a.inv + (size_t)tile * kTileWords - iw, ibytes, &bar[b]);
+        mbar_expect_tx(&full[b], sbytes + ibytes);
+        bulk_g2s(&buf[b].seq[2 - sw], a.seq + (size_t)tile * kTileWords - sw, sbytes, &full[b]);
+        bulk_g2s(&buf[b].inv[4 - iw], a.inv + (size_t)tile * kTileWords - iw, ibytes, &full[b]);
     };
 
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = blockIdx.x, it = 0;
-    if (tid == 0 && tile < a.n_tiles) issue(tile, 0);
+    if (tid == 0)
+        for (uint32_t p = 0; p < kPrefetch; p++)
+            if ((uint64_t)tile + (uint64_t)p * gridDim.x < a.n_tiles) issue(tile + p * gridDim.x, p);
 
     for (; tile < a.n_tiles; tile += gridDim.x, it++) {
-        const uint32_t b = it & 1u, phase = (it >> 1) & 1u;
-        const uint32_t next = tile + gridDim.x;
-        if (tid == 0 && next < a.n_tiles) issue(next, b ^ 1u);
-        mbar_wait(&bar[b], phase);
+        if (tid == 0) {
+            const uint32_t nt = it + kPrefetch;
+            const uint64_t ntile = (uint64_t)blockIdx.x + (uint64_t)nt * gridDim.x;
+            if (ntile < a.n_tiles) {
+                const uint32_t sb = nt % kStages;
+                if (nt >= kStages) mbar_wait(&empty[sb], ((nt / kStages) - 1u) & 1u);  // its previous tile was consumed
+                issue((uint32_t)ntile, sb);
+            }
+        }
+        const uint32_t b = it % kStages;
+        mbar_wait(&full[b], (it / kStages) & 1u);
         uint64_t cur = buf[b].seq[tid + 2], prev = buf[b].seq[tid + 1];
         uint32_t icur = buf[b].inv[tid + 4], iprev = buf[b].inv[tid + 3];
-        __syncthreads();  // every thread holds its words: buf[b] may be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[b]);  // this warp holds its words: the stage may be refilled
 
         if (tile == 0 && tid == 0) { prev = 0; iprev = ~0u; }
         const uint64_t pos0 = ((uint64_t)tile * kTileWords + tid) * kBasesPerWord;
@@ -175,7 +211,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
         }
         if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
 
-        for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, [&](int j, uint64_t h) {
+        auto sink = [&](int j, uint64_t h) {
             n_valid++;
             if (a.emit_hash) {
                 a.emit_hash[pos0 + j] = h;
@@ -195,7 +231,11 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
                     n_hits++;
                 }
             }
-        });
+        };
+        if constexpr (kFast)
+            for_each_kmer_in_word_fast<(kFast ? KT : 21)>(prev, cur, iprev, icur, a.seed, a.pw, LF, sink);
+        else
+            for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, sink);
     }
 
     n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);

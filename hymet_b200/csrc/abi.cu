@@ -5,6 +5,8 @@
 // There is deliberately no CPU implementation of any kernel in this library.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -30,6 +32,7 @@ namespace {
 thread_local std::string g_err;
 int g_device = -1;
 int g_sm = 0;
+bool g_debug_timing = false;
 
 int fail(int code, const std::string &msg)
 {
@@ -302,7 +305,6 @@ StreamArgs base_args(const Chunk &c, uint32_t k, uint32_t seed, bool use64)
     a.seq = c.d_seq; a.inv = c.d_inv; a.n_bases = c.n_bases;
     a.n_tiles = (uint32_t)tiles_for(c.n_bases);
     a.k = (int)k; a.seed = seed; a.use64 = use64;
-    a.pw = make_pow2();
     return a;
 }
 
@@ -460,6 +462,7 @@ HS_API int hs_init(int device)
     CU(cudaSetDevice(device));
     g_device = device;
     g_sm = p.multiProcessorCount;
+    g_debug_timing = getenv("HYMET_SCREEN_DEBUG_TIMING") != nullptr;
     return HS_OK;
 }
 
@@ -705,11 +708,17 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
             }
             PackStats ps;
             if (rc == HS_OK) {
+                const double t0 = now_s();
                 pack_text_span(text + spans[i].first, len, g.seq, g.inv, &ps);
+                const double t1 = now_s();
                 std::lock_guard<std::mutex> lk(s->mu);
+                const double t2 = now_s();
                 s->st.n_bases += ps.n_seq_bases;
                 s->st.n_records += ps.n_records;
                 rc = feed_host_chunk(s, g.seq, g.inv, ps.n_positions, g.free_ev);
+                if (g_debug_timing)
+                    fprintf(stderr, "[hs] span %zu thr %d: %zu B pack %.2f ms (%.2f GB/s) lock-wait %.2f ms feed %.2f ms\n", i, t,
+                            len, 1e3 * (t1 - t0), len / (t1 - t0) / 1e9, 1e3 * (t2 - t1), 1e3 * (now_s() - t2));
             }
             if (rc != HS_OK) {
                 std::lock_guard<std::mutex> lk(err_mu);

@@ -179,164 +179,6 @@ HS_HD void for_each_kmer_in_word(uint64_t prev, uint64_t cur, uint32_t inv_prev,
     }
 }
 
-// ============================================================================
-// Fast path for 18 <= k <= 32 (the 64-bit-hash regime HYMET's sketches use).
-//
-// ncu on the straightforward code above (profiles/r01_ncu_full_summary.json): the
-// kernel is bound by the ALU pipe (shifts, logic, compares: 16 lanes/clk/SMSP, 67 %
-// busy, math_pipe_throttle the top stall) while the FMA pipe (IMAD: 32 lanes/clk)
-// idles at 28 %.  So every shift/rotate here is written as a multiplication by a
-// power of two that ptxas cannot see through (Pow2 travels in the kernel
-// parameters), which turns 2-cycle ALU-pipe SHF into 1-cycle FMA-pipe IMAD/IMAD.HI:
-//     x << r          ==  x * 2^r              (mod 2^32)
-//     x >> (32 - r)   ==  mulhi32(x, 2^r)
-// Same values bit for bit; tests/host_emul checks this path against the oracle too.
-// ============================================================================
-struct Pow2 { uint32_t v[32]; };  // v[i] == 1u << i
-inline Pow2 make_pow2()
-{
-    Pow2 p;
-    for (int i = 0; i < 32; i++) p.v[i] = 1u << i;
-    return p;
-}
-
-HS_HD uint32_t mulhi32(uint32_t a, uint32_t b)
-{
-#if defined(__CUDA_ARCH__)
-    return __umulhi(a, b);
-#else
-    return (uint32_t)(((uint64_t)a * b) >> 32);
-#endif
-}
-
-// rotate left by the compile-time constant R (1..63, != 32) using only multiplies
-template <int R>
-HS_HD uint64_t rotl64_fma(uint64_t x, const Pow2 &P)
-{
-    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
-    if (R >= 32) { const uint32_t t = lo; lo = hi; hi = t; }
-    constexpr int r = R & 31;
-    const uint32_t M = P.v[r];
-    const uint32_t nlo = lo * M + mulhi32(hi, M);
-    const uint32_t nhi = hi * M + mulhi32(lo, M);
-    return (uint64_t)nlo | ((uint64_t)nhi << 32);
-}
-
-HS_HD uint64_t fmix64_fma(uint64_t k, const Pow2 &P)
-{
-    k ^= (uint64_t)mulhi32((uint32_t)(k >> 32), P.v[31]);  // k ^= k >> 33
-    k *= 0xff51afd7ed558ccdull;
-    k ^= (uint64_t)mulhi32((uint32_t)(k >> 32), P.v[31]);
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= (uint64_t)mulhi32((uint32_t)(k >> 32), P.v[31]);
-    return k;
-}
-
-template <int K>
-HS_HD uint64_t murmur3_h1_words_fma(const uint32_t w[8], uint32_t seed, const Pow2 &P)
-{
-    const uint64_t c1 = 0x87c37b91114253d5ull, c2 = 0x4cf5ad432745937full;
-    uint64_t h1 = seed, h2 = seed;
-    constexpr int nblocks = K >> 4;
-#pragma unroll
-    for (int b = 0; b < nblocks; b++) {
-        uint64_t k1 = (uint64_t)w[4 * b] | ((uint64_t)w[4 * b + 1] << 32);
-        uint64_t k2 = (uint64_t)w[4 * b + 2] | ((uint64_t)w[4 * b + 3] << 32);
-        k1 *= c1; k1 = rotl64_fma<31>(k1, P); k1 *= c2; h1 ^= k1;
-        h1 = rotl64_fma<27>(h1, P); h1 += h2; h1 = h1 * 5 + 0x52dce729;
-        k2 *= c2; k2 = rotl64_fma<33>(k2, P); k2 *= c1; h2 ^= k2;
-        h2 = rotl64_fma<31>(h2, P); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
-    }
-    if (K & 15) {
-        constexpr int base = 4 * nblocks;
-        if ((K & 15) > 8) {
-            uint64_t k2 = (uint64_t)w[(base + 2) & 7] | ((uint64_t)w[(base + 3) & 7] << 32);
-            k2 *= c2; k2 = rotl64_fma<33>(k2, P); k2 *= c1; h2 ^= k2;
-        }
-        uint64_t k1 = (uint64_t)w[base & 7] | ((uint64_t)w[(base + 1) & 7] << 32);
-        k1 *= c1; k1 = rotl64_fma<31>(k1, P); k1 *= c2; h1 ^= k1;
-    }
-    h1 ^= (uint64_t)K; h2 ^= (uint64_t)K;
-    h1 += h2; h2 += h1;
-    h1 = fmix64_fma(h1, P); h2 = fmix64_fma(h2, P);
-    return h1 + h2;
-}
-
-// Four bases in one byte, FIRST base in the top two bits -> their ASCII letters,
-// first base in the low byte (the fast path keeps k-mers first-base-most-significant).
-HS_HD uint32_t ascii4_msb(uint32_t b)
-{
-    const uint32_t lut = 0x54474341u;
-    return ((lut >> (8 * ((b >> 6) & 3))) & 0xFFu) | (((lut >> (8 * ((b >> 4) & 3))) & 0xFFu) << 8) |
-           (((lut >> (8 * ((b >> 2) & 3))) & 0xFFu) << 16) | (((lut >> (8 * (b & 3))) & 0xFFu) << 24);
-}
-struct AsciiArithMsb {
-    // byte `idx` (0 = least significant) of `word`
-    HS_HD uint32_t operator()(uint32_t word, int idx, const Pow2 &) const { return ascii4_msb((word >> (8 * idx)) & 0xFFu); }
-};
-
-// Canonical k-mer (first base most significant, LEFT aligned in hi:lo) -> hash.
-template <int K, class Lut>
-HS_HD uint64_t hash_canonical_msb(uint32_t c_hi, uint32_t c_lo, uint32_t seed, const Pow2 &P, const Lut &lut)
-{
-    uint32_t w[8];
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-        const int nb = K - 4 * g;  // bases in this group
-        uint32_t v = 0;
-        if (nb > 0) {
-            v = lut(g < 4 ? c_hi : c_lo, 3 - (g & 3), P);
-            if (nb < 4) v &= (1u << (8 * nb)) - 1u;  // also discards whatever sits below the k-mer
-        }
-        w[g] = v;
-    }
-    return murmur3_h1_words_fma<K>(w, seed, P);
-}
-
-// The 32 k-mers ending in `cur`, fast path.  State per thread: forward k-mer and its
-// reverse complement, both first-base-most-significant and left aligned; the reverse
-// complement is allowed to carry stale bits BELOW the k-mer (they lose every
-// comparison that matters and are masked before hashing).
-template <int K, class Lut, class Sink>
-HS_HD void for_each_kmer_in_word_fast(uint64_t prev, uint64_t cur, uint32_t inv_prev, uint32_t inv_cur,
-                                      uint32_t seed, const Pow2 &P, const Lut &lut, Sink &&sink)
-{
-    static_assert(K >= 18 && K <= 32, "fast path covers the 64-bit-hash regime with k >= 18");
-    constexpr int sh = 64 - 2 * K;  // 0..28: bit offset of the newest base inside hi:lo
-    const uint32_t bad = invalid_kmer_ends(inv_prev, inv_cur, K);
-    uint32_t fm_lo, fm_hi, rm_lo, rm_hi;
-    {
-        const uint64_t fr = prev & kmer_mask(K);                       // k-mer ending at base 31 of prev
-        const uint64_t rr = (~(pair_reverse64(fr) >> sh)) & kmer_mask(K);  // its reverse complement
-        const uint64_t f = fr << sh, r = rr << sh;
-        fm_lo = (uint32_t)f; fm_hi = (uint32_t)(f >> 32);
-        rm_lo = (uint32_t)r; rm_hi = (uint32_t)(r >> 32);
-    }
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        uint32_t T = half ? (uint32_t)cur : (uint32_t)(cur >> 32);  // 16 bases, next one in the top two bits
-#pragma unroll 4
-        for (int j2 = 0; j2 < 16; j2++) {
-            const uint32_t X = T;
-            T = T * P.v[2];
-            // forward: shift one base up, newest base enters at bit `sh`
-            const uint32_t cs = (sh == 0 ? mulhi32(X, P.v[2]) : mulhi32(X, P.v[2 + sh])) & (3u << sh);
-            const uint32_t nf_hi = fm_hi * P.v[2] + mulhi32(fm_lo, P.v[2]);
-            fm_lo = fm_lo * P.v[2] + cs;
-            fm_hi = nf_hi;
-            // reverse complement: shift one base down, complement of the newest base enters on top
-            const uint32_t nr_lo = rm_hi * P.v[30] + mulhi32(rm_lo, P.v[30]);
-            rm_hi = mulhi32(rm_hi, P.v[30]) | (~X & 0xC0000000u);
-            rm_lo = nr_lo;
-            const int j = half * 16 + j2;
-            if (!((bad >> (31 - j)) & 1u)) {
-                const bool fwd = (fm_hi < rm_hi) || (fm_hi == rm_hi && fm_lo <= rm_lo);  // S5, ties -> forward
-                sink(j, hash_canonical_msb<K>(fwd ? fm_hi : rm_hi, fwd ? fm_lo : rm_lo, seed, P, lut));
-            }
-        }
-    }
-}
-
 // ---- sketch hash table ------------------------------------------------------
 // Buckets of four 8-byte keys (one 32-byte DRAM sector); kEmpty marks a free
 // slot.  Reference hashes are bottom-s values (numerically small) so the bucket

@@ -128,23 +128,9 @@ struct SmemLut {
     __device__ __forceinline__ uint32_t operator()(uint32_t b) const { return lane_base[b * 32]; }
 };
 
-// Fast-path table: entry b = letters of the byte whose FIRST base is in the top two bits.
-// Addressed as lane_base + b*128 with the multiply done on the FMA pipe (Pow2::v[7]).
-struct SmemLutMsb {
-    uint32_t lane_base;  // shared-window byte address of lut[lane]
-    __device__ __forceinline__ uint32_t operator()(uint32_t word, int idx, const Pow2 &P) const
-    {
-        const uint32_t b = __byte_perm(word, 0u, 0x4440u | (uint32_t)idx);  // byte `idx`, zero extended
-        uint32_t v;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(lane_base + b * P.v[7]));
-        return v;
-    }
-};
-
 template <int KT>
 __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
 {
-    constexpr bool kFast = KT >= 18;  // 64-bit-hash regime, k known at compile time
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
@@ -166,10 +152,9 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = kFast ? ascii4_msb(i >> 5) : ascii4(i >> 5);
+    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = ascii4(i >> 5);
     __syncthreads();
     const SmemLut L{lut + lane};
-    const SmemLutMsb LF{smem_u32(lut + lane)};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -232,10 +217,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
                 }
             }
         };
-        if constexpr (kFast)
-            for_each_kmer_in_word_fast<(kFast ? KT : 21)>(prev, cur, iprev, icur, a.seed, a.pw, LF, sink);
-        else
-            for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, sink);
+        for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, sink);
     }
 
     n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);

@@ -50,7 +50,6 @@ struct StreamArgs {
     unsigned long long *stats;  // ST_COUNT slots
     uint64_t *emit_hash;    // optional: per position hash (K1 parity), n_bases entries
     uint8_t *emit_valid;
-    Pow2 pw;                // opaque powers of two for the FMA-pipe fast path (kmer_core.cuh)
 };
 
 // ---- streaming (K1+K2+K3 insert) -------------------------------------------

@@ -12,23 +12,6 @@
 #include "../../hymet_b200/csrc/fasta_pack.h"
 #include "../../hymet_b200/csrc/kmer_core.cuh"
 
-// Same walk through the FMA-pipe fast path (compile-time k, 18..32).
-template <int K>
-static int64_t fast_walk(const std::vector<uint64_t> &seq, const std::vector<uint32_t> &inv, uint64_t nw, uint32_t seed,
-                         uint64_t *out, uint64_t cap)
-{
-    const hs::Pow2 P = hs::make_pow2();
-    uint64_t m = 0;
-    bool overflow = false;
-    for (uint64_t w = 0; w < nw; w++) {
-        const uint64_t prev = w ? seq[w - 1] : 0;
-        const uint32_t iprev = w ? inv[w - 1] : ~0u;
-        hs::for_each_kmer_in_word_fast<K>(prev, seq[w], iprev, inv[w], seed, P, hs::AsciiArithMsb(),
-                                          [&](int, uint64_t h) { if (m < cap) out[m++] = h; else overflow = true; });
-    }
-    return overflow ? -1 : (int64_t)m;
-}
-
 extern "C" {
 
 // returns number of hashes written (valid k-mers, stream order); stats[0..2] = records, bases, positions
@@ -50,20 +33,6 @@ int64_t emul_pack_and_hash(const char *text, uint64_t n, int k, uint32_t seed, u
                                   [&](int, uint64_t h) { if (m < cap) out[m++] = h; else overflow = true; });
     }
     return overflow ? -1 : (int64_t)m;
-}
-
-int64_t emul_pack_and_hash_fast(const char *text, uint64_t n, int k, uint32_t seed, uint64_t *out, uint64_t cap)
-{
-    std::vector<uint64_t> seq(hs::pack_words_bound(n));
-    std::vector<uint32_t> inv(hs::pack_words_bound(n));
-    uint64_t nw = hs::pack_text_span(text, n, seq.data(), inv.data(), nullptr);
-    switch (k) {
-#define HS_CASE(K) case K: return fast_walk<K>(seq, inv, nw, seed, out, cap);
-        HS_CASE(18) HS_CASE(19) HS_CASE(20) HS_CASE(21) HS_CASE(22) HS_CASE(23) HS_CASE(24) HS_CASE(25) HS_CASE(26)
-        HS_CASE(27) HS_CASE(28) HS_CASE(29) HS_CASE(30) HS_CASE(31) HS_CASE(32)
-#undef HS_CASE
-    default: return -2;
-    }
 }
 
 uint64_t emul_pack(const char *text, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t *stats)

@@ -34,8 +34,6 @@ def emul():
     L.emul_pack_and_hash.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint32,
                                      C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64)]
     L.emul_pack_and_hash.restype = C.c_int64
-    L.emul_pack_and_hash_fast.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint64]
-    L.emul_pack_and_hash_fast.restype = C.c_int64
     L.emul_bucket_of.argtypes = [C.c_uint64, C.c_uint32]; L.emul_bucket_of.restype = C.c_uint32
     L.emul_pair_reverse.argtypes = [C.c_uint64]; L.emul_pair_reverse.restype = C.c_uint64
     L.emul_split.argtypes = [C.c_char_p, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
@@ -80,18 +78,6 @@ def test_emulated_thread_walk_equals_oracle(emul, k):
     assert st[0] == len(recs) and st[1] == sum(len(s) for _, s in recs)
     assert st[2] == st[1] + st[0]          # one separator position per record
     assert np.array_equal(got, want)       # same hashes, same stream order
-
-
-@pytest.mark.parametrize("k", list(range(18, 33)))
-def test_fma_fast_path_equals_oracle(emul, k):
-    """The multiply-only fast path (kernel default for k=21/31) against the oracle, every k it admits."""
-    rng = random.Random(500 + k)
-    text = rand_fasta(rng, 10, 1200) + ">pal\n" + "ACGT" * 20 + "\n>polyA\n" + "A" * 100 + "\n>polyT\n" + "T" * 100 + "\n"
-    out = np.zeros(len(text) + 8, np.uint64)
-    n = emul.emul_pack_and_hash_fast(text.encode(), len(text), k, 42, out.ctypes.data_as(C.POINTER(C.c_uint64)), len(out))
-    want, _ = oracle_hashes(text, k)
-    assert n == len(want)
-    assert np.array_equal(out[:n], want)
 
 
 def test_edge_inputs(emul):

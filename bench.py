@@ -208,10 +208,19 @@ def run_b200(args):
         scr.feed_packed_device(wl.d_seq.data_ptr(), wl.d_inv.data_ptr(), wl.n_positions)
         return scr.finish(args.wta)
 
+    text_wall = {"reset": 0.0, "feed": 0.0, "finish": 0.0, "n": 0}
+
     def step_text():
+        t0 = time.perf_counter()
         scr.reset()
+        t1 = time.perf_counter()
         scr.feed_text_ptr(wl.fasta.data_ptr(), wl.fasta.numel(), host_threads)
-        return scr.finish(args.wta)
+        t2 = time.perf_counter()
+        r = scr.finish(args.wta)
+        t3 = time.perf_counter()
+        text_wall.setdefault("steps", []).append([round(1e3 * (t1 - t0), 2), round(1e3 * (t2 - t1), 2),
+                                                  round(1e3 * (t3 - t2), 2)])
+        return r
 
     def step_packed_host():
         scr.reset()
@@ -333,6 +342,8 @@ def run_b200(args):
                        "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": ems / e_steps,
                        "input": "FASTA text (%d B per GPU, 80-column lines) in pinned host memory" % wl.fasta.numel(),
                        "host_threads_per_gpu": host_threads, "steps": e_steps,
+                       "host_wall_ms_reset_feed_finish": text_wall["steps"][-e_steps:],
+                       "stream_kernel_ms_per_step": est["ms_stream"], "launches_per_step": est["n_launches"],
                        "includes": "host FASTA parse + 2-bit pack, H2D, all kernels, D2H of the result columns"}
         pms, pwall, pstats, pres, _ = timed(step_packed_host, e_steps, 1)
         line["e2e_packed"] = {"value": e_steps * total_bases / (pms * 1e-3) / 1e6, "unit": UNIT,

@@ -5,6 +5,7 @@
 // There is deliberately no CPU implementation of any kernel in this library.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -62,32 +63,32 @@ struct Arena {
     struct Slab { char *p; size_t cap, used; };
     std::vector<Slab> slabs;
     size_t slab_bytes = (size_t)256 << 20;
-    size_t total = 0;
+    size_t total = 0, cur = 0;
     cudaError_t alloc(size_t n, void **out)
     {
         n = (n + 255) & ~(size_t)255;
-        if (slabs.empty() || slabs.back().used + n > slabs.back().cap) {
+        while (cur < slabs.size() && slabs[cur].used + n > slabs[cur].cap) cur++;
+        if (cur == slabs.size()) {
             Slab s{nullptr, std::max(n, slab_bytes), 0};
             cudaError_t e = cudaMalloc((void **)&s.p, s.cap);
             if (e != cudaSuccess) return e;
             slabs.push_back(s);
             total += s.cap;
         }
-        *out = slabs.back().p + slabs.back().used;
-        slabs.back().used += n;
+        *out = slabs[cur].p + slabs[cur].used;
+        slabs[cur].used += n;
         return cudaSuccess;
     }
     void reset()
-    {   // keep the first slab for reuse, drop the rest
-        for (size_t i = 1; i < slabs.size(); i++) { cudaFree(slabs[i].p); total -= slabs[i].cap; }
-        if (slabs.size() > 1) slabs.resize(1);
-        if (!slabs.empty()) slabs[0].used = 0;
+    {   // slabs stay allocated: a steady-state screen never calls cudaMalloc/cudaFree
+        for (auto &s : slabs) s.used = 0;
+        cur = 0;
     }
     void release()
     {
         for (auto &s : slabs) cudaFree(s.p);
         slabs.clear();
-        total = 0;
+        total = 0; cur = 0;
     }
 };
 
@@ -98,18 +99,17 @@ struct Chunk {
 };
 
 // ---- mixture bottom-s engine (K3 control logic) --------------------------------
-// ctl words on the device: [0] distinct count, [1] overflow, [2] has_max, [3] n_out, [4] n_unique
+// The threshold tau and the live set are DEVICE state (MixState): streaming launches and
+// their maintenance kernels are enqueued back to back, the host looks at the state only
+// at flush.  Exactness: a value is dropped only when >= s smaller distinct values stay.
 struct MixEngine {
     uint32_t s = 0, cap = 0, cand_cap = 0;
     uint64_t *d_set[2] = {nullptr, nullptr};
-    int cur = 0;
-    uint32_t *d_ctl = nullptr;
-    uint32_t *h_ctl = nullptr;  // pinned
+    MixState *d_state = nullptr;
+    MixState *h_state = nullptr;  // pinned mirror, valid after sync_state()
+    MixState *h_init = nullptr;   // pinned source for resets
     uint64_t *d_cand = nullptr, *d_scratch = nullptr;
-    uint64_t tau = ~0ull;
-    bool dirty = false;    // the set lost elements (overflow): must be rebuilt by re-hashing
-    bool touched = false;  // launches since the last check
-    bool auto_tau = true;  // first pass: lower tau per launch so expected offers stay <= cap/8
+    bool auto_tau = true;  // first pass: cap tau per launch so expected offers stay <= cap/8
     uint32_t passes = 1;
 
     int init(uint32_t s_)
@@ -120,8 +120,9 @@ struct MixEngine {
         cand_cap = 8192;
         while (cand_cap < 4 * s) cand_cap <<= 1;
         for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&d_set[i], (size_t)cap * 8));
-        CU(cudaMalloc((void **)&d_ctl, 8 * sizeof(uint32_t)));
-        CU(cudaHostAlloc((void **)&h_ctl, 8 * sizeof(uint32_t), cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&d_state, sizeof(MixState)));
+        CU(cudaHostAlloc((void **)&h_state, sizeof(MixState), cudaHostAllocDefault));
+        CU(cudaHostAlloc((void **)&h_init, sizeof(MixState), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
         CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
         return HS_OK;
@@ -129,54 +130,38 @@ struct MixEngine {
     void destroy()
     {
         for (int i = 0; i < 2; i++) cudaFree(d_set[i]);
-        cudaFree(d_ctl); cudaFree(d_cand); cudaFree(d_scratch);
-        if (h_ctl) cudaFreeHost(h_ctl);
+        cudaFree(d_state); cudaFree(d_cand); cudaFree(d_scratch);
+        if (h_state) cudaFreeHost(h_state);
+        if (h_init) cudaFreeHost(h_init);
     }
-    size_t bytes() const { return (size_t)cap * 16 + (size_t)cand_cap * 16; }
+    uint32_t *field(size_t off) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(d_state) + off); }
     int reset(cudaStream_t st, uint64_t new_tau = ~0ull, bool automatic = true)
     {
-        CU(cudaMemsetAsync(d_set[cur], 0xFF, (size_t)cap * 8, st));
-        CU(cudaMemsetAsync(d_ctl, 0, 8 * sizeof(uint32_t), st));
-        tau = new_tau; dirty = false; touched = false;
+        CU(cudaStreamSynchronize(st));  // h_init may still be the source of an earlier reset
+        memset(h_init, 0, sizeof(MixState));
+        h_init->tau = new_tau;
+        CU(cudaMemsetAsync(d_set[0], 0xFF, (size_t)cap * 8, st));
+        CU(cudaMemcpyAsync(d_state, h_init, sizeof(MixState), cudaMemcpyHostToDevice, st));
         auto_tau = automatic;  // a re-offer pass runs at exactly the tau the finaliser chose
         return HS_OK;
     }
-    // threshold for a launch over n positions: expected offers <= cap/8
-    void before_launch(uint64_t n)
+    // cap for a launch over n positions: expected offers <= capacity/8
+    uint64_t launch_cap(uint64_t n) const
     {
         const uint64_t budget = cap / 8;
-        if (auto_tau && n > budget) {
-            const uint64_t t = (~0ull / n) * budget;
-            if (t < tau) tau = t;
-        }
-        touched = true;
+        return (auto_tau && n > budget) ? (~0ull / n) * budget : ~0ull;
     }
-    MixView view() const
+    MixView view(uint64_t tau_cap) const
     {
         MixView v;
-        v.set = d_set[cur]; v.mask = cap - 1; v.limit = cap / 2; v.tau = tau;
-        v.count = d_ctl; v.overflow = d_ctl + 1; v.has_max = d_ctl + 2;
+        v.sets[0] = d_set[0]; v.sets[1] = d_set[1];
+        v.mask = cap - 1; v.limit = cap / 2; v.tau_cap = tau_cap; v.st = d_state;
         return v;
     }
-    // Between launches: keep the set sparse by lowering tau (exact: dropped values
-    // are larger than >= s kept ones, so they can never be among the s smallest).
-    int check(cudaStream_t st)
+    int sync_state(cudaStream_t st)
     {
-        if (!touched) return HS_OK;
-        CU(cudaMemcpyAsync(h_ctl, d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_state, d_state, sizeof(MixState), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
-        touched = false;
-        if (h_ctl[1]) { dirty = true; return HS_OK; }
-        while (h_ctl[0] > cap / 4 && (tau >> 2) > 0) {
-            const uint64_t nt = tau >> 2;
-            const int other = cur ^ 1;
-            CU(cudaMemsetAsync(d_set[other], 0xFF, (size_t)cap * 8, st));
-            CU(cudaMemsetAsync(d_ctl, 0, sizeof(uint32_t), st));
-            CU(launch_mix_rebuild(d_set[cur], cap, nt, d_set[other], d_ctl, st));
-            CU(cudaMemcpyAsync(h_ctl, d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            cur = other; tau = nt;
-        }
         return HS_OK;
     }
 };
@@ -215,6 +200,10 @@ struct hs_screen {
     hs_db *db = nullptr;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;      // H2D of query chunks overlaps the kernels of earlier chunks
+    std::vector<cudaEvent_t> copy_evs;
+    size_t copy_ev_used = 0;
+    uint64_t piece_positions = (uint64_t)32 << 20;  // packed host feeds are uploaded + launched in pieces
     uint32_t *d_counts = nullptr;
     unsigned long long *d_stats = nullptr;
     MixEngine mix;
@@ -308,19 +297,19 @@ StreamArgs base_args(const Chunk &c, uint32_t k, uint32_t seed, bool use64)
     return a;
 }
 
-// launch the streaming kernel for one chunk (caller holds s->mu)
-int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix)
+// launch the streaming kernel for tiles [tile_begin, tile_end) of one chunk (caller holds s->mu);
+// tile_end == 0 means the whole chunk
+int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t tile_begin = 0, uint64_t tile_end = 0)
 {
     if (!c.n_bases) return HS_OK;
     if (tiles_for(c.n_bases) > 0xFFFFFFFFull) return fail(HS_EINVAL, "chunk too large");
-    if (mix) {
-        int rc = s->mix.check(s->stream);
-        if (rc) return rc;
-        s->mix.before_launch(c.n_bases);
-    }
+    if (!tile_end) tile_end = tiles_for(c.n_bases);
     StreamArgs a = base_args(c, s->db->k, s->db->seed, s->db->use64);
+    a.tile_begin = (uint32_t)tile_begin; a.n_tiles = (uint32_t)tile_end;
     a.do_count = count; a.do_filter = s->filter; a.do_mix = mix;
-    a.tab = s->db->view(); a.counts = s->d_counts; a.mix = s->mix.view();
+    a.tab = s->db->view(); a.counts = s->d_counts;
+    const uint64_t launch_positions = (tile_end - tile_begin) * kTileWords * 32;
+    a.mix = s->mix.view(mix ? s->mix.launch_cap(launch_positions) : ~0ull);
     a.stats = count ? s->d_stats : s->d_stats + ST_COUNT;  // re-offer passes must not double count
     if (s->ev_used == s->ev_pool.size()) {
         cudaEvent_t e0, e1;
@@ -332,7 +321,11 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix)
     CU(launch_stream(a, g_sm, s->stream));
     CU(cudaEventRecord(ev.second, s->stream));
     s->st.n_launches++;
-    s->st.n_positions += c.n_bases;
+    if (mix) {
+        CU(launch_mix_maintain(a.mix, s->stream));
+        s->st.n_launches += 3;
+    }
+    s->st.n_positions += std::min<uint64_t>(c.n_bases, tile_end * kTileWords * 32) - tile_begin * kTileWords * 32;
     return HS_OK;
 }
 
@@ -346,8 +339,10 @@ int screen_zero(hs_screen *s)
     s->mixture.clear();
     s->flushed = false;
     s->chunks.clear();
+    if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
     s->arena.reset();
     s->ev_used = 0;
+    s->copy_ev_used = 0;
     memset(&s->st, 0, sizeof s->st);
     return HS_OK;
 }
@@ -359,10 +354,10 @@ template <class Rehash>
 int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint32_t &n_launches, Rehash &&rehash)
 {
     for (int round = 0; round < 40; round++) {
-        int rc = m.check(st);
+        int rc = m.sync_state(st);
         if (rc) return rc;
-        if (m.dirty) {  // overflow: too many distinct values below tau -> lower it and re-offer
-            const uint64_t nt = m.tau >> 4;
+        if (m.h_state->overflow) {  // too many distinct values below tau: lower it and re-offer
+            const uint64_t nt = m.h_state->tau >> 4;
             rc = m.reset(st, nt ? nt : 1, false);
             if (rc) return rc;
             m.passes++;
@@ -370,30 +365,32 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
             if (rc) return rc;
             continue;
         }
+        const uint64_t tau = m.h_state->tau;
+        const uint64_t *live = m.d_set[m.h_state->cur & 1u];
         // distinct values <= tau (older, larger ones may linger from before tau dropped)
-        uint64_t thr = m.tau;
+        uint64_t thr = tau;
         uint32_t M = 0;
         for (int iter = 0; iter < 64; iter++) {
-            CU(cudaMemsetAsync(m.d_ctl + 3, 0, sizeof(uint32_t), st));
-            CU(launch_mix_collect(m.d_set[m.cur], m.cap, thr, m.d_cand, m.cand_cap, m.d_ctl + 3, st));
+            CU(cudaMemsetAsync(m.field(offsetof(MixState, n_out)), 0, sizeof(uint32_t), st));
+            CU(launch_mix_collect(live, m.cap, thr, m.d_cand, m.cand_cap, m.field(offsetof(MixState, n_out)), st));
             n_launches++;
-            CU(cudaMemcpyAsync(m.h_ctl, m.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            M = m.h_ctl[3];
-            if (M <= m.cand_cap && (M >= m.s || thr == m.tau)) break;
+            rc = m.sync_state(st);
+            if (rc) return rc;
+            M = m.h_state->n_out;
+            if (M <= m.cand_cap && (M >= m.s || thr == tau)) break;
             if (M > m.cand_cap) {
                 // aim for ~1.5 s candidates assuming hashes are uniform below thr
                 const long double f = ((long double)m.s * 1.5L + 64.0L) / (long double)M;
                 thr = (uint64_t)((long double)thr * (f < 0.9L ? f : 0.9L));
             } else {
-                thr = (thr > m.tau / 2) ? m.tau : thr * 2;
+                thr = (thr > tau / 2) ? tau : thr * 2;
             }
         }
         if (M > m.cand_cap) return fail(HS_ECUDA, "mixture candidate selection did not converge");
-        if (M < m.s && m.tau != ~0ull) {
+        if (M < m.s && tau != ~0ull) {
             // complete below tau but fewer than s distinct values there (very repetitive
             // input): raise tau and re-offer everything
-            const uint64_t nt = (m.tau > (~0ull >> 4)) ? ~0ull : (m.tau << 4);
+            const uint64_t nt = (tau > (~0ull >> 4)) ? ~0ull : (tau << 4);
             rc = m.reset(st, nt, false);
             if (rc) return rc;
             m.passes++;
@@ -403,15 +400,15 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
         }
         out.clear();
         if (M) {
-            CU(launch_sort_unique(m.d_cand, M, m.d_scratch, m.d_ctl + 4, st));
+            CU(launch_sort_unique(m.d_cand, M, m.d_scratch, m.field(offsetof(MixState, n_unique)), st));
             n_launches++;
-            CU(cudaMemcpyAsync(m.h_ctl, m.d_ctl, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CU(cudaStreamSynchronize(st));
-            const uint32_t nu = std::min(m.h_ctl[4], m.s);
+            rc = m.sync_state(st);
+            if (rc) return rc;
+            const uint32_t nu = std::min(m.h_state->n_unique, m.s);
             out.resize(nu);
             CU(cudaMemcpy(out.data(), m.d_cand, (size_t)nu * 8, cudaMemcpyDeviceToHost));
         }
-        if (m.h_ctl[2] && out.size() < m.s) out.push_back(~0ull);  // hash == 2^64-1 present
+        if (m.h_state->has_max && out.size() < m.s) out.push_back(~0ull);  // hash == 2^64-1 present
         return HS_OK;
     }
     return fail(HS_ECUDA, "mixture threshold search did not settle");
@@ -586,6 +583,7 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
 #define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(HS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); return bail(HS_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
+    CUB(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUB(cudaMalloc((void **)&s->d_counts, E * 4));
     CUB(cudaMalloc((void **)&s->d_stats, 2 * ST_COUNT * sizeof(unsigned long long)));
     CUB(cudaMalloc((void **)&s->d_shared, N * 4));
@@ -623,6 +621,7 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     if (!s || !key) return fail(HS_EINVAL, "null argument");
     if (!strcmp(key, "filter")) s->filter = value != 0;
     else if (!strcmp(key, "chunk_bases")) s->chunk_text = value > 4096 ? (uint64_t)value : 4096;
+    else if (!strcmp(key, "piece_bases")) s->piece_positions = value > 8192 ? (uint64_t)value : 8192;
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
     else return fail(HS_EINVAL, std::string("unknown option ") + key);
     return HS_OK;
@@ -644,7 +643,8 @@ HS_API int hs_pack_text(const char *text, size_t n, uint64_t *seq2, uint32_t *in
 
 namespace {
 
-// copy a packed host chunk into the arena (padding flagged invalid) and launch
+// copy a packed host chunk into the arena (padding flagged invalid) and launch it, in
+// pieces: the copy of piece i+1 (copy stream) overlaps the kernel of piece i (compute stream)
 int feed_host_chunk(hs_screen *s, const uint64_t *seq, const uint32_t *inv, uint64_t n_bases, cudaEvent_t done_ev)
 {
     if (!n_bases) return HS_OK;
@@ -652,17 +652,35 @@ int feed_host_chunk(hs_screen *s, const uint64_t *seq, const uint32_t *inv, uint
     void *dseq = nullptr, *dinv = nullptr;
     CU(s->arena.alloc(alloc * 8, &dseq));
     CU(s->arena.alloc(alloc * 4, &dinv));
-    CU(cudaMemcpyAsync(dseq, seq, words * 8, cudaMemcpyHostToDevice, s->stream));
-    CU(cudaMemcpyAsync(dinv, inv, words * 4, cudaMemcpyHostToDevice, s->stream));
-    if (alloc > words) {
-        CU(cudaMemsetAsync((char *)dseq + words * 8, 0, (alloc - words) * 8, s->stream));
-        CU(cudaMemsetAsync((char *)dinv + words * 4, 0xFF, (alloc - words) * 4, s->stream));
-    }
-    if (done_ev) CU(cudaEventRecord(done_ev, s->stream));
-    s->st.h2d_bytes += words * 12;
     Chunk c{(const uint64_t *)dseq, (const uint32_t *)dinv, n_bases};
     s->chunks.push_back(c);
-    return launch_chunk(s, c, true, true);
+    s->st.h2d_bytes += words * 12;
+    const uint64_t piece_words = std::max<uint64_t>(kTileWords, s->piece_positions / 32 / kTileWords * kTileWords);
+    for (uint64_t w0 = 0; w0 < alloc; w0 += piece_words) {
+        const uint64_t w1 = std::min(alloc, w0 + piece_words);      // tile aligned
+        const uint64_t cw1 = std::min(words, w1);                   // words that exist in the host buffer
+        if (cw1 > w0) {
+            CU(cudaMemcpyAsync((char *)dseq + w0 * 8, seq + w0, (cw1 - w0) * 8, cudaMemcpyHostToDevice, s->copy_stream));
+            CU(cudaMemcpyAsync((char *)dinv + w0 * 4, inv + w0, (cw1 - w0) * 4, cudaMemcpyHostToDevice, s->copy_stream));
+        }
+        if (w1 > cw1) {
+            const uint64_t p0 = std::max(cw1, w0);
+            CU(cudaMemsetAsync((char *)dseq + p0 * 8, 0, (w1 - p0) * 8, s->copy_stream));
+            CU(cudaMemsetAsync((char *)dinv + p0 * 4, 0xFF, (w1 - p0) * 4, s->copy_stream));
+        }
+        if (s->copy_ev_used == s->copy_evs.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->copy_evs.push_back(e);
+        }
+        cudaEvent_t ev = s->copy_evs[s->copy_ev_used++];
+        CU(cudaEventRecord(ev, s->copy_stream));
+        CU(cudaStreamWaitEvent(s->stream, ev, 0));
+        int rc = launch_chunk(s, c, true, true, w0 / kTileWords, w1 / kTileWords);
+        if (rc) return rc;
+    }
+    if (done_ev) CU(cudaEventRecord(done_ev, s->copy_stream));  // the host buffer may be reused
+    return HS_OK;
 }
 
 int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
@@ -923,6 +941,8 @@ HS_API void hs_screen_free(hs_screen *s)
     if (s->red0) cudaEventDestroy(s->red0);
     if (s->red1) cudaEventDestroy(s->red1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
+    for (auto &e : s->copy_evs) cudaEventDestroy(e);
     delete s;
 }
 
@@ -1047,10 +1067,10 @@ int sketch_device(uint32_t k, uint32_t s_, uint32_t seed, const uint64_t *dseq, 
     Chunk c{dseq, dinv, n_bases};
     const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
     auto offer = [&]() -> int {
-        mix.before_launch(c.n_bases);
         StreamArgs a = base_args(c, k, seed, use64);
-        a.do_mix = 1; a.mix = mix.view(); a.stats = dst;
+        a.do_mix = 1; a.mix = mix.view(mix.launch_cap(c.n_bases)); a.stats = dst;
         CU(launch_stream(a, g_sm, 0));
+        CU(launch_mix_maintain(a.mix, 0));
         return HS_OK;
     };
     std::vector<uint64_t> out;

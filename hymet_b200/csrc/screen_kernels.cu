@@ -93,23 +93,23 @@ __device__ __forceinline__ uint32_t table_find(const TableView &t, uint64_t h, u
     return kNoEntry;
 }
 
-__device__ __forceinline__ void mix_insert(const MixView &m, uint64_t h)
+__device__ __forceinline__ void mix_insert(const MixView &m, uint64_t *set, uint64_t h)
 {
-    if (h == kEmptyKey) { atomicExch(m.has_max, 1u); return; }
+    if (h == kEmptyKey) { atomicExch(&m.st->has_max, 1u); return; }
     uint32_t slot = mixset_slot(h, m.mask);
     for (uint32_t tries = 0; tries <= m.mask; tries++) {
-        unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(m.set + slot));
+        unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(set + slot));
         if (cur == h) return;
         if (cur == kEmptyKey) {
-            if (__ldcg(m.count) >= m.limit) { atomicExch(m.overflow, 1u); return; }
-            cur = atomicCAS(reinterpret_cast<unsigned long long *>(m.set + slot), (unsigned long long)kEmptyKey,
+            if (__ldcg(&m.st->count) >= m.limit) { atomicExch(&m.st->overflow, 1u); return; }
+            cur = atomicCAS(reinterpret_cast<unsigned long long *>(set + slot), (unsigned long long)kEmptyKey,
                             (unsigned long long)h);
-            if (cur == kEmptyKey) { atomicAdd(m.count, 1u); return; }
+            if (cur == kEmptyKey) { atomicAdd(&m.st->count, 1u); return; }
             if (cur == h) return;
         }
         slot = (slot + 1) & m.mask;
     }
-    atomicExch(m.overflow, 1u);
+    atomicExch(&m.st->overflow, 1u);
 }
 
 // ---------------------------------------------------------------------------
@@ -165,8 +165,17 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
         bulk_g2s(&buf[b].inv[4 - iw], a.inv + (size_t)tile * kTileWords - iw, ibytes, &full[b]);
     };
 
+    // mixture threshold and live set come from device state (maintained between launches)
+    uint64_t mix_tau = 0;
+    uint64_t *mix_set = nullptr;
+    if (a.do_mix) {
+        const unsigned long long t = __ldcg(&a.mix.st->tau);
+        mix_tau = t < a.mix.tau_cap ? t : a.mix.tau_cap;
+        mix_set = a.mix.sets[__ldcg(&a.mix.st->cur) & 1u];
+    }
+
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
-    uint32_t tile = blockIdx.x, it = 0;
+    uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
         for (uint32_t p = 0; p < kPrefetch; p++)
             if ((uint64_t)tile + (uint64_t)p * gridDim.x < a.n_tiles) issue(tile + p * gridDim.x, p);
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
     for (; tile < a.n_tiles; tile += gridDim.x, it++) {
         if (tid == 0) {
             const uint32_t nt = it + kPrefetch;
-            const uint64_t ntile = (uint64_t)blockIdx.x + (uint64_t)nt * gridDim.x;
+            const uint64_t ntile = (uint64_t)a.tile_begin + blockIdx.x + (uint64_t)nt * gridDim.x;
             if (ntile < a.n_tiles) {
                 const uint32_t sb = nt % kStages;
                 if (nt >= kStages) mbar_wait(&empty[sb], ((nt / kStages) - 1u) & 1u);  // its previous tile was consumed
@@ -202,9 +211,9 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
                 a.emit_hash[pos0 + j] = h;
                 a.emit_valid[pos0 + j] = 1;
             }
-            if (a.do_mix && h <= a.mix.tau) {
+            if (a.do_mix && h <= mix_tau) {
                 n_mix++;
-                mix_insert(a.mix, h);
+                mix_insert(a.mix, mix_set, h);
             }
             if (a.do_count && (!a.do_filter || h <= a.tab.max_key)) {
                 n_probe++;
@@ -241,7 +250,7 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
         if (occ < 1) occ = 1;
     }
     uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
-    if (grid > a.n_tiles) grid = a.n_tiles;
+    if (grid > a.n_tiles - a.tile_begin) grid = a.n_tiles - a.tile_begin;
     if (!grid) return cudaSuccess;
     k_stream<KT><<<grid, kCtaThreads, 0, st>>>(a);
     return cudaGetLastError();
@@ -369,20 +378,56 @@ __global__ void k_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, u
     }
 }
 
-__global__ void k_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count)
+// ---- maintenance after every streaming launch (no host involvement) ----------
+__device__ __forceinline__ bool mix_needs_shrink(const MixView &v, unsigned long long &t)
 {
-    const uint32_t mask = cap - 1;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        const uint64_t v = src[i];
-        if (v == kEmptyKey || v > thr) continue;
-        uint32_t slot = mixset_slot(v, mask);
+    const MixState *st = v.st;
+    t = st->tau < v.tau_cap ? st->tau : v.tau_cap;
+    return !st->overflow && st->count > (v.mask + 1u) / 4u && (t >> 2) > 0;
+}
+
+__global__ void k_mix_clear_cond(const MixView v)
+{
+    unsigned long long t;
+    if (!mix_needs_shrink(v, t)) return;
+    uint64_t *dst = v.sets[(v.st->cur & 1u) ^ 1u];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= v.mask; i += gridDim.x * blockDim.x) dst[i] = kEmptyKey;
+}
+
+__global__ void k_mix_rebuild_cond(const MixView v)
+{
+    unsigned long long t;
+    if (!mix_needs_shrink(v, t)) return;
+    const uint64_t thr = t >> 2;
+    const uint64_t *src = v.sets[v.st->cur & 1u];
+    uint64_t *dst = v.sets[(v.st->cur & 1u) ^ 1u];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= v.mask; i += gridDim.x * blockDim.x) {
+        const uint64_t x = src[i];
+        if (x == kEmptyKey || x > thr) continue;
+        uint32_t slot = mixset_slot(x, v.mask);
         for (;;) {
             const unsigned long long cur = atomicCAS(reinterpret_cast<unsigned long long *>(dst + slot),
-                                                     (unsigned long long)kEmptyKey, (unsigned long long)v);
-            if (cur == kEmptyKey) { atomicAdd(count, 1u); break; }
-            slot = (slot + 1) & mask;
+                                                     (unsigned long long)kEmptyKey, (unsigned long long)x);
+            if (cur == kEmptyKey) { atomicAdd(&v.st->new_count, 1u); break; }
+            slot = (slot + 1) & v.mask;
         }
     }
+}
+
+__global__ void k_mix_apply(const MixView v)
+{
+    unsigned long long t;
+    const bool shrink = mix_needs_shrink(v, t);
+    MixState *st = v.st;
+    if (shrink) {
+        st->tau = t >> 2;
+        st->cur = (st->cur & 1u) ^ 1u;
+        st->count = st->new_count;
+        st->rebuilds++;
+    } else {
+        st->tau = t;
+    }
+    st->new_count = 0;
 }
 
 cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
@@ -391,10 +436,12 @@ cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, 
     k_mix_collect<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(set, cap, thr, out, out_cap, n_out);
     return cudaGetLastError();
 }
-cudaError_t launch_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count,
-                               cudaStream_t st)
+cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st)
 {
-    k_mix_rebuild<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(src, cap, thr, dst, count);
+    const uint32_t cap = v.mask + 1u;
+    k_mix_clear_cond<<<grid_for(cap, 256, 148 * 4), 256, 0, st>>>(v);
+    k_mix_rebuild_cond<<<grid_for(cap, 256, 148 * 4), 256, 0, st>>>(v);
+    k_mix_apply<<<1, 1, 0, st>>>(v);
     return cudaGetLastError();
 }
 

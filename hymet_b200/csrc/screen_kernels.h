@@ -23,21 +23,32 @@ struct TableView {
     uint32_t special;       // canonical entry id of key == kEmptyKey, or kNoEntry
 };
 
+// Mixture bottom-s state lives on the device so that streaming never waits for the host:
+// the threshold is lowered by a maintenance kernel after each chunk, not by a host check.
+struct MixState {
+    unsigned long long tau;  // accept h <= tau (min over launches of their caps, /4 per shrink)
+    uint32_t count;          // distinct values in sets[cur]
+    uint32_t new_count;      // scratch while rebuilding into sets[cur ^ 1]
+    uint32_t overflow;       // an insert was dropped: the set is incomplete below tau
+    uint32_t has_max;        // hash == kEmptyKey seen (only possible while tau == 2^64-1)
+    uint32_t cur;            // live set
+    uint32_t n_out, n_unique;  // finalisation scratch
+    uint32_t rebuilds;
+};
 struct MixView {
-    uint64_t *set;          // open addressing, capacity mask+1, kEmptyKey = free
+    uint64_t *sets[2];      // open addressing, capacity mask+1, kEmptyKey = free
     uint32_t mask;
     uint32_t limit;         // max distinct before `overflow` is raised
-    uint64_t tau;           // accept h <= tau
-    uint32_t *count;        // distinct inserted
-    uint32_t *overflow;
-    uint32_t *has_max;      // key == kEmptyKey seen (only possible when tau == max)
+    uint64_t tau_cap;       // this launch's cap: expected offers stay <= capacity/8
+    MixState *st;
 };
 
 struct StreamArgs {
     const uint64_t *seq;    // packed words (16-byte aligned), n_tiles * kTileWords allocated
     const uint32_t *inv;
     uint64_t n_bases;       // positions >= n_bases are invalid whatever inv says
-    uint32_t n_tiles;
+    uint32_t n_tiles;       // END tile (exclusive) of this launch
+    uint32_t tile_begin;    // first tile of this launch (> 0: a later piece of the same chunk, halo is real data)
     int k;
     uint32_t seed;
     int use64;
@@ -69,9 +80,9 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
 // copy keys <= thr from the set into out (append with atomic cursor); counts all <= thr
 cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
                                uint32_t *n_out, cudaStream_t st);
-// rebuild: insert every key <= thr of `src` into (empty) `dst`
-cudaError_t launch_mix_rebuild(const uint64_t *src, uint32_t cap, uint64_t thr, uint64_t *dst, uint32_t *count,
-                               cudaStream_t st);
+// after a streaming launch: fold its cap into tau and, if the live set is more than a
+// quarter full, rebuild it at tau/4 into the other buffer (exact: >= s smaller values stay)
+cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st);
 // sort ascending + unique in place (n <= cap_pow2 handled by padding); *n_unique out
 cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st);
 

@@ -335,13 +335,24 @@ def run_b200(args):
     # ---- e2e: FASTA text in pinned host memory -> TSV columns on the host --------------
     if not args.no_e2e:
         e_steps = max(1, min(args.steps, 3))
+        # three ways to get FASTA text into HBM (option "ingest"): host AVX2 packer threads,
+        # device parser fed by DMA of the raw text, or both competing for chunks (the default)
+        modes = {}
+        for mode, name in ((0, "host_packer"), (1, "device_parser"), (2, "hybrid")):
+            scr.set_option("ingest", mode)
+            mms, _, mstats, mres, _ = timed(step_text, e_steps, 2)
+            modes[name] = {"value": e_steps * total_bases / (mms * 1e-3) / 1e6, "ms_per_step": mms / e_steps,
+                           "h2d_bytes_per_step": int(mstats[-1]["h2d_bytes"]),
+                           "ok": bool(mres.shared.tolist() == res.shared.tolist() and mres.set_size == res.set_size)}
+        scr.set_option("ingest", 2)
         ems, ewall, estats, eres, _ = timed(step_text, e_steps, 1)
         est = estats[-1]
         e_val = e_steps * total_bases / (ems * 1e-3) / 1e6
         line["e2e"] = {"value": e_val, "unit": UNIT, "h2d_bytes_per_step": int(est["h2d_bytes"]),
                        "d2h_bytes_per_step": int(est["d2h_bytes"]), "ms_per_step": ems / e_steps,
                        "input": "FASTA text (%d B per GPU, 80-column lines) in pinned host memory" % wl.fasta.numel(),
-                       "host_threads_per_gpu": host_threads, "steps": e_steps,
+                       "host_threads_per_gpu": host_threads, "steps": e_steps, "ingest": "hybrid (default)",
+                       "ingest_modes": modes,
                        "host_wall_ms_reset_feed_finish": text_wall["steps"][-e_steps:],
                        "stream_kernel_ms_per_step": est["ms_stream"], "launches_per_step": est["n_launches"],
                        "includes": "host FASTA parse + 2-bit pack, H2D, all kernels, D2H of the result columns"}

@@ -76,6 +76,8 @@ SIGNATURES = {
     "hs_packed_words": (C.c_uint64, [C.c_uint64]),
     "hs_pack_text": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, u64p,
                                C.POINTER(Stats)]),
+    "hs_pack_text_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, u64p,
+                                      C.POINTER(Stats)]),
     "hs_screen_flush": (C.c_int, [C.c_void_p]),
     "hs_screen_counts_devptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "hs_screen_mixture_get": (C.c_int, [C.c_void_p, u64p, u32p]),

@@ -95,7 +95,86 @@ struct Arena {
 struct Chunk {
     const uint64_t *d_seq;
     const uint32_t *d_inv;
-    uint64_t n_bases;
+    uint64_t n_bases;                                // exact, or an upper bound when n_dev is set
+    const unsigned long long *n_dev = nullptr;       // device-parsed chunk: true length lives in HBM
+};
+
+// ---- device-side FASTA ingest: raw text slots + scan scratch ------------------------
+struct Ingest {
+    static constexpr int kSlots = 3;
+    struct Slot { uint8_t *raw = nullptr, *codes = nullptr; size_t cap = 0; cudaEvent_t done = nullptr, copied = nullptr; };
+    Slot slots[kSlots];
+    int next = 0;
+    FaScratch sc{};
+    size_t tile_cap = 0;
+    std::vector<unsigned long long *> counter_blocks;   // per-chunk position counters (512 per block)
+    size_t counters_used = 0;
+    unsigned long long *d_totals = nullptr;             // [0] positions [1] bases [2] records
+    bool ready = false;
+
+    int ensure(size_t bytes)
+    {
+        if (!ready) {
+            CU(cudaMalloc((void **)&d_totals, 4 * sizeof(unsigned long long)));
+            CU(cudaMemset(d_totals, 0, 4 * sizeof(unsigned long long)));
+            for (auto &sl : slots) {
+                CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming | cudaEventBlockingSync));
+                CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
+            }
+            ready = true;
+        }
+        const size_t tiles = (bytes + kFaTileBytes - 1) / kFaTileBytes + 1;
+        if (tiles > tile_cap) {
+            cudaDeviceSynchronize();
+            cudaFree(sc.tile_event); cudaFree(sc.tile_carry); cudaFree(sc.tile_event_b); cudaFree(sc.tile_carry_b);
+            cudaFree(sc.tile_count); cudaFree(sc.tile_offset);
+            tile_cap = tiles + tiles / 4;
+            CU(cudaMalloc((void **)&sc.tile_event, tile_cap * 4));
+            CU(cudaMalloc((void **)&sc.tile_carry, tile_cap * 4));
+            CU(cudaMalloc((void **)&sc.tile_event_b, tile_cap * 4));
+            CU(cudaMalloc((void **)&sc.tile_carry_b, tile_cap * 4));
+            CU(cudaMalloc((void **)&sc.tile_count, tile_cap * 4));
+            CU(cudaMalloc((void **)&sc.tile_offset, tile_cap * 8));
+        }
+        sc.totals = d_totals;
+        return HS_OK;
+    }
+    int slot_for(size_t bytes, Slot **out)
+    {
+        Slot &sl = slots[next];
+        next = (next + 1) % kSlots;
+        CU(cudaEventSynchronize(sl.done));  // throttle: at most kSlots chunks of raw text in flight
+        if (sl.cap < bytes) {
+            cudaFree(sl.raw); cudaFree(sl.codes);
+            sl.cap = bytes + bytes / 8 + 64;
+            CU(cudaMalloc((void **)&sl.raw, sl.cap));
+            CU(cudaMalloc((void **)&sl.codes, sl.cap));
+        }
+        *out = &sl;
+        return HS_OK;
+    }
+    int counter(unsigned long long **out)
+    {
+        if (counters_used == counter_blocks.size() * 512) {
+            unsigned long long *b = nullptr;
+            CU(cudaMalloc((void **)&b, 512 * sizeof(unsigned long long)));
+            counter_blocks.push_back(b);
+        }
+        *out = counter_blocks[counters_used / 512] + counters_used % 512;
+        counters_used++;
+        return HS_OK;
+    }
+    void release()
+    {
+        for (auto &sl : slots) {
+            cudaFree(sl.raw); cudaFree(sl.codes);
+            if (sl.done) cudaEventDestroy(sl.done);
+            if (sl.copied) cudaEventDestroy(sl.copied);
+        }
+        cudaFree(sc.tile_event); cudaFree(sc.tile_carry); cudaFree(sc.tile_event_b); cudaFree(sc.tile_carry_b);
+        cudaFree(sc.tile_count); cudaFree(sc.tile_offset); cudaFree(d_totals);
+        for (auto *b : counter_blocks) cudaFree(b);
+    }
 };
 
 // ---- mixture bottom-s engine (K3 control logic) --------------------------------
@@ -204,6 +283,8 @@ struct hs_screen {
     std::vector<cudaEvent_t> copy_evs;
     size_t copy_ev_used = 0;
     uint64_t piece_positions = (uint64_t)32 << 20;  // packed host feeds are uploaded + launched in pieces
+    Ingest ingest;
+    int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
     uint32_t *d_counts = nullptr;
     unsigned long long *d_stats = nullptr;
     MixEngine mix;
@@ -305,6 +386,7 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
     if (tiles_for(c.n_bases) > 0xFFFFFFFFull) return fail(HS_EINVAL, "chunk too large");
     if (!tile_end) tile_end = tiles_for(c.n_bases);
     StreamArgs a = base_args(c, s->db->k, s->db->seed, s->db->use64);
+    a.n_bases_dev = c.n_dev;
     a.tile_begin = (uint32_t)tile_begin; a.n_tiles = (uint32_t)tile_end;
     a.do_count = count; a.do_filter = s->filter; a.do_mix = mix;
     a.tab = s->db->view(); a.counts = s->d_counts;
@@ -325,7 +407,8 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
         CU(launch_mix_maintain(a.mix, s->stream));
         s->st.n_launches += 3;
     }
-    s->st.n_positions += std::min<uint64_t>(c.n_bases, tile_end * kTileWords * 32) - tile_begin * kTileWords * 32;
+    if (!c.n_dev)  // device-parsed chunks are accounted from the parser's own totals at flush
+        s->st.n_positions += std::min<uint64_t>(c.n_bases, tile_end * kTileWords * 32) - tile_begin * kTileWords * 32;
     return HS_OK;
 }
 
@@ -343,6 +426,8 @@ int screen_zero(hs_screen *s)
     s->arena.reset();
     s->ev_used = 0;
     s->copy_ev_used = 0;
+    s->ingest.counters_used = 0;
+    if (s->ingest.ready) CU(cudaMemsetAsync(s->ingest.d_totals, 0, 4 * sizeof(unsigned long long), s->stream));
     memset(&s->st, 0, sizeof s->st);
     return HS_OK;
 }
@@ -622,6 +707,7 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     if (!strcmp(key, "filter")) s->filter = value != 0;
     else if (!strcmp(key, "chunk_bases")) s->chunk_text = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "piece_bases")) s->piece_positions = value > 8192 ? (uint64_t)value : 8192;
+    else if (!strcmp(key, "ingest")) s->ingest_mode = (int)value;
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
     else return fail(HS_EINVAL, std::string("unknown option ") + key);
     return HS_OK;
@@ -683,15 +769,68 @@ int feed_host_chunk(hs_screen *s, const uint64_t *seq, const uint32_t *inv, uint
     return HS_OK;
 }
 
+// Row a6 on the GPU: upload one record-aligned span of raw FASTA text, parse + pack it on
+// the device, stream it.  Everything is enqueued; the host only waits for a free slot.
+int feed_span_device(hs_screen *s, const char *text, size_t len)
+{
+    if (!len) return HS_OK;
+    if (len >= ((size_t)1 << 30)) return fail(HS_EINVAL, "text chunk too large for the device parser");
+    Ingest &in = s->ingest;
+    Ingest::Slot *sl = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        int rc = in.ensure(len);
+        if (rc) return rc;
+    }
+    int rc = in.slot_for(len, &sl);   // may wait for the GPU (outside the lock)
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(s->mu);
+    unsigned long long *d_npos = nullptr;
+    rc = in.counter(&d_npos);
+    if (rc) return rc;
+    const uint64_t alloc = hs_packed_words(len);      // positions <= bytes
+    void *dseq = nullptr, *dinv = nullptr;
+    CU(s->arena.alloc(alloc * 8, &dseq));
+    CU(s->arena.alloc(alloc * 4, &dinv));
+    CU(cudaMemcpyAsync(sl->raw, text, len, cudaMemcpyHostToDevice, s->copy_stream));
+    CU(cudaEventRecord(sl->copied, s->copy_stream));
+    CU(cudaStreamWaitEvent(s->stream, sl->copied, 0));
+    FaScratch sc = in.sc;
+    sc.chunk_positions = d_npos;
+    CU(launch_fasta_to_codes(sl->raw, (uint32_t)len, sl->codes, sc, s->stream));
+    CU(launch_pack_codes_dyn(sl->codes, d_npos, (uint64_t *)dseq, (uint32_t *)dinv, alloc, s->stream));
+    CU(cudaEventRecord(sl->done, s->stream));
+    s->st.n_launches += 7;
+    s->st.h2d_bytes += len;
+    Chunk c{(const uint64_t *)dseq, (const uint32_t *)dinv, (uint64_t)len, d_npos};
+    s->chunks.push_back(c);
+    return launch_chunk(s, c, true, true);
+}
+
+bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
 {
     if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
-    if (threads < 1) threads = 1;
+    if (threads < 0) threads = 0;
     if (threads > 64) threads = 64;
     const int parts = (int)std::min<uint64_t>(1u << 20, n / s->chunk_text + 1);
     auto spans = split_records(text, n, parts, 1 << 16);
+    // the device parser handles FASTA ('>' records) whose text the DMA engine can read directly
+    size_t first = 0;
+    while (first < n && (text[first] == '\n' || text[first] == '\r')) first++;
+    const bool fasta = first < n && text[first] != '@';
+    const bool device_ok = fasta && s->ingest_mode != 0 && is_pinned_host(text) && is_pinned_host(text + n - 1);
+    const bool use_device = device_ok;
+    if (s->ingest_mode == 1 && device_ok) threads = 0;          // device parser only
+    if (!use_device && threads < 1) threads = 1;
     if ((int)spans.size() < threads) threads = (int)spans.size();
-    if (threads < 1) return HS_OK;
+    if (spans.empty()) return HS_OK;
     // two staging buffers per packer thread (pinned), reused through events
     const size_t need = (size_t)threads * 2;
     while (s->staging.size() < need) {
@@ -745,10 +884,30 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
             }
         }
     };
-    if (threads == 1) {
+    // the device-ingest worker competes with the packer threads for spans: it costs no CPU
+    // (one cudaMemcpyAsync + kernel launches per span) and is throttled by its raw-text slots
+    auto device_worker = [&]() {
+        cudaSetDevice(g_device);
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= spans.size() || rc_all.load() != HS_OK) break;
+            const double t0 = now_s();
+            int rc = feed_span_device(s, text + spans[i].first, spans[i].second - spans[i].first);
+            if (g_debug_timing)
+                fprintf(stderr, "[hs] span %zu device-ingest: %zu B enqueue+wait %.2f ms\n", i,
+                        spans[i].second - spans[i].first, 1e3 * (now_s() - t0));
+            if (rc != HS_OK) {
+                std::lock_guard<std::mutex> lk(err_mu);
+                if (rc_all.load() == HS_OK) { rc_all = rc; err_all = g_err; }
+                break;
+            }
+        }
+    };
+    if (threads == 1 && !use_device) {
         worker(0);
     } else {
         std::vector<std::thread> pool;
+        if (use_device) pool.emplace_back(device_worker);
         for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
         for (auto &th : pool) th.join();
     }
@@ -809,7 +968,7 @@ HS_API int hs_screen_flush(hs_screen *s)
         for (const Chunk &c : s->chunks) {
             int r = launch_chunk(s, c, false, true);
             if (r) return r;
-            s->st.n_positions -= c.n_bases;  // a mixture-only second pass is not new input
+            if (!c.n_dev) s->st.n_positions -= c.n_bases;  // a mixture-only second pass is not new input
         }
         return HS_OK;
     });
@@ -818,6 +977,12 @@ HS_API int hs_screen_flush(hs_screen *s)
     unsigned long long h[ST_COUNT];
     CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (s->ingest.ready && s->ingest.counters_used) {
+        unsigned long long t[4];
+        CU(cudaMemcpy(t, s->ingest.d_totals, sizeof t, cudaMemcpyDeviceToHost));
+        s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2];
+        CU(cudaMemsetAsync(s->ingest.d_totals, 0, sizeof t, s->stream));  // folded: do not fold twice
+    }
     s->st.n_valid_kmers = h[ST_VALID]; s->st.n_probes = h[ST_PROBES]; s->st.n_bucket_reads = h[ST_BUCKETS];
     s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
     s->st.n_mix_passes = s->mix.passes;
@@ -932,6 +1097,7 @@ HS_API void hs_screen_free(hs_screen *s)
     cudaFree(s->d_identity); cudaFree(s->d_pvalue); cudaFree(s->d_best_score); cudaFree(s->d_best_len); cudaFree(s->d_winner);
     s->mix.destroy();
     s->arena.release();
+    s->ingest.release();
     for (auto &g : s->staging) {
         if (g.seq) cudaFreeHost(g.seq);
         if (g.inv) cudaFreeHost(g.inv);
@@ -981,6 +1147,45 @@ HS_API int hs_hash_packed(uint32_t k, uint32_t seed, const uint64_t *seq2, const
     CU(cudaMemcpy(out_valid, dv, n_bases, cudaMemcpyDeviceToHost));
     cudaFree(dseq); cudaFree(dinv); cudaFree(dh); cudaFree(dv); cudaFree(dst);
     return HS_OK;
+}
+
+HS_API int hs_pack_text_device(const char *text, size_t n, uint64_t *seq2, uint32_t *inv, uint64_t cap_words,
+                               uint64_t *n_bases, hs_stats_t *stats)
+{
+    if ((!text && n) || !seq2 || !inv || !n_bases) return fail(HS_EINVAL, "null argument");
+    if (n >= ((size_t)1 << 30)) return fail(HS_EINVAL, "text too large for one device-parser chunk");
+    NEED_DEVICE();
+    *n_bases = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (!n) return HS_OK;
+    const uint64_t alloc = hs_packed_words(n);
+    Ingest in;
+    int rc = in.ensure(n);
+    if (rc) return rc;
+    uint8_t *raw = nullptr, *codes = nullptr;
+    uint64_t *dseq = nullptr;
+    uint32_t *dinv = nullptr;
+    unsigned long long *d_npos = nullptr, tot[4] = {0, 0, 0, 0};
+    CU(cudaMalloc((void **)&raw, n + 64)); CU(cudaMalloc((void **)&codes, n + 64));
+    CU(cudaMalloc((void **)&dseq, alloc * 8)); CU(cudaMalloc((void **)&dinv, alloc * 4));
+    CU(cudaMalloc((void **)&d_npos, sizeof(unsigned long long)));
+    CU(cudaMemcpy(raw, text, n, cudaMemcpyHostToDevice));
+    FaScratch sc = in.sc;
+    sc.chunk_positions = d_npos;
+    CU(launch_fasta_to_codes(raw, (uint32_t)n, codes, sc, 0));
+    CU(launch_pack_codes_dyn(codes, d_npos, dseq, dinv, alloc, 0));
+    CU(cudaMemcpy(tot, in.d_totals, sizeof tot, cudaMemcpyDeviceToHost));
+    const uint64_t words = (tot[0] + 31) / 32;
+    if (words > cap_words) rc = fail(HS_EINVAL, "output capacity too small");
+    if (rc == HS_OK && words) {
+        CU(cudaMemcpy(seq2, dseq, words * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(inv, dinv, words * 4, cudaMemcpyDeviceToHost));
+    }
+    *n_bases = tot[0];
+    if (stats) { stats->n_positions = tot[0]; stats->n_bases = tot[1]; stats->n_records = tot[2]; }
+    cudaFree(raw); cudaFree(codes); cudaFree(dseq); cudaFree(dinv); cudaFree(d_npos);
+    in.release();
+    return rc;
 }
 
 HS_API int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *out_entry)

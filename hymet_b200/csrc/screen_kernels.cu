@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
         mix_set = a.mix.sets[__ldcg(&a.mix.st->cur) & 1u];
     }
 
+    const uint64_t n_bases = a.n_bases_dev ? (uint64_t)__ldcg(a.n_bases_dev) : a.n_bases;
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
@@ -199,8 +200,8 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
 
         if (tile == 0 && tid == 0) { prev = 0; iprev = ~0u; }
         const uint64_t pos0 = ((uint64_t)tile * kTileWords + tid) * kBasesPerWord;
-        if (pos0 + kBasesPerWord > a.n_bases) {
-            const uint32_t nv = pos0 >= a.n_bases ? 0u : (uint32_t)(a.n_bases - pos0);
+        if (pos0 + kBasesPerWord > n_bases) {
+            const uint32_t nv = pos0 >= n_bases ? 0u : (uint32_t)(n_bases - pos0);
             icur |= nv ? ((1u << (32 - nv)) - 1u) : ~0u;
         }
         if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
@@ -777,6 +778,279 @@ cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, u
 {
     if (!n_words_alloc) return cudaSuccess;
     k_pack_codes<<<grid_for(n_words_alloc, 256, 148 * 16), 256, 0, st>>>(codes, n, seq, inv, n_words_alloc);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_pack_codes_dyn(const uint8_t *codes, const unsigned long long *n_dev,
+                                                        uint64_t *seq, uint32_t *inv, uint64_t n_words)
+{
+    const uint64_t n = __ldcg(n_dev);
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t p0 = w * 32;
+        uint64_t acc = 0;
+        uint32_t bad = 0;
+        if (p0 + 32 <= n) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(codes + p0));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(codes + p0) + 1);
+            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = (v[i] >> (8 * j)) & 0xFFu;
+                    acc = (acc << 2) | (c & 3u);
+                    bad = (bad << 1) | (c > 3u);
+                }
+            }
+        } else if (p0 < n) {
+            for (int j = 0; j < 32; j++) {
+                const uint64_t p = p0 + j;
+                const uint32_t c = p < n ? codes[p] : 4u;
+                acc = (acc << 2) | (c & 3u);
+                bad = (bad << 1) | (c > 3u);
+            }
+        } else {
+            bad = ~0u;
+        }
+        seq[w] = acc;
+        inv[w] = bad;
+    }
+}
+
+cudaError_t launch_pack_codes_dyn(const uint8_t *codes, const unsigned long long *n_dev, uint64_t *seq, uint32_t *inv,
+                                  uint64_t n_words_alloc, cudaStream_t st)
+{
+    if (!n_words_alloc) return cudaSuccess;
+    k_pack_codes_dyn<<<grid_for(n_words_alloc, 256, 148 * 16), 256, 0, st>>>(codes, n_dev, seq, inv, n_words_alloc);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Device-side FASTA ingest.  "Events" are the two things that change the parser
+// state: a header start ('>' as first byte of a line) and a newline.  A byte is
+// inside a header iff the latest event at or before it is a header start, so the
+// parser state is a prefix MAX of event codes and output positions are a prefix SUM
+// -- both done as tile aggregate -> single-CTA scan -> tile re-walk.
+// Same output as fasta_pack.cpp: header => one invalid position, CR before LF dropped,
+// every other byte of a sequence line kept (non-ACGT => code 4).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fa_code(uint32_t c)
+{
+    const uint32_t u = c & 0xDFu;  // fold case (S3)
+    return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+}
+
+struct FaThread {
+    uint8_t b[32];
+    uint32_t prev, next;  // bytes around the thread's 32 ('\n' before the text, '\n' after it)
+    uint32_t i0, n_here;  // first byte index, bytes that exist (0..32)
+};
+
+__device__ __forceinline__ void fa_load(const uint8_t *text, uint32_t n, uint32_t i0, FaThread &t)
+{
+    t.i0 = i0;
+    t.n_here = i0 >= n ? 0u : min(32u, n - i0);
+    if (t.n_here == 32 && ((uintptr_t)(text + i0) & 15) == 0) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + i0));
+        const uint4 c = __ldg(reinterpret_cast<const uint4 *>(text + i0) + 1);
+        const uint32_t v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int i = 0; i < 32; i++) t.b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) t.b[i] = (uint32_t)i < t.n_here ? text[i0 + i] : (uint8_t)'\n';
+    }
+    t.prev = i0 == 0 ? (uint32_t)'\n' : (i0 <= n ? (uint32_t)text[i0 - 1] : (uint32_t)'\n');
+    t.next = i0 + 32 < n ? (uint32_t)text[i0 + 32] : (uint32_t)'\n';
+}
+
+// Two event streams, each "latest event wins" (codes grow with the byte index; +2 so 0 = none):
+//   A: newline (even) / header start (odd)      -> inside a header line iff latest A is odd
+//   B: header start (even) / '+' line start (odd) -> skipping until the next header iff latest B
+//      is odd.  B starts odd: everything before the first header is skipped, like the host
+//      packer's SEEK_HDR state; a '+' line ends a record's sequence (kseq's quality marker).
+__device__ __forceinline__ void fa_last_events(const FaThread &t, uint32_t &eva, uint32_t &evb)
+{
+    uint32_t p = t.prev;
+    eva = 0; evb = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if ((uint32_t)i < t.n_here) {
+            const uint32_t c = t.b[i], idx = t.i0 + i;
+            if (c == '\n') eva = 2u * idx + 2u;
+            else if (p == '\n' && c == '>') { eva = 2u * idx + 3u; evb = 2u * idx + 2u; }
+            else if (p == '\n' && c == '+') evb = 2u * idx + 3u;
+            p = c;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t block_excl_max(uint32_t v, uint32_t *warp_buf, uint32_t &total)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc = max(inc, t);
+    }
+    uint32_t excl = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) excl = 0;
+    __syncthreads();
+    if (lane == 31) warp_buf[wid] = inc;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; w++) {
+        const uint32_t x = warp_buf[w];
+        if (w < wid) before = max(before, x);
+        tot = max(tot, x);
+    }
+    total = tot;
+    return max(before, excl);
+}
+
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t *warp_buf, uint32_t &total)
+{
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_buf[wid] = inc;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; w++) {
+        const uint32_t x = warp_buf[w];
+        if (w < wid) before += x;
+        tot += x;
+    }
+    total = tot;
+    return before + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_fa_events(const uint8_t *text, uint32_t n, uint32_t *tile_event_a,
+                                                   uint32_t *tile_event_b)
+{
+    __shared__ uint32_t wb[8];
+    FaThread t;
+    fa_load(text, n, blockIdx.x * kFaTileBytes + threadIdx.x * 32, t);
+    uint32_t ea, eb, ta, tb;
+    fa_last_events(t, ea, eb);
+    block_excl_max(ea, wb, ta);
+    block_excl_max(eb, wb, tb);
+    if (threadIdx.x == 0) { tile_event_a[blockIdx.x] = ta; tile_event_b[blockIdx.x] = tb; }
+}
+
+// single CTA: exclusive prefix max (mode 0, 32-bit) or exclusive prefix sum (mode 1, 64-bit out)
+__global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *in, uint32_t n, uint32_t *out_max, uint64_t *out_sum,
+                                                    unsigned long long *total_out, uint32_t init)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = init;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < n ? in[i] : 0ull;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc = out_max ? max(inc, t) : inc + t;
+        }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        unsigned long long before = carry_s;
+        for (uint32_t w = 0; w < wid; w++) before = out_max ? max(before, wsum[w]) : before + wsum[w];
+        unsigned long long excl = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) excl = 0;
+        const unsigned long long e = out_max ? max(before, excl) : before + excl;
+        if (i < n) {
+            if (out_max) out_max[i] = (uint32_t)e; else out_sum[i] = e;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = out_max ? max(e, v) : e + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
+}
+
+// walk the thread's bytes with the parser state; MODE 0: count emitted positions,
+// MODE 1: write codes at out[base + ...]
+template <int MODE>
+__global__ void __launch_bounds__(256) k_fa_walk(const uint8_t *text, uint32_t n, const uint32_t *tile_carry_a,
+                                                 const uint32_t *tile_carry_b, uint32_t *tile_count,
+                                                 const uint64_t *tile_offset, uint8_t *codes, unsigned long long *totals)
+{
+    __shared__ uint32_t wb[8];
+    FaThread t;
+    fa_load(text, n, blockIdx.x * kFaTileBytes + threadIdx.x * 32, t);
+    uint32_t ea, eb, tot_ev;
+    fa_last_events(t, ea, eb);
+    const uint32_t carry_a = max(tile_carry_a[blockIdx.x], block_excl_max(ea, wb, tot_ev));
+    const uint32_t carry_b = max(tile_carry_b[blockIdx.x], block_excl_max(eb, wb, tot_ev));
+    bool in_header = (carry_a & 1u) != 0;  // latest of {newline, header start} is a header start
+    bool in_skip = (carry_b & 1u) != 0;    // latest of {header start, '+' line} is a '+' line (or nothing yet)
+    uint32_t emit_mask = 0, sep_mask = 0, p = t.prev;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        if ((uint32_t)i < t.n_here) {
+            const uint32_t c = t.b[i];
+            const uint32_t nxt = i < 31 ? ((uint32_t)(i + 1) < t.n_here ? (uint32_t)t.b[i + 1] : (uint32_t)'\n') : t.next;
+            if (c == '\n') {
+                in_header = false;
+            } else if (p == '\n' && c == '>') {
+                in_header = true; in_skip = false;
+                emit_mask |= 1u << i; sep_mask |= 1u << i;  // one separator per record (S6)
+            } else if (p == '\n' && c == '+') {
+                in_skip = true;
+            } else if (!in_header && !in_skip && !(c == '\r' && nxt == '\n')) {
+                emit_mask |= 1u << i;
+            }
+            p = c;
+        }
+    }
+    uint32_t tile_total;
+    const uint32_t local = block_excl_sum(__popc(emit_mask), wb, tile_total);
+    if (MODE == 0) {
+        if (threadIdx.x == 0) tile_count[blockIdx.x] = tile_total;
+        const uint32_t nsep = __popc(sep_mask);
+        uint32_t bases = __popc(emit_mask) - nsep, recs = nsep;
+        bases = warp_sum(bases); recs = warp_sum(recs);
+        if ((threadIdx.x & 31) == 0) {
+            if (bases) atomicAdd(totals + 1, (unsigned long long)bases);
+            if (recs) atomicAdd(totals + 2, (unsigned long long)recs);
+        }
+    } else {
+        uint8_t *out = codes + tile_offset[blockIdx.x] + local;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            if (emit_mask & (1u << i)) *out++ = (sep_mask & (1u << i)) ? (uint8_t)4 : (uint8_t)fa_code(t.b[i]);
+        }
+    }
+}
+
+__global__ void k_fa_totals(const unsigned long long *chunk_positions, unsigned long long *totals)
+{
+    totals[0] += *chunk_positions;
+}
+
+cudaError_t launch_fasta_to_codes(const uint8_t *text, uint32_t n, uint8_t *codes, const FaScratch &sc, cudaStream_t st)
+{
+    if (!n) return cudaMemsetAsync(sc.chunk_positions, 0, sizeof(unsigned long long), st);
+    const uint32_t tiles = (n + kFaTileBytes - 1) / kFaTileBytes;
+    k_fa_events<<<tiles, 256, 0, st>>>(text, n, sc.tile_event, sc.tile_event_b);
+    k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_event, tiles, sc.tile_carry, nullptr, nullptr, 0u);
+    k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_event_b, tiles, sc.tile_carry_b, nullptr, nullptr, 1u);
+    k_fa_walk<0><<<tiles, 256, 0, st>>>(text, n, sc.tile_carry, sc.tile_carry_b, sc.tile_count, nullptr, nullptr, sc.totals);
+    k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_count, tiles, nullptr, sc.tile_offset, sc.chunk_positions, 0u);
+    k_fa_walk<1><<<tiles, 256, 0, st>>>(text, n, sc.tile_carry, sc.tile_carry_b, nullptr, sc.tile_offset, codes, nullptr);
+    k_fa_totals<<<1, 1, 0, st>>>(sc.chunk_positions, sc.totals);
     return cudaGetLastError();
 }
 

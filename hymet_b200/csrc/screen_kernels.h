@@ -47,6 +47,7 @@ struct StreamArgs {
     const uint64_t *seq;    // packed words (16-byte aligned), n_tiles * kTileWords allocated
     const uint32_t *inv;
     uint64_t n_bases;       // positions >= n_bases are invalid whatever inv says
+    const unsigned long long *n_bases_dev;  // if set, the length is read from HBM (device-parsed chunks)
     uint32_t n_tiles;       // END tile (exclusive) of this launch
     uint32_t tile_begin;    // first tile of this launch (> 0: a later piece of the same chunk, halo is real data)
     int k;
@@ -102,4 +103,26 @@ cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32
 cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t n_words_alloc,
                               cudaStream_t st);
 
+}  // namespace hs
+
+// ---- device-side FASTA ingest (row a6 on the GPU) --------------------------------
+// Raw FASTA bytes in HBM -> base codes (0..3, 4 = invalid / record separator), compacted:
+// headers and line ends removed, one separator per record, exactly like fasta_pack.cpp.
+namespace hs {
+constexpr int kFaTileBytes = 8192;   // 256 threads x 32 bytes
+struct FaScratch {
+    uint32_t *tile_event;   // per tile: its last newline/header-start event code (0 = none)
+    uint32_t *tile_carry;   // exclusive prefix max of tile_event
+    uint32_t *tile_event_b; // per tile: its last header-start/'+'-line event code
+    uint32_t *tile_carry_b; // exclusive prefix max of tile_event_b, seeded "skipping"
+    uint32_t *tile_count;   // per tile: positions emitted
+    uint64_t *tile_offset;  // exclusive prefix sum of tile_count
+    unsigned long long *totals;  // [0] positions, [1] sequence bases, [2] records  (accumulated)
+    unsigned long long *chunk_positions;  // positions of THIS chunk (read by the pack/stream launches)
+};
+// text: n bytes (n < 2^30) starting at a record header; codes: capacity >= n
+cudaError_t launch_fasta_to_codes(const uint8_t *text, uint32_t n, uint8_t *codes, const FaScratch &sc, cudaStream_t st);
+// k_pack_codes / k_stream variants whose length comes from device memory (no host sync)
+cudaError_t launch_pack_codes_dyn(const uint8_t *codes, const unsigned long long *n_dev, uint64_t *seq, uint32_t *inv,
+                                  uint64_t n_words_alloc, cudaStream_t st);
 }  // namespace hs

@@ -242,6 +242,18 @@ def pack_text(text: bytes):
     return seq[:words], inv[:words], int(n.value), st.asdict()
 
 
+def pack_text_device(text: bytes, device: int = 0):
+    """Device FASTA parser alone: same outputs as pack_text()."""
+    _abi.init(device)
+    cap = packed_words(len(text)) + 4
+    seq = np.zeros(cap, np.uint64); inv = np.zeros(cap, np.uint32)
+    n = C.c_uint64(); st = _abi.Stats()
+    check(_abi.load().hs_pack_text_device(text, len(text), C.c_void_p(seq.ctypes.data), C.c_void_p(inv.ctypes.data), cap,
+                                          C.byref(n), C.byref(st)))
+    words = (n.value + 31) // 32
+    return seq[:words], inv[:words], int(n.value), st.asdict()
+
+
 def hash_packed(k: int, seed: int, seq2: np.ndarray, inv: np.ndarray, n_bases: int, device: int = 0):
     """K1 alone: (hash, valid) indexed by the position of each k-mer's last base."""
     _abi.init(device)

@@ -129,6 +129,14 @@ uint64_t hs_packed_words(uint64_t n_bases);
 int hs_pack_text(const char *text, size_t n, uint64_t *seq2, uint32_t *inv, uint64_t cap_words,
                  uint64_t *n_bases, hs_stats_t *stats);
 
+/* Device parser alone (row a6 on the GPU): same contract and same output as hs_pack_text,
+ * computed by the FASTA-ingest kernels ('>' records only; FASTQ goes through the host
+ * packer).  Used by the parity tests; the streaming path calls the same kernels when
+ * hs_screen_feed_text is given pinned host memory (option "ingest": 0 host packer,
+ * 1 device parser, 2 both compete for chunks -- default). */
+int hs_pack_text_device(const char *text, size_t n, uint64_t *seq2, uint32_t *inv, uint64_t cap_words,
+                        uint64_t *n_bases, hs_stats_t *stats);
+
 /* rows a8-a10 complete: wait for the stream, settle the local mixture bottom-s. */
 int hs_screen_flush(hs_screen *s);
 

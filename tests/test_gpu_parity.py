@@ -111,6 +111,56 @@ def test_k1_empty_and_padding():
     assert not v.any()
 
 
+# ------------------------------------------------ device FASTA parser (row a6) ---
+def test_device_parser_equals_host_packer():
+    rng = random.Random(61)
+    cases = [
+        b">only_header\n",
+        b">short\nACGT\n",
+        b">a\n" + b"A" * 64 + b"\n>b\n" + b"C" * 64 + b"\n",
+        b">crlf\r\nACGTACGTACGTACGTACGTACGT\r\nACGTACGT\r\n>x\r\nAC\r\rGT\r\n",
+        b">nonl\nACGTACGTACGTACGTACGTACGTACG",
+        b">nonl_cr\nACGTACGT\r",
+        b">x\nACGTACGTACGT ACGTACGTACGTACG\tTACGTACGT\n",
+        b"junk before header\nmore junk\n>x\n" + b"GATTACA" * 9 + b"\n\n\n>y\n\n" + b"TTGACCA" * 9 + b"\n",
+        b"\n\n>lead\nACGT>notheader\n>real header > with gt\nGG>CC\n",
+        b">plus\nACGTACGT\n+\nIIIIIIII\nACGT\n>next\nTTTT\n",
+        b">big\n" + bytes(rng.choice(b"ACGTacgtNn") for _ in range(100_000)) + b"\n",
+    ]
+    text = ""
+    for r in range(300):
+        L = rng.choice([0, 1, 31, 32, 33, 79, 80, 81, 500, 8191, 8192, 8193, 30000])
+        s = "".join(rng.choice("ACGTacgtNRY") if rng.random() < 0.01 else rng.choice("ACGT") for _ in range(L))
+        w = rng.choice([60, 70, 80, 10 ** 9])
+        text += ">r%d some text\n" % r + "\n".join(s[i:i + w] for i in range(0, len(s), w)) + "\n"
+    cases.append(text.encode())
+    for t in cases:
+        hs_, hi, hn, hst = hs.pack_text(t)
+        ds, di, dn, dst = hs.pack_text_device(t)
+        assert dn == hn, t[:40]
+        assert (dst["n_records"], dst["n_bases"]) == (hst["n_records"], hst["n_bases"])
+        assert np.array_equal(di, hi) and np.array_equal(ds, hs_), t[:40]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_ingest_modes_agree_on_pinned_text(c1_case, mode):
+    import torch
+    offsets, hashes, lengths, fasta = c1_case
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    want = odb.screen_text(fasta, threads=2)
+    pinned = torch.empty(len(fasta), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(fasta, np.uint8)
+    scr = hs.Screen(db)
+    scr.set_option("ingest", mode)
+    scr.set_option("chunk_bases", 300_000)
+    scr.feed_text_ptr(pinned.data_ptr(), pinned.numel(), 3)
+    res = scr.finish(False)
+    assert res.shared.tolist() == want.shared.tolist() and res.median.tolist() == want.median.tolist()
+    assert res.set_size == want.set_size
+    assert res.stats["n_bases"] == want.n_bases and res.stats["n_valid_kmers"] == want.n_kmers
+
+
 # ---------------------------------------------------------------- K2 ----------
 def test_k2_probe_membership_and_canonical_ids():
     rng = np.random.default_rng(5)

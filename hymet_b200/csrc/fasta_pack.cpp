@@ -96,7 +96,8 @@ __attribute__((target("avx2"))) inline void convert32(__m256i v, uint64_t &codes
     const uint32_t mm = ~(uint32_t)_mm256_movemask_epi8(_mm256_shuffle_epi8(ok, rev));
     bad = (mm << 16) | (mm >> 16);
     // four codes -> one byte (first base in the top two bits), then 8 bytes -> big-endian u64
-    const __m256i w16 = _mm256_maddubs_epi16(code, _mm256_set1_epi32(0x01041040));  // (c0*64+c1*16), (c2*4+c3)
+    const __m256i w16 = _mm256_maddubs_epi16(_mm256_and_si256(code, ok),  // invalid positions carry code 0
+                                             _mm256_set1_epi32(0x01041040));  // (c0*64+c1*16), (c2*4+c3)
     const __m256i w32 = _mm256_madd_epi16(w16, _mm256_set1_epi16(1));
     const __m256i b16 = _mm256_packus_epi32(w32, w32);
     const __m256i b8 = _mm256_packus_epi16(b16, b16);

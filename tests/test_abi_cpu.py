@@ -62,6 +62,14 @@ def test_host_packer_layout():
     assert codes[1:5] == [0, 1, 2, 3] and codes[6:10] == [0, 1, 2, 3] and codes[11:13] == [3, 3]
     assert bad[:13] == [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0] and all(bad[13:])
     assert hs.packed_words(1) == 256 and hs.packed_words(8192) == 256 and hs.packed_words(8193) == 512
+    # invalid positions carry code 0 whatever the byte was (vector and scalar paths agree bit for bit)
+    line = (b"ACGT\rN-*xyz" * 30)[:300]
+    seq, inv, n, _ = hs.pack_text(b">v\n" + line + b"\n")
+    for pos, ch in enumerate(b"!" + line):
+        code = (int(seq[pos // 32]) >> (62 - 2 * (pos % 32))) & 3
+        bad = (int(inv[pos // 32]) >> (31 - pos % 32)) & 1
+        want = b"ACGT".find(bytes([ch]).upper())
+        assert (code, bad) == ((want, 0) if want >= 0 else (0, 1)), (pos, ch)
 
 
 def _toy_db(rng, n=7, s=50, k=21, bits=64):

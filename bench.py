@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -250,7 +250,17 @@ def run_b200(args):
         if sample_clocks:
             torch.cuda.profiler.stop()
         wall = time.perf_counter() - t0
+        n_timed = len(sampler.rows) if sampler else 0
+        if sampler and n_timed < 25:
+            # the timed region is only tens of ms: keep the same load running (untimed) until the
+            # sampler has seen it for ~0.7 s, so the median clock is of the kernel, not of idle
+            t_end = time.perf_counter() + 0.7
+            while time.perf_counter() < t_end:
+                fn()
+            torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
+        if clocks is not None:
+            clocks["samples_in_timed_region"] = n_timed
         ms = e0.elapsed_time(e1)
         if world > 1:
             t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)

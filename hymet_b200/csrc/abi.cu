@@ -127,8 +127,10 @@ struct Ingest {
         if (tiles > tile_cap) {
             cudaDeviceSynchronize();
             cudaFree(sc.tile_event); cudaFree(sc.tile_carry); cudaFree(sc.tile_event_b); cudaFree(sc.tile_carry_b);
-            cudaFree(sc.tile_count); cudaFree(sc.tile_offset);
+            cudaFree(sc.tile_count); cudaFree(sc.tile_offset); cudaFree(sc.masks); cudaFree(sc.emit);
             tile_cap = tiles + tiles / 4;
+            CU(cudaMalloc((void **)&sc.masks, tile_cap * 256 * sizeof(uint4)));
+            CU(cudaMalloc((void **)&sc.emit, tile_cap * 256 * sizeof(uint2)));
             CU(cudaMalloc((void **)&sc.tile_event, tile_cap * 4));
             CU(cudaMalloc((void **)&sc.tile_carry, tile_cap * 4));
             CU(cudaMalloc((void **)&sc.tile_event_b, tile_cap * 4));
@@ -172,7 +174,7 @@ struct Ingest {
             if (sl.copied) cudaEventDestroy(sl.copied);
         }
         cudaFree(sc.tile_event); cudaFree(sc.tile_carry); cudaFree(sc.tile_event_b); cudaFree(sc.tile_carry_b);
-        cudaFree(sc.tile_count); cudaFree(sc.tile_offset); cudaFree(d_totals);
+        cudaFree(sc.tile_count); cudaFree(sc.tile_offset); cudaFree(sc.masks); cudaFree(sc.emit); cudaFree(d_totals);
         for (auto *b : counter_blocks) cudaFree(b);
     }
 };

@@ -827,63 +827,61 @@ cudaError_t launch_pack_codes_dyn(const uint8_t *codes, const unsigned long long
 }
 
 // ---------------------------------------------------------------------------
-// Device-side FASTA ingest.  "Events" are the two things that change the parser
-// state: a header start ('>' as first byte of a line) and a newline.  A byte is
-// inside a header iff the latest event at or before it is a header start, so the
-// parser state is a prefix MAX of event codes and output positions are a prefix SUM
-// -- both done as tile aggregate -> single-CTA scan -> tile re-walk.
+// Device-side FASTA ingest (row a6 on the GPU).
+//
+// "Events" change the parser state: a newline, a header start ('>' as first byte of a
+// line) and a '+' line start.  Two "latest event wins" streams,
+//   A: newline (even code) / header start (odd)        -> in a header line iff latest A is odd
+//   B: header start (even) / '+' line start (odd)      -> skipping to the next header iff
+//      latest B is odd (B is seeded odd: everything before the first header is skipped, like
+//      the host packer's SEEK_HDR state; a '+' line ends a record's sequence, kseq's rule),
+// make the state a prefix MAX of event codes and output positions a prefix SUM; each scan is
+// tile aggregate -> single-CTA scan -> tile re-walk.  Bytes are turned into 32-bit masks
+// ONCE (k_fa_masks, SIMD-in-register compares); the later passes work on masks.
 // Same output as fasta_pack.cpp: header => one invalid position, CR before LF dropped,
 // every other byte of a sequence line kept (non-ACGT => code 4).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fa_code(uint32_t c)
+// 4-bit mask (bit b = byte b) of the bytes of w equal to the byte replicated in pat
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t pat)
 {
-    const uint32_t u = c & 0xDFu;  // fold case (S3)
-    return u == 'A' ? 0u : u == 'C' ? 1u : u == 'G' ? 2u : u == 'T' ? 3u : 4u;
+    const uint32_t x = w ^ pat;
+    const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;  // bit 7 of a byte set iff that byte != 0
+    const uint32_t z = (~t & 0x80808080u) >> 7;               // 0x01 per equal byte
+    return (z * 0x01020408u) >> 24;                           // gather the four flags (no carries collide)
 }
 
-struct FaThread {
-    uint8_t b[32];
-    uint32_t prev, next;  // bytes around the thread's 32 ('\n' before the text, '\n' after it)
-    uint32_t i0, n_here;  // first byte index, bytes that exist (0..32)
-};
+struct FaMasks { uint32_t nl, hs, pl, crdrop; };
 
-__device__ __forceinline__ void fa_load(const uint8_t *text, uint32_t n, uint32_t i0, FaThread &t)
+__device__ __forceinline__ void fa_load_words(const uint8_t *text, uint32_t n, uint32_t i0, uint32_t w[8], uint32_t &n_here,
+                                              uint32_t &prev, uint32_t &next)
 {
-    t.i0 = i0;
-    t.n_here = i0 >= n ? 0u : min(32u, n - i0);
-    if (t.n_here == 32 && ((uintptr_t)(text + i0) & 15) == 0) {
+    n_here = i0 >= n ? 0u : min(32u, n - i0);
+    if (n_here == 32 && ((uintptr_t)(text + i0) & 15) == 0) {
         const uint4 a = __ldg(reinterpret_cast<const uint4 *>(text + i0));
         const uint4 c = __ldg(reinterpret_cast<const uint4 *>(text + i0) + 1);
-        const uint32_t v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int i = 0; i < 32; i++) t.b[i] = (uint8_t)(v[i >> 2] >> (8 * (i & 3)));
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < 32; i++) t.b[i] = (uint32_t)i < t.n_here ? text[i0 + i] : (uint8_t)'\n';
-    }
-    t.prev = i0 == 0 ? (uint32_t)'\n' : (i0 <= n ? (uint32_t)text[i0 - 1] : (uint32_t)'\n');
-    t.next = i0 + 32 < n ? (uint32_t)text[i0 + 32] : (uint32_t)'\n';
-}
-
-// Two event streams, each "latest event wins" (codes grow with the byte index; +2 so 0 = none):
-//   A: newline (even) / header start (odd)      -> inside a header line iff latest A is odd
-//   B: header start (even) / '+' line start (odd) -> skipping until the next header iff latest B
-//      is odd.  B starts odd: everything before the first header is skipped, like the host
-//      packer's SEEK_HDR state; a '+' line ends a record's sequence (kseq's quality marker).
-__device__ __forceinline__ void fa_last_events(const FaThread &t, uint32_t &eva, uint32_t &evb)
-{
-    uint32_t p = t.prev;
-    eva = 0; evb = 0;
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-        if ((uint32_t)i < t.n_here) {
-            const uint32_t c = t.b[i], idx = t.i0 + i;
-            if (c == '\n') eva = 2u * idx + 2u;
-            else if (p == '\n' && c == '>') { eva = 2u * idx + 3u; evb = 2u * idx + 2u; }
-            else if (p == '\n' && c == '+') evb = 2u * idx + 3u;
-            p = c;
+            for (int b = 0; b < 4; b++) {
+                const uint32_t i = q * 4 + b;
+                v |= (uint32_t)(i < n_here ? text[i0 + i] : (uint8_t)'\n') << (8 * b);
+            }
+            w[q] = v;
         }
     }
+    prev = (i0 == 0 || i0 > n) ? (uint32_t)'\n' : (uint32_t)text[i0 - 1];
+    next = i0 + 32 < n ? (uint32_t)text[i0 + 32] : (uint32_t)'\n';
+}
+
+__device__ __forceinline__ void fa_event_codes(const FaMasks &m, uint32_t i0, uint32_t &eva, uint32_t &evb)
+{
+    eva = 0; evb = 0;
+    const uint32_t a = m.nl | m.hs, b = m.hs | m.pl;
+    if (a) { const uint32_t top = 31 - __clz(a); eva = 2u * (i0 + top) + 2u + ((m.hs >> top) & 1u); }
+    if (b) { const uint32_t top = 31 - __clz(b); evb = 2u * (i0 + top) + 2u + ((m.pl >> top) & 1u); }
 }
 
 __device__ __forceinline__ uint32_t block_excl_max(uint32_t v, uint32_t *warp_buf, uint32_t &total)
@@ -932,20 +930,39 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t *warp_bu
     return before + inc - v;
 }
 
-__global__ void __launch_bounds__(256) k_fa_events(const uint8_t *text, uint32_t n, uint32_t *tile_event_a,
-                                                   uint32_t *tile_event_b)
+// pass 1: bytes -> per-thread masks (stored) + per-tile last events
+__global__ void __launch_bounds__(256) k_fa_masks(const uint8_t *text, uint32_t n, uint4 *masks, uint32_t *tile_event_a,
+                                                  uint32_t *tile_event_b)
 {
     __shared__ uint32_t wb[8];
-    FaThread t;
-    fa_load(text, n, blockIdx.x * kFaTileBytes + threadIdx.x * 32, t);
+    const uint32_t i0 = blockIdx.x * kFaTileBytes + threadIdx.x * 32;
+    uint32_t w[8], n_here, prev, next;
+    fa_load_words(text, n, i0, w, n_here, prev, next);
+    uint32_t nl = 0, gt = 0, plus = 0, cr = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        nl |= eq_mask4(w[q], 0x0A0A0A0Au) << (4 * q);
+        gt |= eq_mask4(w[q], 0x3E3E3E3Eu) << (4 * q);
+        plus |= eq_mask4(w[q], 0x2B2B2B2Bu) << (4 * q);
+        cr |= eq_mask4(w[q], 0x0D0D0D0Du) << (4 * q);
+    }
+    const uint32_t here = n_here >= 32 ? ~0u : ((1u << n_here) - 1u);
+    const uint32_t nl_real = nl & here;                 // bytes past the text were loaded as '\n'
+    const uint32_t line_start = (nl << 1) | (prev == '\n');
+    FaMasks m;
+    m.nl = nl_real;
+    m.hs = gt & line_start & here;
+    m.pl = plus & line_start & here;
+    m.crdrop = cr & ((nl >> 1) | ((next == '\n') ? 0x80000000u : 0u)) & here;
+    masks[blockIdx.x * 256 + threadIdx.x] = make_uint4(m.nl, m.hs, m.pl, m.crdrop);
     uint32_t ea, eb, ta, tb;
-    fa_last_events(t, ea, eb);
+    fa_event_codes(m, i0, ea, eb);
     block_excl_max(ea, wb, ta);
     block_excl_max(eb, wb, tb);
     if (threadIdx.x == 0) { tile_event_a[blockIdx.x] = ta; tile_event_b[blockIdx.x] = tb; }
 }
 
-// single CTA: exclusive prefix max (mode 0, 32-bit) or exclusive prefix sum (mode 1, 64-bit out)
+// single CTA: exclusive prefix max (out_max) or exclusive prefix sum (out_sum) over the tiles
 __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *in, uint32_t n, uint32_t *out_max, uint64_t *out_sum,
                                                     unsigned long long *total_out, uint32_t init)
 {
@@ -980,59 +997,82 @@ __global__ void __launch_bounds__(1024) k_tile_scan(const uint32_t *in, uint32_t
     if (threadIdx.x == 0 && total_out) *total_out = carry_s;
 }
 
-// walk the thread's bytes with the parser state; MODE 0: count emitted positions,
-// MODE 1: write codes at out[base + ...]
-template <int MODE>
-__global__ void __launch_bounds__(256) k_fa_walk(const uint8_t *text, uint32_t n, const uint32_t *tile_carry_a,
-                                                 const uint32_t *tile_carry_b, uint32_t *tile_count,
-                                                 const uint64_t *tile_offset, uint8_t *codes, unsigned long long *totals)
+// pass 2: masks + carried state -> which bytes are emitted; per-tile counts
+__global__ void __launch_bounds__(256) k_fa_state(uint32_t n, const uint4 *masks, const uint32_t *tile_carry_a,
+                                                  const uint32_t *tile_carry_b, uint2 *emit, uint32_t *tile_count,
+                                                  unsigned long long *totals)
 {
     __shared__ uint32_t wb[8];
-    FaThread t;
-    fa_load(text, n, blockIdx.x * kFaTileBytes + threadIdx.x * 32, t);
+    const uint32_t i0 = blockIdx.x * kFaTileBytes + threadIdx.x * 32;
+    const uint4 mm = masks[blockIdx.x * 256 + threadIdx.x];
+    const FaMasks m{mm.x, mm.y, mm.z, mm.w};
     uint32_t ea, eb, tot_ev;
-    fa_last_events(t, ea, eb);
+    fa_event_codes(m, i0, ea, eb);
     const uint32_t carry_a = max(tile_carry_a[blockIdx.x], block_excl_max(ea, wb, tot_ev));
     const uint32_t carry_b = max(tile_carry_b[blockIdx.x], block_excl_max(eb, wb, tot_ev));
-    bool in_header = (carry_a & 1u) != 0;  // latest of {newline, header start} is a header start
-    bool in_skip = (carry_b & 1u) != 0;    // latest of {header start, '+' line} is a '+' line (or nothing yet)
-    uint32_t emit_mask = 0, sep_mask = 0, p = t.prev;
-#pragma unroll
-    for (int i = 0; i < 32; i++) {
-        if ((uint32_t)i < t.n_here) {
-            const uint32_t c = t.b[i];
-            const uint32_t nxt = i < 31 ? ((uint32_t)(i + 1) < t.n_here ? (uint32_t)t.b[i + 1] : (uint32_t)'\n') : t.next;
-            if (c == '\n') {
-                in_header = false;
-            } else if (p == '\n' && c == '>') {
-                in_header = true; in_skip = false;
-                emit_mask |= 1u << i; sep_mask |= 1u << i;  // one separator per record (S6)
-            } else if (p == '\n' && c == '+') {
-                in_skip = true;
-            } else if (!in_header && !in_skip && !(c == '\r' && nxt == '\n')) {
-                emit_mask |= 1u << i;
-            }
-            p = c;
-        }
+    bool in_header = (carry_a & 1u) != 0, in_skip = (carry_b & 1u) != 0;
+    const uint32_t n_here = i0 >= n ? 0u : min(32u, n - i0);
+    const uint32_t here = n_here >= 32 ? ~0u : ((1u << n_here) - 1u);
+    uint32_t keep = 0, pos = 0, ev = m.nl | m.hs | m.pl;
+    while (ev) {  // one iteration per event (about one per 80 bytes of wrapped FASTA)
+        const uint32_t e = __ffs(ev) - 1;
+        if (!in_header && !in_skip && e > pos) keep |= ((1u << e) - 1u) & ~((1u << pos) - 1u);
+        const uint32_t bit = 1u << e;
+        if (m.nl & bit) in_header = false;
+        else if (m.hs & bit) { in_header = true; in_skip = false; }
+        else in_skip = true;
+        pos = e + 1;
+        ev &= ev - 1;
     }
+    if (!in_header && !in_skip && pos < 32) keep |= ~((1u << pos) - 1u);
+    keep &= here & ~m.crdrop;
+    const uint32_t em = keep | m.hs;  // a header start emits the record separator (S6)
+    emit[blockIdx.x * 256 + threadIdx.x] = make_uint2(em, m.hs);
     uint32_t tile_total;
-    const uint32_t local = block_excl_sum(__popc(emit_mask), wb, tile_total);
-    if (MODE == 0) {
-        if (threadIdx.x == 0) tile_count[blockIdx.x] = tile_total;
-        const uint32_t nsep = __popc(sep_mask);
-        uint32_t bases = __popc(emit_mask) - nsep, recs = nsep;
-        bases = warp_sum(bases); recs = warp_sum(recs);
-        if ((threadIdx.x & 31) == 0) {
-            if (bases) atomicAdd(totals + 1, (unsigned long long)bases);
-            if (recs) atomicAdd(totals + 2, (unsigned long long)recs);
-        }
-    } else {
-        uint8_t *out = codes + tile_offset[blockIdx.x] + local;
+    block_excl_sum(__popc(em), wb, tile_total);
+    if (threadIdx.x == 0) tile_count[blockIdx.x] = tile_total;
+    uint32_t bases = warp_sum((uint32_t)__popc(keep)), recs = warp_sum((uint32_t)__popc(m.hs));
+    if ((threadIdx.x & 31) == 0) {
+        if (bases) atomicAdd(totals + 1, (unsigned long long)bases);
+        if (recs) atomicAdd(totals + 2, (unsigned long long)recs);
+    }
+}
+
+// pass 3: emitted bytes -> base codes, compacted through shared memory, written coalesced
+__global__ void __launch_bounds__(256) k_fa_emit(const uint8_t *text, uint32_t n, const uint2 *emit,
+                                                 const uint64_t *tile_offset, uint8_t *codes)
+{
+    __shared__ uint32_t wb[8];
+    __shared__ __align__(16) uint8_t out[kFaTileBytes];
+    const uint32_t i0 = blockIdx.x * kFaTileBytes + threadIdx.x * 32;
+    const uint2 e = emit[blockIdx.x * 256 + threadIdx.x];
+    uint32_t tile_total;
+    uint32_t local = block_excl_sum(__popc(e.x), wb, tile_total);
+    if (e.x) {
+        uint32_t w[8], n_here, prev, next;
+        fa_load_words(text, n, i0, w, n_here, prev, next);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            if (emit_mask & (1u << i)) *out++ = (sep_mask & (1u << i)) ? (uint8_t)4 : (uint8_t)fa_code(t.b[i]);
+        for (int q = 0; q < 8; q++) {
+            // SIMD-in-register: fold case, (c>>1)&3 gives A0 C1 T2 G3, xor with its own high bit -> A0 C1 G2 T3
+            const uint32_t up = w[q] & 0xDFDFDFDFu;
+            const uint32_t c1 = (up >> 1) & 0x03030303u;
+            uint32_t code = c1 ^ ((c1 >> 1) & 0x01010101u);
+            const uint32_t ok = eq_mask4(up, 0x41414141u) | eq_mask4(up, 0x43434343u) | eq_mask4(up, 0x47474747u) |
+                                eq_mask4(up, 0x54545454u);
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const uint32_t bit = 1u << (q * 4 + b);
+                if (e.x & bit) {
+                    uint32_t c = (code >> (8 * b)) & 3u;
+                    if (!((ok >> b) & 1u) || (e.y & bit)) c = 4u;  // not A/C/G/T, or the record separator
+                    out[local++] = (uint8_t)c;
+                }
+            }
         }
     }
+    __syncthreads();
+    uint8_t *dst = codes + tile_offset[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < tile_total; i += 256) dst[i] = out[i];
 }
 
 __global__ void k_fa_totals(const unsigned long long *chunk_positions, unsigned long long *totals)
@@ -1044,12 +1084,12 @@ cudaError_t launch_fasta_to_codes(const uint8_t *text, uint32_t n, uint8_t *code
 {
     if (!n) return cudaMemsetAsync(sc.chunk_positions, 0, sizeof(unsigned long long), st);
     const uint32_t tiles = (n + kFaTileBytes - 1) / kFaTileBytes;
-    k_fa_events<<<tiles, 256, 0, st>>>(text, n, sc.tile_event, sc.tile_event_b);
+    k_fa_masks<<<tiles, 256, 0, st>>>(text, n, sc.masks, sc.tile_event, sc.tile_event_b);
     k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_event, tiles, sc.tile_carry, nullptr, nullptr, 0u);
     k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_event_b, tiles, sc.tile_carry_b, nullptr, nullptr, 1u);
-    k_fa_walk<0><<<tiles, 256, 0, st>>>(text, n, sc.tile_carry, sc.tile_carry_b, sc.tile_count, nullptr, nullptr, sc.totals);
+    k_fa_state<<<tiles, 256, 0, st>>>(n, sc.masks, sc.tile_carry, sc.tile_carry_b, sc.emit, sc.tile_count, sc.totals);
     k_tile_scan<<<1, 1024, 0, st>>>(sc.tile_count, tiles, nullptr, sc.tile_offset, sc.chunk_positions, 0u);
-    k_fa_walk<1><<<tiles, 256, 0, st>>>(text, n, sc.tile_carry, sc.tile_carry_b, nullptr, sc.tile_offset, codes, nullptr);
+    k_fa_emit<<<tiles, 256, 0, st>>>(text, n, sc.emit, sc.tile_offset, codes);
     k_fa_totals<<<1, 1, 0, st>>>(sc.chunk_positions, sc.totals);
     return cudaGetLastError();
 }

@@ -115,6 +115,8 @@ struct FaScratch {
     uint32_t *tile_carry;   // exclusive prefix max of tile_event
     uint32_t *tile_event_b; // per tile: its last header-start/'+'-line event code
     uint32_t *tile_carry_b; // exclusive prefix max of tile_event_b, seeded "skipping"
+    uint4 *masks;           // per 32 input bytes: newline / header-start / '+'-start / dropped-CR masks
+    uint2 *emit;            // per 32 input bytes: emitted-byte mask, separator mask
     uint32_t *tile_count;   // per tile: positions emitted
     uint64_t *tile_offset;  // exclusive prefix sum of tile_count
     unsigned long long *totals;  // [0] positions, [1] sequence bases, [2] records  (accumulated)

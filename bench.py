@@ -336,10 +336,16 @@ def run_b200(args):
         for _ in range(4):
             hits, reads, pms = db.probe_device(hq.data_ptr(), n_probe)
             best = pms if best is None else min(best, pms)
+        # what this GPU delivers for raw random 32-byte sector reads (no hashing), same footprint
+        gbuf = torch.empty(int(db.info.n_buckets) * 4, dtype=torch.int64, device=dev)
+        g_ms = min(hs.gather_bench(gbuf.data_ptr(), gbuf.numel() * 8, n_probe) for _ in range(3))
+        del gbuf
         gbs = (32.0 * reads + 8.0 * n_probe) / (best * 1e-3) / 1e9
         line["probe_kernel"] = {"kernel": "k_probe", "probes": n_probe, "bucket_reads": int(reads), "ms": best,
                                 "probes_per_s": n_probe / (best * 1e-3), "achieved": gbs, "peak": peak, "unit": "GB/s",
-                                "frac": gbs / peak, "bytes": "32 B bucket sector per read + 8 B hash read per probe"}
+                                "frac": gbs / peak, "bytes": "32 B bucket sector per read + 8 B hash read per probe",
+                                "random_sector_reads_per_s_of_this_gpu": n_probe / (g_ms * 1e-3),
+                                "frac_of_random_sector_rate": (reads / (best * 1e-3)) / (n_probe / (g_ms * 1e-3))}
         del hq
 
     # ---- e2e: FASTA text in pinned host memory -> TSV columns on the host --------------

@@ -89,6 +89,7 @@ SIGNATURES = {
     "hs_hash_packed": (C.c_int, [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, u64p, u8p]),
     "hs_db_probe": (C.c_int, [C.c_void_p, u64p, C.c_uint64, u32p]),
     "hs_db_probe_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p, u64p, C.POINTER(C.c_float)]),
+    "hs_gather_bench": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_float)]),
     "hs_db_entry_ids": (C.c_int, [C.c_void_p, u32p]),
     "hs_stat_batch": (C.c_int, [C.c_uint32, C.c_uint64, C.c_uint64, u64p, u64p, f64p, f64p]),
     "hs_sketch_text": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t, u64p, u32p, u64p]),

@@ -101,7 +101,7 @@ struct Chunk {
 
 // ---- device-side FASTA ingest: raw text slots + scan scratch ------------------------
 struct Ingest {
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 4;
     struct Slot { uint8_t *raw = nullptr, *codes = nullptr; size_t cap = 0; cudaEvent_t done = nullptr, copied = nullptr; };
     Slot slots[kSlots];
     int next = 0;
@@ -890,14 +890,19 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     // (one cudaMemcpyAsync + kernel launches per span) and is throttled by its raw-text slots
     auto device_worker = [&]() {
         cudaSetDevice(g_device);
+        // consecutive spans are contiguous text: take a few at a time so that the parser and
+        // stream kernels run on >= 48 MB launches (fewer, fuller waves; fewer host wake-ups)
+        const size_t batch = threads > 0 ? 3 : 4;
         for (;;) {
-            const size_t i = next.fetch_add(1);
+            const size_t i = next.fetch_add(batch);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;
+            const size_t last = std::min(spans.size(), i + batch) - 1;
+            const size_t len = spans[last].second - spans[i].first;
             const double t0 = now_s();
-            int rc = feed_span_device(s, text + spans[i].first, spans[i].second - spans[i].first);
+            int rc = feed_span_device(s, text + spans[i].first, len);
             if (g_debug_timing)
-                fprintf(stderr, "[hs] span %zu device-ingest: %zu B enqueue+wait %.2f ms\n", i,
-                        spans[i].second - spans[i].first, 1e3 * (now_s() - t0));
+                fprintf(stderr, "[hs] spans %zu-%zu device-ingest: %zu B enqueue+wait %.2f ms\n", i, last, len,
+                        1e3 * (now_s() - t0));
             if (rc != HS_OK) {
                 std::lock_guard<std::mutex> lk(err_mu);
                 if (rc_all.load() == HS_OK) { rc_all = rc; err_all = g_err; }
@@ -1230,6 +1235,22 @@ HS_API int hs_db_probe_device(hs_db *db, const void *d_hashes, uint64_t n, uint6
     if (n_bucket_reads) *n_bucket_reads = h[1];
     if (ms) *ms = t;
     cudaFree(dst); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return HS_OK;
+}
+
+HS_API int hs_gather_bench(const void *d_buf, uint64_t bytes, uint64_t n_reads, float *ms)
+{
+    if (!d_buf || bytes < 64 || !ms) return fail(HS_EINVAL, "bad argument");
+    NEED_DEVICE();
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(launch_gather_bench(d_buf, bytes, n_reads, g_sm, 0));  // warm-up
+    CU(cudaEventRecord(e0, 0));
+    CU(launch_gather_bench(d_buf, bytes, n_reads, g_sm, 0));
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return HS_OK;
 }
 

@@ -314,20 +314,99 @@ __global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_distinct, (unsigned long long)local);
 }
 
+// K2 alone.  Four independent probes per thread: their eight 128-bit bucket loads are all
+// issued before the first compare, so a warp keeps 128 sectors in flight.
+constexpr int kProbeUnroll = 4;
 __global__ void __launch_bounds__(256) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
                                                uint32_t *out_entry, unsigned long long *stats)
 {
     uint32_t hits = 0, reads = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = table_find(t, __ldg(hashes + i), reads);
-        if (out_entry) out_entry[i] = id;
-        hits += id != kNoEntry;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kProbeUnroll;
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kProbeUnroll; base < n; base += stride) {
+        uint64_t h[kProbeUnroll];
+        uint32_t b[kProbeUnroll];
+        ulonglong2 k01[kProbeUnroll], k23[kProbeUnroll];
+#pragma unroll
+        for (int u = 0; u < kProbeUnroll; u++) h[u] = base + u < n ? __ldg(hashes + base + u) : kEmptyKey;
+#pragma unroll
+        for (int u = 0; u < kProbeUnroll; u++) {
+            b[u] = bucket_of(h[u], t.n_buckets);
+            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)b[u] * kBucketSlots);
+            k01[u] = __ldg(p); k23[u] = __ldg(p + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < kProbeUnroll; u++) {
+            if (base + u >= n) continue;
+            uint32_t id;
+            if (h[u] == kEmptyKey) {
+                id = t.special;
+            } else {
+                reads++;
+                const size_t v = (size_t)b[u] * kBucketSlots;
+                if (k01[u].x == h[u]) id = __ldg(t.vals + v);
+                else if (k01[u].y == h[u]) id = __ldg(t.vals + v + 1);
+                else if (k23[u].x == h[u]) id = __ldg(t.vals + v + 2);
+                else if (k23[u].y == h[u]) id = __ldg(t.vals + v + 3);
+                else if (k01[u].x == kEmptyKey || k01[u].y == kEmptyKey || k23[u].x == kEmptyKey || k23[u].y == kEmptyKey)
+                    id = kNoEntry;
+                else {  // bucket full of other keys: continue along the chain (rare at load 1/3)
+                    id = kNoEntry;
+                    uint32_t bb = (b[u] + 1 == t.n_buckets) ? 0u : b[u] + 1;
+                    for (uint32_t tries = 1; tries < t.n_buckets; tries++) {
+                        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)bb * kBucketSlots);
+                        const ulonglong2 a = __ldg(p), c = __ldg(p + 1);
+                        reads++;
+                        const size_t vv = (size_t)bb * kBucketSlots;
+                        if (a.x == h[u]) { id = __ldg(t.vals + vv); break; }
+                        if (a.y == h[u]) { id = __ldg(t.vals + vv + 1); break; }
+                        if (c.x == h[u]) { id = __ldg(t.vals + vv + 2); break; }
+                        if (c.y == h[u]) { id = __ldg(t.vals + vv + 3); break; }
+                        if (a.x == kEmptyKey || a.y == kEmptyKey || c.x == kEmptyKey || c.y == kEmptyKey) break;
+                        bb = (bb + 1 == t.n_buckets) ? 0u : bb + 1;
+                    }
+                }
+            }
+            if (out_entry) out_entry[base + u] = id;
+            hits += id != kNoEntry;
+        }
     }
     hits = warp_sum(hits); reads = warp_sum(reads);
     if ((threadIdx.x & 31) == 0) {
         if (hits) atomicAdd(stats + 0, (unsigned long long)hits);
         if (reads) atomicAdd(stats + 1, (unsigned long long)reads);
     }
+}
+
+// Reference point for K2: the rate at which this GPU serves independent random 32-byte
+// sector reads from a buffer far larger than L2 (no hashing, no compares, 8 loads in flight
+// per thread).  k_probe is reported against this as well as against the streaming peak.
+__global__ void __launch_bounds__(256) k_gather_bench(const ulonglong2 *buf, uint64_t n_sectors, uint64_t per_thread,
+                                                      unsigned long long *sink)
+{
+    uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    unsigned long long acc = 0;
+    for (uint64_t i = 0; i < per_thread; i += 8) {
+        ulonglong2 v[16];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x = x * 6364136223846793005ull + 1442695040888963407ull;
+            const uint64_t sct = (uint64_t)(((unsigned __int128)(x >> 11) * n_sectors) >> 53);
+            v[2 * u] = __ldg(buf + 2 * sct); v[2 * u + 1] = __ldg(buf + 2 * sct + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) acc += v[u].x ^ v[u].y;
+    }
+    if (acc == 0x0123456789ABCDEFull) *sink = acc;  // keeps the loads alive
+}
+
+cudaError_t launch_gather_bench(const void *buf, uint64_t bytes, uint64_t total_reads, int sm_count, cudaStream_t st)
+{
+    const uint32_t grid = (uint32_t)sm_count * 8u;
+    const uint64_t per_thread = (total_reads / ((uint64_t)grid * 256) + 7) / 8 * 8;
+    static unsigned long long *sink = nullptr;
+    if (!sink) { cudaError_t e = cudaMalloc((void **)&sink, 8); if (e != cudaSuccess) return e; }
+    k_gather_bench<<<grid, 256, 0, st>>>((const ulonglong2 *)buf, bytes / 32, per_thread, sink);
+    return cudaGetLastError();
 }
 
 static inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap)
@@ -360,7 +439,7 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
                          unsigned long long *stats, int sm_count, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_probe<<<grid_for(n, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
+    k_probe<<<grid_for((n + kProbeUnroll - 1) / kProbeUnroll, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
     return cudaGetLastError();
 }
 

@@ -77,6 +77,9 @@ cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint6
 cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n, uint32_t *out_entry,
                          unsigned long long *stats, int sm_count, cudaStream_t st);
 
+// random 32-byte sector reads over `bytes` of device memory (measurement reference for K2)
+cudaError_t launch_gather_bench(const void *buf, uint64_t bytes, uint64_t total_reads, int sm_count, cudaStream_t st);
+
 // ---- mixture bottom-s (K3) ---------------------------------------------------
 // copy keys <= thr from the set into out (append with atomic cursor); counts all <= thr
 cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,

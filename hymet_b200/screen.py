@@ -283,6 +283,13 @@ def sketch_text(text: bytes, k: int, s: int, seed: int = 42, device: int = 0):
     return out[:n.value].copy(), int(ln.value)
 
 
+def gather_bench(d_buf_ptr: int, nbytes: int, n_reads: int) -> float:
+    """ms for n_reads independent random 32-byte sector reads over a device buffer."""
+    ms = C.c_float()
+    check(_abi.load().hs_gather_bench(C.c_void_p(d_buf_ptr), nbytes, n_reads, C.byref(ms)))
+    return ms.value
+
+
 def sketch_packed_device(d_seq_ptr: int, d_inv_ptr: int, n_bases: int, k: int, s: int, seed: int = 42):
     out = np.zeros(max(s, 1), np.uint64)
     n = C.c_uint32()

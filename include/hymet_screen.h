@@ -167,6 +167,9 @@ int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *out_ent
 /* K2 alone on DEVICE hashes, timed: increments nothing, returns hits and device ms. */
 int hs_db_probe_device(hs_db *db, const void *d_hashes, uint64_t n, uint64_t *n_hits,
                        uint64_t *n_bucket_reads, float *ms);
+/* Measurement reference for K2: time n_reads independent random 32-byte sector reads over a
+ * device buffer of `bytes` (make it much larger than L2). */
+int hs_gather_bench(const void *d_buf, uint64_t bytes, uint64_t n_reads, float *ms);
 /* canonical entry id of every stored entry (n_entries values). */
 int hs_db_entry_ids(hs_db *db, uint32_t *out);
 /* K6 alone (rows a14/a15). */

@@ -340,10 +340,21 @@ def run_b200(args):
         gbuf = torch.empty(int(db.info.n_buckets) * 4, dtype=torch.int64, device=dev)
         g_ms = min(hs.gather_bench(gbuf.data_ptr(), gbuf.numel() * 8, n_probe) for _ in range(3))
         del gbuf
+        p_traffic = None
+        try:
+            ent = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_probe", {})
+            if ent.get("probes") == n_probe and ent.get("sketches") == args.sketches:
+                p_traffic = ent.get("dram_bytes_per_launch")
+        except Exception:
+            pass
         gbs = (32.0 * reads + 8.0 * n_probe) / (best * 1e-3) / 1e9
         line["probe_kernel"] = {"kernel": "k_probe", "probes": n_probe, "bucket_reads": int(reads), "ms": best,
                                 "probes_per_s": n_probe / (best * 1e-3), "achieved": gbs, "peak": peak, "unit": "GB/s",
                                 "frac": gbs / peak, "bytes": "32 B bucket sector per read + 8 B hash read per probe",
+                                "traffic": p_traffic,
+                                "dram_frac_with_measured_traffic": (p_traffic / (best * 1e-3) / 1e9 / peak) if p_traffic else None,
+                                "note": "B200 serves each random 32-byte bucket read as a 128-byte DRAM fetch (ncu: 3.8 sectors per "
+                                        "read), so the kernel runs at the DRAM roofline while a quarter of the moved bytes are useful",
                                 "random_sector_reads_per_s_of_this_gpu": n_probe / (g_ms * 1e-3),
                                 "frac_of_random_sector_rate": (reads / (best * 1e-3)) / (n_probe / (g_ms * 1e-3))}
         del hq

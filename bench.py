@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-filter", action="store_true", help="probe the table for every k-mer (mash semantics, no range pre-filter)")
     ap.add_argument("--wta", action="store_true")
+    ap.add_argument("--k", type=int, default=21)
+    ap.add_argument("--s", type=int, default=1000)
+    ap.add_argument("--clusters", type=int, default=0,
+                    help="config 4: make this many of the real genomes 1-5 %% diverged copies of the others")
     return ap.parse_args()
 
 
@@ -189,7 +193,8 @@ def run_b200(args):
     t_setup = time.perf_counter()
     want_host = not args.no_e2e
     wl = workload.make_c2(local, mbp=args.mbp, n_sketches=args.sketches, n_real=args.real, shard=rank,
-                          with_fasta=want_host, with_host_packed=want_host)
+                          with_fasta=want_host, with_host_packed=want_host, k=args.k, s=args.s,
+                          cluster_copies=args.clusters)
     db = hs.Database.from_arrays(wl.k, wl.s, 42, wl.offsets, wl.hashes, wl.lengths, device=local)
     stream = torch.cuda.Stream(device=dev)   # explicit stream: the library launches on it, the events time it
     torch.cuda.set_stream(stream)
@@ -294,7 +299,7 @@ def run_b200(args):
             traffic = ent.get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"kernel": "k_stream<21>", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"kernel": "k_stream<%d>" % args.k, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "ms_per_launch": ms_stream, "share_of_step": ms_stream / (ms / args.steps),
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -308,8 +313,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "c2: synthetic %d Mbp CAMI-shaped contig set per GPU vs %d-sketch db (k=21, s=1000)"
-                               % (args.mbp, args.sketches),
+        "config": {"workload": "c2: synthetic %d Mbp CAMI-shaped contig set per GPU vs %d-sketch db (k=%d, s=%d)"
+                               % (args.mbp, args.sketches, args.k, args.s), "k": args.k, "s": args.s,
                    "query_mbp_per_gpu": args.mbp, "contigs_per_gpu": wl.n_contigs, "sketches": args.sketches,
                    "real_genome_sketches": wl.n_real, "mutation_rate": 0.01, "probe_filter": not args.no_filter,
                    "winner_take_all": bool(args.wta), "parallelism": "query sharded x%d, table replicated" % world,

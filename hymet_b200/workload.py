@@ -134,7 +134,7 @@ def pack_codes(codes: torch.Tensor):
 
 def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int = 500, genome_len: int = 2_000_000,
             k: int = 21, s: int = 1000, rate: float = 0.01, seed: int = 2, shard: int = 0, with_fasta: bool = True,
-            with_host_packed: bool = True, fasta_width: int = 80) -> Workload:
+            with_host_packed: bool = True, fasta_width: int = 80, cluster_copies: int = 0) -> Workload:
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
     hs._abi.init(device)
@@ -142,6 +142,16 @@ def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int 
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)                      # genomes + db identical on every rank
     genomes = torch.randint(0, 4, (n_real * genome_len,), dtype=torch.uint8, device=dev, generator=gen)
+    if cluster_copies:
+        # config 4: the last `cluster_copies` genomes become near-identical relatives (1-5 % substitutions,
+        # mutationGCF.py model) of the first ones -> clusters that winner-take-all has to separate
+        cluster_copies = min(cluster_copies, n_real // 2)
+        for c in range(cluster_copies):
+            src = genomes[(c % (n_real - cluster_copies)) * genome_len:][:genome_len]
+            m = 0.01 + 0.04 * ((c * 7919) % 1000) / 1000.0
+            hit = torch.rand(genome_len, device=dev, generator=gen) < m
+            shift = torch.randint(1, 4, (genome_len,), device=dev, generator=gen, dtype=torch.uint8)
+            genomes[(n_real - cluster_copies + c) * genome_len:][:genome_len] = torch.where(hit, (src + shift) % 4, src)
     real = np.zeros((n_real, s), np.uint64)
     for i in range(n_real):
         gseq, ginv, gn = pack_codes(genomes[i * genome_len:(i + 1) * genome_len])
@@ -151,7 +161,10 @@ def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int 
     rng = np.random.default_rng(seed)
     decoy, dlen = synth.decoy_sketches(rng, n_sketches - n_real, s)
     hashes = np.concatenate([real.reshape(-1), decoy.reshape(-1)])
-    lengths = np.concatenate([np.full(n_real, genome_len, np.uint64), dlen])
+    real_len = np.full(n_real, genome_len, np.uint64)
+    if cluster_copies:  # distinct lengths inside a cluster so (score, length) ties are rare but present
+        real_len[n_real - cluster_copies:] -= (np.arange(cluster_copies, dtype=np.uint64) % np.uint64(7))
+    lengths = np.concatenate([real_len, dlen])
     offsets = np.arange(n_sketches + 1, dtype=np.uint64) * np.uint64(s)
 
     qrng = np.random.default_rng(seed * 1000 + shard)      # each rank cuts its own shard of contigs

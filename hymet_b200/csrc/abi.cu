@@ -842,12 +842,21 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     }
     std::atomic<size_t> next{0};
     std::atomic<int> rc_all{HS_OK};
+    std::atomic<int> dev_us_per_span{350};  // measured pace of the device-ingest worker
     std::string err_all;
     std::mutex err_mu;
     auto worker = [&](int t) {
         cudaSetDevice(g_device);
         int flip = 0;
+        double my_ms = 4.0;  // how long this thread needs to pack one span
         for (;;) {
+            if (use_device) {
+                // do not start a span the DMA + device parser would finish before we do: near the end
+                // of the input a slow packer thread would otherwise be the tail of the whole feed
+                const size_t nx = next.load();
+                if (nx >= spans.size()) break;
+                if ((double)(spans.size() - nx) * dev_us_per_span.load() * 1e-3 < my_ms) break;
+            }
             const size_t i = next.fetch_add(1);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;
             Staging &g = s->staging[(size_t)t * 2 + (flip ^= 1)];
@@ -870,6 +879,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
                 const double t0 = now_s();
                 pack_text_span(text + spans[i].first, len, g.seq, g.inv, &ps);
                 const double t1 = now_s();
+                my_ms = 1e3 * (t1 - t0);
                 std::lock_guard<std::mutex> lk(s->mu);
                 const double t2 = now_s();
                 s->st.n_bases += ps.n_seq_bases;
@@ -900,6 +910,12 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
             const size_t len = spans[last].second - spans[i].first;
             const double t0 = now_s();
             int rc = feed_span_device(s, text + spans[i].first, len);
+            {   // pace = wall time per span including the wait for a free slot (EMA)
+                // never faster than the PCIe link can move the raw text (~60 GB/s)
+                const int floor_us = (int)(len / (last - i + 1) / 60000) + 1;
+                const int us = (int)(1e6 * (now_s() - t0) / (double)(last - i + 1));
+                dev_us_per_span.store((dev_us_per_span.load() * 3 + std::max(us, floor_us)) / 4);
+            }
             if (g_debug_timing)
                 fprintf(stderr, "[hs] spans %zu-%zu device-ingest: %zu B enqueue+wait %.2f ms\n", i, last, len,
                         1e3 * (now_s() - t0));

@@ -136,7 +136,7 @@ def run_reference(args):
     from hymet_b200 import synth
     from tests import _oracle as orc
 
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     k, s = 21, 1000
     rng = np.random.default_rng(2)
     n_real = 24
@@ -200,7 +200,8 @@ def run_b200(args):
     torch.cuda.set_stream(stream)
     scr = hd.DistributedScreen(db, local, stream_ptr=stream.cuda_stream, probe_filter=not args.no_filter)
     t_setup = time.perf_counter() - t_setup
-    host_threads = max(1, (os.cpu_count() or 1) // world)
+    n_cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    host_threads = max(1, n_cpus // world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -403,7 +404,7 @@ def run_b200(args):
     # ---- CPU baseline on a bounded sample (rank 0, N=1) + parity of that sample ----------
     if rank == 0 and world == 1 and not args.no_cpu and not args.no_e2e:
         from tests import _oracle as orc
-        threads = os.cpu_count() or 1
+        threads = n_cpus
         sample = cpu_sample_from_fasta(wl.fasta.numpy(), int(args.cpu_mbp * 1_000_000 * 82 / 80))
         t0 = time.perf_counter()
         odb = orc.OracleDB.from_arrays(wl.k, wl.s, 42, wl.offsets, wl.hashes, wl.lengths)

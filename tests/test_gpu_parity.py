@@ -420,3 +420,56 @@ cut -f5 "$TOP_HITS" > "$SELECTED_GENOMES"
         outs[tag] = [open(f, "rb").read() for f in files]
     assert outs["gpu"] == outs["oracle"]
     assert len(outs["gpu"][4].splitlines()) >= 3
+
+
+# ------------------------------------------------- BASELINE-size properties -------
+def test_baseline_shape_properties():
+    """Config-2 shape (50 000 sketches, CAMI-shaped contigs, here 300 Mbp to stay within seconds):
+    results that do not need the oracle -- the three entry points agree, the exact pre-filter
+    changes nothing, multiplicities are linear in the input, planted genomes are found and
+    decoys are not, counts add up, winner-take-all assigns every present hash exactly once."""
+    import torch
+
+    from hymet_b200 import dist as hd
+    from hymet_b200 import workload
+    wl = workload.make_c2(0, mbp=300, n_sketches=50_000, n_real=120, with_fasta=True, with_host_packed=True)
+    db = hs.Database.from_arrays(wl.k, wl.s, 42, wl.offsets, wl.hashes, wl.lengths)
+    scr = hs.Screen(db)
+
+    def run(feed, wta=False, twice=False, probe_filter=True):
+        scr.reset()
+        scr.set_option("filter", int(probe_filter))
+        for _ in range(2 if twice else 1):
+            feed()
+        r = scr.finish(wta)
+        return r
+
+    dev = lambda: scr.feed_packed_device(wl.d_seq.data_ptr(), wl.d_inv.data_ptr(), wl.n_positions)
+    host = lambda: scr.feed_packed_ptr(wl.h_seq.data_ptr(), wl.h_inv.data_ptr(), wl.n_positions)
+    text = lambda: scr.feed_text_ptr(wl.fasta.data_ptr(), wl.fasta.numel(), 8)
+    a = run(dev)
+    assert a.stats["n_valid_kmers"] > 0.99 * wl.n_bases
+    for other in (run(host), run(text), run(dev, probe_filter=False)):
+        assert other.shared.tolist() == a.shared.tolist() and other.median.tolist() == a.median.tolist()
+        assert other.set_size == a.set_size
+    assert run(dev, probe_filter=False).stats["n_probes"] == a.stats["n_valid_kmers"]
+    # linearity: the same contigs twice -> same shared hashes, doubled multiplicities, same mixture
+    b = run(dev, twice=True)
+    assert b.shared.tolist() == a.shared.tolist() and b.median.tolist() == (2 * a.median).tolist()
+    assert b.set_size == a.set_size
+    # planted truth: contigs come from the first 120 sketches at 1 % substitutions; decoys are random hashes
+    real, decoy = a.shared[:wl.n_real], a.shared[wl.n_real:]
+    assert int(decoy.sum()) == 0
+    assert (real > 0.5 * wl.s).sum() >= 0.9 * wl.n_real          # expected containment ~ 0.99^21 = 0.81
+    assert np.all(a.identity[:wl.n_real][real > 0] > 0.9) and np.all(a.pvalue[:wl.n_real][real > 100] < 1e-50)
+    # counts add up to the kernel's own hit counter
+    run(dev)
+    counts = hd.counts_tensor(scr, 0)
+    torch.cuda.synchronize()
+    assert int(counts.to(torch.int64).sum()) == a.stats["n_hits"]
+    present = int((counts != 0).sum())
+    # winner-take-all: every present hash credited to exactly one sketch
+    w = run(dev, wta=True)
+    assert int(w.shared.sum()) == present
+    assert int(w.shared.sum()) <= int(a.shared.sum())
+    scr.close()

@@ -140,9 +140,8 @@ HS_HD uint64_t murmur3_h1_words(const uint32_t w[8], int k, uint32_t seed)
     return h1;
 }
 
-// Expand a canonical LSB-first k-mer and hash it.  `Lut` maps one byte of 2-bit
-// codes to 4 ASCII letters: a shared-memory table on the device (lut4.lookup),
-// plain arithmetic on the host.
+// Expand a canonical LSB-first k-mer and hash it.  `Lut(cl, i)` returns the 4 ASCII
+// letters of byte i of cl: a shared-memory table on the device, plain arithmetic on the host.
 template <class Lut>
 HS_HD uint64_t hash_canonical(uint64_t cl, int k, uint32_t seed, bool use64, const Lut &lut)
 {
@@ -152,7 +151,7 @@ HS_HD uint64_t hash_canonical(uint64_t cl, int k, uint32_t seed, bool use64, con
         const int nb = k - 4 * i;  // bases available for this word
         uint32_t v = 0;
         if (nb > 0) {
-            v = lut((uint32_t)(cl >> (8 * i)) & 0xFFu);
+            v = lut(cl, i);  // letters of bases 4i..4i+3
             if (nb < 4) v &= (1u << (8 * nb)) - 1u;
         }
         w[i] = v;
@@ -161,7 +160,9 @@ HS_HD uint64_t hash_canonical(uint64_t cl, int k, uint32_t seed, bool use64, con
     return use64 ? h : (h & 0xFFFFFFFFull);
 }
 
-struct AsciiArith { HS_HD uint32_t operator()(uint32_t b) const { return ascii4(b); } };
+struct AsciiArith {
+    HS_HD uint32_t operator()(uint64_t cl, int i) const { return ascii4((uint32_t)(cl >> (8 * i)) & 0xFFu); }
+};
 
 // One thread's unit of work: the 32 k-mers that END inside word `cur` (their
 // first bases may lie in `prev`; k <= 32 so never further back).  sink(j, hash)

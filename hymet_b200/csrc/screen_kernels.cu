@@ -121,15 +121,28 @@ struct __align__(16) TileBuf {
 };
 static_assert(sizeof(TileBuf) % 16 == 0, "tile buffers must keep 16-byte alignment");
 
-// 256 x 4-base ASCII expansions, replicated per bank (entry b of lane l at [b*32+l])
-// so that 32 lanes with 32 different indices never conflict.
-struct SmemLut {
-    const uint32_t *lane_base;
-    __device__ __forceinline__ uint32_t operator()(uint32_t b) const { return lane_base[b * 32]; }
+// 256 x 4-base ASCII expansions, 16 lane copies each (entry b, copy c at b*64 + c*4 bytes), at a
+// 16 KB-ALIGNED shared address: the address of a lookup is then
+//     ((k-mer >> s) & 0x3FC0) | (table base | (lane & 15) * 4)
+// i.e. one shift + one LOP3 instead of shift/and/or/lea -- the kernel is ALU-pipe bound (ncu),
+// and this removes 12 of its ~87 ALU instructions per k-mer.  Lanes l and l+16 share a bank:
+// a 2-way conflict on 6 loads per k-mer, invisible next to ~170 ALU cycles.
+constexpr uint32_t kLutBytes = 256 * 16 * 4;
+struct SmemLut16 {
+    uint32_t base;  // 16 KB-aligned shared-window address of the table | (lane & 15) * 4
+    __device__ __forceinline__ uint32_t operator()(uint64_t cl, int i) const
+    {
+        const uint32_t w = i < 4 ? (uint32_t)cl : (uint32_t)(cl >> 32);
+        const int sh = 8 * (i & 3) - 6;
+        const uint32_t x = sh < 0 ? (w << 6) : (w >> sh);
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((x & 0x3FC0u) | base));
+        return v;
+    }
 };
 
 template <int KT>
-__global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
+__global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
 {
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
@@ -138,7 +151,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
     constexpr uint32_t kStages = 3, kPrefetch = 1;
     __shared__ TileBuf buf[kStages];
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
-    __shared__ uint32_t lut[256 * 32];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];  // 2 * kLutBytes: room to align the table to 16 KB
 
     const int k = KT ? KT : a.k;
     const bool use64 = KT ? (KT > 16) : (a.use64 != 0);
@@ -152,9 +165,17 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (uint32_t i = tid; i < 256 * 32; i += kCtaThreads) lut[i] = ascii4(i >> 5);
+    const uint32_t dyn_addr = smem_u32(dyn_smem);
+    const uint32_t lut_addr = (dyn_addr + (kLutBytes - 1)) & ~(kLutBytes - 1);
+    {
+        uint32_t *lut = reinterpret_cast<uint32_t *>(dyn_smem + (lut_addr - dyn_addr));
+        for (uint32_t i = tid; i < 256 * 16; i += kCtaThreads) lut[i] = ascii4(i >> 4);
+    }
     __syncthreads();
-    const SmemLut L{lut + lane};
+    uint32_t lut_lane = lut_addr | ((lane & 15u) << 2);
+    asm volatile("mov.u32 %0, %0;" : "+r"(lut_lane));  // one opaque per-thread register: keeps ptxas from
+                                                        // splitting it back into uniform base + lane term
+    const SmemLut16 L{lut_lane};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -175,6 +196,9 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
     }
 
     const uint64_t n_bases = a.n_bases_dev ? (uint64_t)__ldcg(a.n_bases_dev) : a.n_bases;
+    // one compare per k-mer decides whether anything at all has to happen with its hash
+    uint64_t gate = a.do_mix ? mix_tau : 0;
+    if (a.do_count) gate = a.do_filter ? (a.tab.max_key > gate ? a.tab.max_key : gate) : ~0ull;
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
@@ -212,6 +236,7 @@ __global__ void __launch_bounds__(kCtaThreads, 4) k_stream(const StreamArgs a)
                 a.emit_hash[pos0 + j] = h;
                 a.emit_valid[pos0 + j] = 1;
             }
+            if (h > gate) return;
             if (a.do_mix && h <= mix_tau) {
                 n_mix++;
                 mix_insert(a.mix, mix_set, h);
@@ -246,14 +271,14 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
 {
     static int occ = 0;
     if (!occ) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT>, kCtaThreads, 0);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT>, kCtaThreads, 2 * kLutBytes);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
     }
     uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
     if (grid > a.n_tiles - a.tile_begin) grid = a.n_tiles - a.tile_begin;
     if (!grid) return cudaSuccess;
-    k_stream<KT><<<grid, kCtaThreads, 0, st>>>(a);
+    k_stream<KT><<<grid, kCtaThreads, 2 * kLutBytes, st>>>(a);
     return cudaGetLastError();
 }
 

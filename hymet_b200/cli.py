@@ -126,14 +126,116 @@ def screen_main(args: List[str], stdout=None) -> int:
         return 1
 
 
+SKETCH_USAGE = """
+Usage:
+
+  mash sketch [options] <input> [<input>] ...
+
+Description:
+
+  Create a sketch file (.msh): for every input file the s smallest distinct
+  canonical k-mer hashes of all its records (one reference per file, named after
+  the file).  Computed on the GPU with the same hash kernel as `mash screen`.
+
+Options:
+
+  -h          Help
+  -o <path>   Output prefix (".msh" is appended unless present) [first input]
+  -k <int>    K-mer size, 1-32 [21]
+  -s <int>    Sketch size [1000]
+  -S <int>    Hash seed [42]
+"""
+
+
+def sketch_main(args: List[str], stdout=None) -> int:
+    """`mash sketch`: HYMET never runs it (its three databases are
+    downloaded pre-built, README.md:164-169) but a drop-in without it cannot refresh them."""
+    stdout = stdout or sys.stdout
+    k, s, seed, out = 21, 1000, 42, None
+    pos: List[str] = []
+    i = 0
+    try:
+        while i < len(args):
+            a = args[i]
+            if a == "-h":
+                stdout.write(SKETCH_USAGE)
+                return 0
+            if a in ("-o", "-k", "-s", "-S", "-p"):
+                if i + 1 >= len(args):
+                    _err("-%s requires an argument" % a[1])
+                    return 1
+                v = args[i + 1]
+                i += 1
+                if a == "-o":
+                    out = v
+                elif a == "-k":
+                    k = int(v)
+                elif a == "-s":
+                    s = int(v)
+                elif a == "-S":
+                    seed = int(v)
+            elif a.startswith("-") and a != "-":
+                _err("Unrecognized option: %s" % a)
+                return 1
+            else:
+                pos.append(a)
+            i += 1
+    except ValueError:
+        _err("malformed numeric option value")
+        return 1
+    if not pos:
+        stdout.write(SKETCH_USAGE)
+        return 0
+    if not (1 <= k <= 32) or s < 1:
+        _err("k-mer size must be 1-32 and sketch size positive")
+        return 1
+    import gzip
+
+    import numpy as np
+
+    from . import msh as mshfmt
+    from . import screen as hs
+    device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
+    names, comments, lengths, sketches = [], [], [], []
+    try:
+        for p in pos:
+            if not os.path.exists(p):
+                _err("could not open %s for reading." % p)
+                return 1
+            with (gzip.open(p, "rb") if p.endswith(".gz") else open(p, "rb")) as fh:
+                text = fh.read()
+            sys.stderr.write("Sketching %s...\n" % p)
+            h, total = hs.sketch_text(text, k, s, seed, device)
+            n_rec = text.count(b"\n>") + (1 if text.startswith(b">") else 0)
+            first = text[1:text.find(b"\n")].decode("utf-8", "replace").strip() if text.startswith(b">") else ""
+            if n_rec > 1:  # Mash's comment convention for multi-record genomes
+                first = "[%d seqs] %s [...]" % (n_rec, first)
+            names.append(p); comments.append(first); lengths.append(total); sketches.append(h)
+    except hs.HsError as e:
+        _err(e.msg)
+        return 1
+    offsets = np.concatenate([[0], np.cumsum([len(h) for h in sketches])]).astype(np.uint64)
+    db = mshfmt.SketchDB(k=k, s=s, seed=seed, names=names, comments=comments,
+                         lengths=np.array(lengths, np.uint64), offsets=offsets,
+                         hashes=np.concatenate(sketches) if sketches else np.zeros(0, np.uint64))
+    out = out or pos[0]
+    if not out.endswith(".msh"):
+        out += ".msh"
+    sys.stderr.write("Writing to %s...\n" % out)
+    mshfmt.write_msh(out, db)
+    return 0
+
+
 def main(argv: Optional[List[str]] = None) -> int:
     argv = sys.argv[1:] if argv is None else argv
     if not argv or argv[0] in ("-h", "--help", "help"):
-        sys.stdout.write("mash (hymet-screen-b200): only the `screen` command is provided.\n" + USAGE)
+        sys.stdout.write("mash (hymet-screen-b200): commands `screen` and `sketch` are provided.\n" + USAGE)
         return 0
     if argv[0] == "--version":
         sys.stdout.write("2.3-hymet-screen-b200\n")
         return 0
+    if argv[0] == "sketch":
+        return sketch_main(argv[1:])
     if argv[0] != "screen":
         # HYMET uses nothing else (SURVEY.md 8b); hand over to a real mash when one exists further down PATH
         me = os.path.realpath(sys.argv[0])

@@ -473,3 +473,32 @@ def test_baseline_shape_properties():
     assert int(w.shared.sum()) == present
     assert int(w.shared.sum()) <= int(a.shared.sum())
     scr.close()
+
+
+def test_cli_sketch_then_screen(tmp_path):
+    """`mash sketch` on the GPU writes a .msh that all three readers accept, equal to the oracle's
+    sketches, and `mash screen` against it finds the genomes the contigs came from."""
+    rng = np.random.default_rng(12)
+    genomes = [synth.random_genome(rng, 80_000) for _ in range(6)]
+    paths = []
+    for i, g in enumerate(genomes):
+        p = tmp_path / (synth.gcf_name(i)); paths.append(str(p))
+        p.write_bytes(synth.to_fasta([g[:50_000], g[50_000:]], "chr"))
+    mash = [sys.executable, os.path.join(ROOT, "bin", "mash")]
+    out = str(tmp_path / "db")
+    r = subprocess.run(mash + ["sketch", "-k", "21", "-s", "500", "-o", out] + paths, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    db = mshfmt.read_msh(out + ".msh")
+    assert (db.k, db.s, db.n_refs) == (21, 500, 6) and db.names == paths
+    assert db.comments[0].startswith("[2 seqs] chr_0")
+    odb = orc.OracleDB.load_msh(out + ".msh")
+    for i, p in enumerate(paths):
+        want, ln = orc.sketch_text(open(p, "rb").read(), 21, 500)
+        assert db.ref_hashes(i).tolist() == want.tolist() and int(db.lengths[i]) == ln == 80_000
+        assert odb.hashes(i).tolist() == want.tolist()
+    q = tmp_path / "q.fna"
+    q.write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[:2], 200_000, 0.005, median=5000.0), "c"))
+    r = subprocess.run(mash + ["screen", "-v", "0.9", out + ".msh", str(q)], capture_output=True)
+    assert r.returncode == 0
+    hits = [l.split(b"\t")[4].decode() for l in r.stdout.splitlines()]
+    assert hits == paths[:2]

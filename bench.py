@@ -319,6 +319,7 @@ def run_b200(args):
                    "query_mbp_per_gpu": args.mbp, "contigs_per_gpu": wl.n_contigs, "sketches": args.sketches,
                    "real_genome_sketches": wl.n_real, "mutation_rate": 0.01, "probe_filter": not args.no_filter,
                    "winner_take_all": bool(args.wta), "parallelism": "query sharded x%d, table replicated" % world,
+                   "count_exchange": scr.last_exchange,
                    "l2": "inputs larger than L2 (%.0f MB packed query + %.0f MB table per GPU)"
                          % (wl.n_positions * 0.375 / 1e6, db.info.device_bytes / 1e6),
                    "timing": "CUDA events on the launching stream, max over ranks"},

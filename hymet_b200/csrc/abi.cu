@@ -1028,6 +1028,30 @@ HS_API int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n)
     return HS_OK;
 }
 
+HS_API int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, uint32_t *n)
+{
+    if (!s || !d_pairs || !n) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    uint32_t *d_n = s->mix.field(offsetof(MixState, n_out));   // free scratch word once the mixture is settled
+    CU(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), s->stream));
+    CU(launch_counts_compact(s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, d_n, s->stream));
+    CU(cudaMemcpyAsync(n, d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->st.n_launches++;
+    return HS_OK;
+}
+
+HS_API int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs)
+{
+    if (!s || (!d_pairs && n_pairs)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    CU(launch_counts_scatter_add(s->d_counts, s->db->n_entries, (const unsigned long long *)d_pairs, n_pairs, s->stream));
+    s->st.n_launches++;
+    return HS_OK;
+}
+
 HS_API int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes, uint32_t *n)
 {
     if (!s || !n) return fail(HS_EINVAL, "null argument");

@@ -1198,4 +1198,47 @@ cudaError_t launch_fasta_to_codes(const uint8_t *text, uint32_t n, uint8_t *code
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// Sparse form of the multi-GPU count exchange: counts[] is almost all zeros (only hashes
+// that occurred in this rank's shard), so ranks trade (entry id, count) pairs instead of
+// the dense vector when that is smaller.  Integer adds: order independent, exact.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs,
+                                                        uint32_t cap, uint32_t *n_out)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i];
+        if (c) {
+            const uint32_t p = atomicAdd(n_out, 1u);
+            if (p < cap) pairs[p] = ((unsigned long long)i << 32) | c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_counts_scatter_add(uint32_t *counts, uint64_t n_counts,
+                                                            const unsigned long long *pairs, uint64_t n_pairs)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long p = pairs[i];
+        const uint64_t id = p >> 32;
+        if (id < n_counts) atomicAdd(counts + id, (uint32_t)p);  // padding carries id 0xFFFFFFFF
+    }
+}
+
+cudaError_t launch_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs, uint32_t cap,
+                                  uint32_t *n_out, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    k_counts_compact<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(counts, n, pairs, cap, n_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_counts_scatter_add(uint32_t *counts, uint64_t n_counts, const unsigned long long *pairs,
+                                      uint64_t n_pairs, cudaStream_t st)
+{
+    if (!n_pairs) return cudaSuccess;
+    k_counts_scatter_add<<<grid_for(n_pairs, 256, 148 * 8), 256, 0, st>>>(counts, n_counts, pairs, n_pairs);
+    return cudaGetLastError();
+}
+
 }  // namespace hs

@@ -102,6 +102,12 @@ cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32
                          const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes,
                          double *identity, double *pvalue, cudaStream_t st);
 
+// ---- sparse count exchange (multi-GPU) -------------------------------------------
+cudaError_t launch_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs, uint32_t cap,
+                                  uint32_t *n_out, cudaStream_t st);
+cudaError_t launch_counts_scatter_add(uint32_t *counts, uint64_t n_counts, const unsigned long long *pairs,
+                                      uint64_t n_pairs, cudaStream_t st);
+
 // ---- device-side packer (codes -> 2-bit words + invalid mask) -------------------
 cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t n_words_alloc,
                               cudaStream_t st);

@@ -98,12 +98,23 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
 
 
 class DistributedScreen:
-    """hs.Screen whose finish() first exchanges counts and mixture with the other ranks."""
+    """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
-    def __init__(self, db: hs.Database, device: int, **kw):
+    One small all-gather carries every rank's hit count and mixture hashes.  The counts then
+    travel either as ONE dense NCCL all-reduce of counts[E] (the north-star formulation), or --
+    when hits are so few that it is cheaper, which is the normal case: a metagenome touches a
+    tiny part of a 50 000-genome table -- as an all-gather of each rank's non-zero
+    (entry id, count) pairs, scatter-added locally.  Both are exact integer sums.
+    `exchange = "dense" | "sparse" | "auto"`.
+    """
+
+    def __init__(self, db: hs.Database, device: int, exchange: str = "auto", **kw):
         self.db, self.device = db, device
         self.scr = hs.Screen(db, **kw)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.exchange_mode = os.environ.get("HYMET_SCREEN_EXCHANGE", exchange)
+        self.last_exchange = None
+        self._pairs = None
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
         return getattr(self.scr, name)
@@ -112,16 +123,50 @@ class DistributedScreen:
         self.scr.flush()
         if self.world == 1:
             return
-        t = counts_tensor(self.scr, self.device)
-        torch.cuda.current_stream().synchronize()
-        if t.numel():
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)          # the one NCCL all-reduce of the path
-        parts = all_gather_mixture(self.scr.mixture(), self.db.s)
+        dev = torch.device("cuda", self.device)
+        s = self.db.s
+        local = self.scr.mixture()
+        n_hits = int(self.scr.stats()["n_hits"])
+        meta = torch.zeros(s + 2, dtype=torch.int64)
+        meta[0], meta[1] = n_hits, len(local)
+        if len(local):
+            meta[2:2 + len(local)] = torch.from_numpy(local.view(np.int64).copy())
+        meta = meta.to(dev)
+        allmeta = torch.empty(self.world * (s + 2), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allmeta, meta)
+        allmeta = allmeta.view(self.world, s + 2).cpu().numpy()
         me = dist.get_rank()
-        for r, p in enumerate(parts):
-            if r != me and len(p):
-                self.scr.merge_mixture(p)
-        torch.cuda.current_stream().synchronize()
+        for r in range(self.world):
+            n = int(allmeta[r, 1])
+            if r != me and n:
+                self.scr.merge_mixture(allmeta[r, 2:2 + n].view(np.uint64))
+        # counts: non-zero entries <= hits; sparse moves world*cap*8 bytes, dense ~2*E*4
+        cap = int(allmeta[:, 0].max())
+        E = int(self.db.n_entries)
+        sparse = self.exchange_mode == "sparse" or (self.exchange_mode == "auto" and cap * 8 * self.world < E * 4)
+        if sparse and cap > 0 and cap < (1 << 31):
+            if self._pairs is None or self._pairs.numel() < cap:
+                self._pairs = torch.empty(max(cap, 1024), dtype=torch.int64, device=dev)
+            mine = self._pairs[:cap]
+            mine.fill_(-1)                                   # id 0xFFFFFFFF = padding
+            torch.cuda.current_stream().synchronize()
+            n = self.scr.counts_compact(mine.data_ptr(), cap)
+            assert n <= cap
+            gathered = torch.empty(self.world * cap, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(gathered, mine)
+            torch.cuda.current_stream().synchronize()
+            for r in range(self.world):
+                if r != me:
+                    self.scr.counts_scatter_add(gathered[r * cap:(r + 1) * cap].data_ptr(), cap)
+            self._keep = gathered                            # alive until finish() has synchronised
+            self.last_exchange = "sparse"
+        elif cap > 0:
+            t = counts_tensor(self.scr, self.device)
+            torch.cuda.current_stream().synchronize()
+            if t.numel():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)      # the one dense NCCL all-reduce of the path
+            torch.cuda.current_stream().synchronize()
+            self.last_exchange = "dense"
 
     def finish(self, wta: bool = False) -> hs.ScreenResult:
         self.exchange()

@@ -183,6 +183,14 @@ class Screen:
         check(_abi.load().hs_screen_counts_devptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
+    def counts_compact(self, d_pairs_ptr: int, cap: int) -> int:
+        n = C.c_uint32()
+        check(_abi.load().hs_screen_counts_compact(self._h, C.c_void_p(d_pairs_ptr), cap, C.byref(n)))
+        return n.value
+
+    def counts_scatter_add(self, d_pairs_ptr: int, n_pairs: int):
+        check(_abi.load().hs_screen_counts_scatter_add(self._h, C.c_void_p(d_pairs_ptr), n_pairs))
+
     def mixture(self) -> np.ndarray:
         out = np.zeros(max(self.db.s, 1), np.uint64)
         n = C.c_uint32()

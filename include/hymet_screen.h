@@ -144,6 +144,12 @@ int hs_screen_flush(hs_screen *s);
  * entry id; device pointer) may be summed across ranks in place, and every rank's local
  * mixture hashes merged into every other rank, before finish. */
 int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n);
+/* Sparse form of the same exchange, for when few hashes were hit: compact the non-zero
+ * counts into (entry id << 32 | count) pairs in a DEVICE buffer of `cap` pairs (*n = pairs
+ * found, may exceed cap: then nothing useful was written), and add another rank's pairs into
+ * counts[] (pairs whose id is >= n_entries are padding and ignored). */
+int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, uint32_t *n);
+int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs);
 int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);
 int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n);
 

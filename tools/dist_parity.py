@@ -31,8 +31,8 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ok = True
-    for wta in (False, True):
-        scr = hd.DistributedScreen(db, local, stream_ptr=stream.cuda_stream)
+    for wta, mode in ((False, "dense"), (True, "dense"), (False, "sparse"), (True, "sparse"), (False, "auto")):
+        scr = hd.DistributedScreen(db, local, exchange=mode, stream_ptr=stream.cuda_stream)
         b, e = hd.record_aligned_range(fasta, rank, world)
         scr.feed_text(fasta[b:e], 2)
         res = scr.finish(wta)
@@ -42,7 +42,8 @@ def main():
                     and res.set_size == want.set_size and scr.mixture().tolist() == want.mixture.tolist()
                     and bool(np.all(np.abs(res.identity - want.identity) <= 1e-12 * np.abs(want.identity)))
                     and bool(np.all(np.abs(res.pvalue - want.pvalue) <= 1e-12 * np.abs(want.pvalue))))
-            print("world=%d wta=%d shared_total=%d parity=%s" % (world, wta, int(res.shared.sum()), same), flush=True)
+            print("world=%d wta=%d exchange=%s(%s) shared_total=%d parity=%s" % (world, wta, mode, scr.last_exchange,
+                                                                                  int(res.shared.sum()), same), flush=True)
             ok = ok and same
         scr.scr.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-filter", action="store_true", help="probe the table for every k-mer (mash semantics, no range pre-filter)")
     ap.add_argument("--wta", action="store_true")
+    ap.add_argument("--tiny", type=int, default=0,
+                    help="this many decoy sketches come from tiny genomes (1.5-20 k k-mers): their hashes spread "
+                         "over the whole range and defeat the range pre-filter (viral/plasmid-heavy databases)")
     ap.add_argument("--k", type=int, default=21)
     ap.add_argument("--s", type=int, default=1000)
     ap.add_argument("--clusters", type=int, default=0,
@@ -194,7 +197,7 @@ def run_b200(args):
     want_host = not args.no_e2e
     wl = workload.make_c2(local, mbp=args.mbp, n_sketches=args.sketches, n_real=args.real, shard=rank,
                           with_fasta=want_host, with_host_packed=want_host, k=args.k, s=args.s,
-                          cluster_copies=args.clusters)
+                          cluster_copies=args.clusters, tiny=args.tiny)
     db = hs.Database.from_arrays(wl.k, wl.s, 42, wl.offsets, wl.hashes, wl.lengths, device=local)
     stream = torch.cuda.Stream(device=dev)   # explicit stream: the library launches on it, the events time it
     torch.cuda.set_stream(stream)
@@ -331,6 +334,8 @@ def run_b200(args):
         "counters": {k_: st[k_] for k_ in ("n_positions", "n_valid_kmers", "n_probes", "n_bucket_reads", "n_hits",
                                           "n_mix_inserts", "n_mix_passes", "set_size")},
         "db": {"distinct_hashes": int(db.n_distinct), "table_mb": db.info.device_bytes / 1e6,
+               "tiny_genome_sketches": args.tiny, "bloom_mb": db.info.bloom_bytes / 1e6,
+               "range_filter_pass_fraction": db.info.max_key / 2.0 ** 64,
                "table_build_s": db.info.t_build_s},
         "setup_s": t_setup,
     }

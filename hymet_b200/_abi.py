@@ -32,6 +32,7 @@ class DbInfo(C.Structure):
     _fields_ = [("k", C.c_uint32), ("s", C.c_uint32), ("seed", C.c_uint32), ("use64", C.c_uint32),
                 ("n_refs", C.c_uint64), ("n_entries", C.c_uint64), ("n_distinct", C.c_uint64),
                 ("n_buckets", C.c_uint64), ("max_key", C.c_uint64), ("device_bytes", C.c_uint64),
+                ("bloom_bytes", C.c_uint64),
                 ("t_parse_s", C.c_double), ("t_build_s", C.c_double)]
 
 

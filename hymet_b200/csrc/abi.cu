@@ -267,7 +267,9 @@ struct hs_db {
     uint64_t *d_offsets = nullptr, *d_lengths = nullptr;
     uint64_t device_bytes = 0;
     double t_parse = 0, t_build = 0;
-    TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special}; }
+    unsigned long long *d_bloom = nullptr;
+    uint32_t bloom_mask = 0;
+    TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special, d_bloom, bloom_mask}; }
 };
 
 struct Staging {
@@ -352,6 +354,23 @@ int db_build(hs_db *db, const uint64_t *hashes)
     if (flags[1]) return fail(HS_ECUDA, "hash table build failed (table full)");
     db->special = flags[0];
     if (db->special != kNoEntry) db->max_key = ~0ull;
+    {
+        // Bloom second level: worth it when the range test lets more than ~1 % of uniformly
+        // distributed query hashes through, and only while >= 8 bits per key still fit in ~64 MB
+        // (beyond that it would neither filter nor stay in L2).  HYMET_SCREEN_BLOOM=0/1 overrides.
+        const double pass = (double)db->max_key / 18446744073709551615.0;
+        uint64_t words = 1;
+        while (words * 64 < E * 12 && words < ((uint64_t)1 << 23)) words <<= 1;
+        bool want = pass > 0.01 && words * 64 >= E * 8;
+        if (const char *e = getenv("HYMET_SCREEN_BLOOM")) want = atoi(e) != 0 && E > 0;
+        if (want && E) {
+            CU(cudaMalloc((void **)&db->d_bloom, words * 8));
+            CU(cudaMemset(db->d_bloom, 0, words * 8));
+            db->bloom_mask = (uint32_t)(words - 1);
+            CU(launch_bloom_build(db->d_bloom, db->bloom_mask, d_hashes, E, 0));
+            db->device_bytes += words * 8;
+        }
+    }
     CU(launch_table_canon(db->view(), d_hashes, E, db->d_canon, d_nd, 0));
     unsigned long long nd = 0;
     CU(cudaMemcpy(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost));
@@ -367,6 +386,7 @@ void fill_info(const hs_db *db, hs_db_info_t *o)
     o->k = db->k; o->s = db->s; o->seed = db->seed; o->use64 = db->use64;
     o->n_refs = db->n_refs; o->n_entries = db->n_entries; o->n_distinct = db->n_distinct;
     o->n_buckets = db->n_buckets; o->max_key = db->max_key; o->device_bytes = db->device_bytes;
+    o->bloom_bytes = db->d_bloom ? ((uint64_t)db->bloom_mask + 1) * 8 : 0;
     o->t_parse_s = db->t_parse; o->t_build_s = db->t_build;
 }
 
@@ -653,6 +673,7 @@ HS_API void hs_db_free(hs_db *db)
     if (!db) return;
     if (g_device >= 0) cudaSetDevice(g_device);
     cudaFree(db->d_keys); cudaFree(db->d_vals); cudaFree(db->d_canon); cudaFree(db->d_offsets); cudaFree(db->d_lengths);
+    cudaFree(db->d_bloom);
     delete db;
 }
 

@@ -200,6 +200,14 @@ HS_HD uint32_t bucket_of(uint64_t h, uint32_t n_buckets)
 #endif
 }
 
+// Blocked Bloom filter: which 64-bit word, and which 3 bits inside it, belong to hash h.
+HS_HD void bloom_slot(uint64_t h, uint32_t word_mask, uint32_t &word, unsigned long long &bits)
+{
+    const uint64_t g = h * 0x9E3779B97F4A7C15ull;
+    word = (uint32_t)(g >> 34) & word_mask;
+    bits = (1ull << (g & 63)) | (1ull << ((g >> 6) & 63)) | (1ull << ((g >> 12) & 63));
+}
+
 HS_HD uint32_t mixset_slot(uint64_t h, uint32_t mask)
 {
     uint64_t x = h * 0x9E3779B97F4A7C15ull;

@@ -242,6 +242,12 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
                 mix_insert(a.mix, mix_set, h);
             }
             if (a.do_count && (!a.do_filter || h <= a.tab.max_key)) {
+                if (a.do_filter && a.tab.bloom) {  // L2-resident second-level filter (exact: no false negatives)
+                    uint32_t bw;
+                    unsigned long long bb;
+                    bloom_slot(h, a.tab.bloom_mask, bw, bb);
+                    if ((__ldg(a.tab.bloom + bw) & bb) != bb) return;
+                }
                 n_probe++;
                 const uint32_t id = table_find(a.tab, h, n_reads);
                 if (id != kNoEntry) {
@@ -323,6 +329,16 @@ __global__ void k_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_bucket
             b = (b + 1 == n_buckets) ? 0u : b + 1;
         }
         if (!done) atomicExch(fail, 1u);
+    }
+}
+
+__global__ void k_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t w;
+        unsigned long long b;
+        bloom_slot(hashes[e], bloom_mask, w, b);
+        atomicOr(bloom + w, b);
     }
 }
 
@@ -449,6 +465,14 @@ cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_bucke
     if (!n_entries) return cudaSuccess;
     k_table_insert<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(keys, vals, n_buckets, hashes, n_entries,
                                                                       special, fail);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n,
+                               cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    k_bloom_build<<<grid_for(n, 256, 148 * 32), 256, 0, st>>>(bloom, bloom_mask, hashes, n);
     return cudaGetLastError();
 }
 

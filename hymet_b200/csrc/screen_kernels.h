@@ -21,6 +21,12 @@ struct TableView {
     uint32_t n_buckets;
     uint64_t max_key;       // largest stored key (range pre-filter)
     uint32_t special;       // canonical entry id of key == kEmptyKey, or kNoEntry
+    // Second-level pre-filter for databases whose keys are spread over the whole hash range
+    // (sketches of tiny genomes keep ALL their k-mer hashes, so max_key ~ 2^64 and the range
+    // test stops helping): a blocked Bloom filter, one 64-bit word and 3 bits per key, sized to
+    // stay L2 resident.  No false negatives => results unchanged.  NULL when not built.
+    const unsigned long long *bloom;
+    uint32_t bloom_mask;    // words - 1 (power of two)
 };
 
 // Mixture bottom-s state lives on the device so that streaming never waits for the host:
@@ -73,6 +79,8 @@ cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_bucke
                                 uint32_t *fail, cudaStream_t st);
 cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint64_t n_entries, uint32_t *canon,
                                unsigned long long *n_distinct, cudaStream_t st);
+cudaError_t launch_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n,
+                               cudaStream_t st);
 // standalone probe (K2): out_entry may be NULL; stats[0]=hits, stats[1]=bucket reads
 cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n, uint32_t *out_entry,
                          unsigned long long *stats, int sm_count, cudaStream_t st);

@@ -134,7 +134,7 @@ def pack_codes(codes: torch.Tensor):
 
 def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int = 500, genome_len: int = 2_000_000,
             k: int = 21, s: int = 1000, rate: float = 0.01, seed: int = 2, shard: int = 0, with_fasta: bool = True,
-            with_host_packed: bool = True, fasta_width: int = 80, cluster_copies: int = 0) -> Workload:
+            with_host_packed: bool = True, fasta_width: int = 80, cluster_copies: int = 0, tiny: int = 0) -> Workload:
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
     hs._abi.init(device)
@@ -160,6 +160,9 @@ def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int 
         real[i] = h
     rng = np.random.default_rng(seed)
     decoy, dlen = synth.decoy_sketches(rng, n_sketches - n_real, s)
+    if tiny:   # sketches of tiny genomes: bottom-s of only 1.5-20 thousand k-mers, i.e. spread over the hash range
+        tiny = min(tiny, len(decoy))
+        decoy[:tiny], dlen[:tiny] = synth.decoy_sketches(rng, tiny, s, g_lo=1.5 * s, g_hi=20.0 * s)
     hashes = np.concatenate([real.reshape(-1), decoy.reshape(-1)])
     real_len = np.full(n_real, genome_len, np.uint64)
     if cluster_copies:  # distinct lengths inside a cluster so (score, length) ties are rare but present

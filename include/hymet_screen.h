@@ -51,6 +51,7 @@ typedef struct {
     uint64_t n_buckets;           /* hash-table buckets of 4 keys (device dbs only) */
     uint64_t max_key;             /* largest stored hash: exact range pre-filter */
     uint64_t device_bytes;        /* HBM held by the db */
+    uint64_t bloom_bytes;         /* size of the L2-resident Bloom second-level filter (0 = not built) */
     double t_parse_s, t_build_s;  /* .msh parse / GPU table build, seconds */
 } hs_db_info_t;
 

@@ -502,3 +502,21 @@ def test_cli_sketch_then_screen(tmp_path):
     assert r.returncode == 0
     hits = [l.split(b"\t")[4].decode() for l in r.stdout.splitlines()]
     assert hits == paths[:2]
+
+
+def test_bloom_second_level_filter_is_exact():
+    """A database with tiny genomes keeps ALL their k-mer hashes, so max_key ~ 2^64 and the range
+    test passes everything; the Bloom second level is built and must not change any result."""
+    rng = np.random.default_rng(77)
+    genomes = [synth.random_genome(rng, 40_000) for _ in range(20)]
+    genomes += [synth.random_genome(rng, int(n)) for n in rng.integers(300, 3000, size=40)]   # < s k-mers each
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    fasta = synth.to_fasta(synth.cut_contigs(rng, genomes[:6] + genomes[20:30], 500_000, 0.01, median=2500.0, lo=300), "c")
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    assert db.info.max_key > 2 ** 63 and db.info.bloom_bytes > 0
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    res, want = compare_screen(db, odb, fasta, False)
+    compare_screen(db, odb, fasta, True)
+    off, _ = compare_screen(db, odb, fasta, False, probe_filter=False)
+    assert res.stats["n_hits"] == off.stats["n_hits"] and res.stats["n_probes"] < 0.2 * off.stats["n_probes"]
+    assert int(res.shared[20:30].min()) > 100     # the tiny genomes in the query are found

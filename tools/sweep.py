@@ -10,6 +10,8 @@ runs = [
     ("c3_300k_sketches_1250mbp", ["--sketches", "300000", "--real", "3000", "--mbp", "1250"]),
     ("c4_wta_clusters", ["--wta", "--clusters", "250"]),
     ("c4_plain_clusters", ["--clusters", "250"]),
+    ("c2_tiny10k_bloom", ["--tiny", "10000"]),
+    ("c2_tiny10k_nobloom", ["--tiny", "10000"]),
     ("c5_k21_s5000", ["--s", "5000"]),
     ("c5_k21_s10000", ["--s", "10000"]),
     ("c5_k31_s1000", ["--k", "31"]),
@@ -22,7 +24,8 @@ with open(out, "a") as fh:
         if only and name not in only:
             continue
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-e2e", "--no-cpu"] + extra
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+        env = dict(os.environ, HYMET_SCREEN_BLOOM="0") if name.endswith("nobloom") else dict(os.environ)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
         try:
             d = json.loads(line)

@@ -219,6 +219,14 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
         mbar_wait(&full[b], (it / kStages) & 1u);
         uint64_t cur = buf[b].seq[tid + 2], prev = buf[b].seq[tid + 1];
         uint32_t icur = buf[b].inv[tid + 4], iprev = buf[b].inv[tid + 3];
+        // Handing the stage back is a write-after-read hazard ACROSS PROXIES: these were generic-proxy
+        // reads (LDS), the refill is an async-proxy write (TMA).  The mbarrier arrive alone does not
+        // order the two: with the load/store pipe backed up by table probes, about one word per 1e9
+        // was read after the TMA engine had refilled the stage (found as +-1 differences in per-hash
+        // counts between filter modes; 10/10 runs deterministic with the proxy fence, 9/10 with a
+        // CTA memory fence only).  So: retire the loads, fence the proxies, then release.
+        __threadfence_block();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[b]);  // this warp holds its words: the stage may be refilled
 

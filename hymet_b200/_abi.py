@@ -82,6 +82,7 @@ SIGNATURES = {
     "hs_screen_flush": (C.c_int, [C.c_void_p]),
     "hs_screen_counts_devptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "hs_screen_counts_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
+    "hs_screen_counts_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "hs_screen_counts_scatter_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "hs_screen_mixture_get": (C.c_int, [C.c_void_p, u64p, u32p]),
     "hs_screen_mixture_merge": (C.c_int, [C.c_void_p, u64p, C.c_uint32]),

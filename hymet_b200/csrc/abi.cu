@@ -1063,6 +1063,17 @@ HS_API int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, u
     return HS_OK;
 }
 
+HS_API int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t cap, void *d_n_out)
+{
+    if (!s || !d_pairs || !d_n_out) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    CU(cudaMemsetAsync(d_n_out, 0, sizeof(uint32_t), s->stream));
+    CU(launch_counts_compact(s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, (uint32_t *)d_n_out, s->stream));
+    s->st.n_launches++;
+    return HS_OK;
+}
+
 HS_API int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs)
 {
     if (!s || (!d_pairs && n_pairs)) return fail(HS_EINVAL, "null argument");

@@ -100,12 +100,15 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
 class DistributedScreen:
     """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
-    One small all-gather carries every rank's hit count and mixture hashes.  The counts then
-    travel either as ONE dense NCCL all-reduce of counts[E] (the north-star formulation), or --
-    when hits are so few that it is cheaper, which is the normal case: a metagenome touches a
-    tiny part of a 50 000-genome table -- as an all-gather of each rank's non-zero
-    (entry id, count) pairs, scatter-added locally.  Both are exact integer sums.
-    `exchange = "dense" | "sparse" | "auto"`.
+    Default ("auto"): ONE all-gather per screen.  Every rank contributes a fixed-size record
+    [n_pairs | mixture length | <= s mixture hashes | up to `cap` non-zero (entry id, count)
+    pairs]; the pairs are compacted on the device straight into the record
+    (k_counts_compact), so the host synchronises once, after the collective.  Each rank then
+    merges the other mixtures and scatter-adds the other ranks' pairs into its counts[].  A
+    metagenome touches a tiny part of a 50 000-genome table, so the pairs are a few MB where
+    the dense vector is hundreds.  If any rank has more than `cap` non-zero counts the exchange
+    falls back to the north star's single dense NCCL all-reduce of counts[E]
+    (`exchange="dense"` forces it).  Both are exact integer sums.
     """
 
     def __init__(self, db: hs.Database, device: int, exchange: str = "auto", **kw):
@@ -114,59 +117,56 @@ class DistributedScreen:
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.exchange_mode = os.environ.get("HYMET_SCREEN_EXCHANGE", exchange)
         self.last_exchange = None
-        self._pairs = None
+        self.cap = int(min(1 << 20, max(4096, int(db.n_entries) // 8)))
+        self._rec = self._all = self._pin = None
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
         return getattr(self.scr, name)
+
+    def _dense(self):
+        t = counts_tensor(self.scr, self.device)
+        torch.cuda.current_stream().synchronize()
+        if t.numel():
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)      # the one dense NCCL all-reduce of the path
+        torch.cuda.current_stream().synchronize()
+        self.last_exchange = "dense"
 
     def exchange(self):
         self.scr.flush()
         if self.world == 1:
             return
         dev = torch.device("cuda", self.device)
-        s = self.db.s
+        s, cap, me = self.db.s, self.cap, dist.get_rank()
+        sparse = self.exchange_mode != "dense"
+        hdr = 2 + s
+        n_rec = hdr + (cap if sparse else 0)
+        if self._rec is None or self._rec.numel() != n_rec:
+            self._rec = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+            self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
+            self._pin = torch.zeros(hdr, dtype=torch.int64, pin_memory=True)
         local = self.scr.mixture()
-        n_hits = int(self.scr.stats()["n_hits"])
-        meta = torch.zeros(s + 2, dtype=torch.int64)
-        meta[0], meta[1] = n_hits, len(local)
+        self._pin[1] = len(local)
         if len(local):
-            meta[2:2 + len(local)] = torch.from_numpy(local.view(np.int64).copy())
-        meta = meta.to(dev)
-        allmeta = torch.empty(self.world * (s + 2), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allmeta, meta)
-        allmeta = allmeta.view(self.world, s + 2).cpu().numpy()
-        me = dist.get_rank()
+            self._pin[2:2 + len(local)] = torch.from_numpy(local.view(np.int64).copy())
+        self._rec[:hdr].copy_(self._pin, non_blocking=True)     # slot 0 (pair count) is rewritten by the kernel
+        if sparse:
+            self.scr.counts_compact_async(self._rec[hdr:].data_ptr(), cap, self._rec.data_ptr())
+        dist.all_gather_into_tensor(self._all, self._rec)
+        heads = self._all.view(self.world, n_rec)[:, :hdr].cpu().numpy()   # the one host sync of the exchange
         for r in range(self.world):
-            n = int(allmeta[r, 1])
+            n = int(heads[r, 1])
             if r != me and n:
-                self.scr.merge_mixture(allmeta[r, 2:2 + n].view(np.uint64))
-        # counts: non-zero entries <= hits; sparse moves world*cap*8 bytes, dense ~2*E*4
-        cap = int(allmeta[:, 0].max())
-        E = int(self.db.n_entries)
-        sparse = self.exchange_mode == "sparse" or (self.exchange_mode == "auto" and cap * 8 * self.world < E * 4)
-        if sparse and cap > 0 and cap < (1 << 31):
-            if self._pairs is None or self._pairs.numel() < cap:
-                self._pairs = torch.empty(max(cap, 1024), dtype=torch.int64, device=dev)
-            mine = self._pairs[:cap]
-            mine.fill_(-1)                                   # id 0xFFFFFFFF = padding
-            torch.cuda.current_stream().synchronize()
-            n = self.scr.counts_compact(mine.data_ptr(), cap)
-            assert n <= cap
-            gathered = torch.empty(self.world * cap, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(gathered, mine)
-            torch.cuda.current_stream().synchronize()
-            for r in range(self.world):
-                if r != me:
-                    self.scr.counts_scatter_add(gathered[r * cap:(r + 1) * cap].data_ptr(), cap)
-            self._keep = gathered                            # alive until finish() has synchronised
-            self.last_exchange = "sparse"
-        elif cap > 0:
-            t = counts_tensor(self.scr, self.device)
-            torch.cuda.current_stream().synchronize()
-            if t.numel():
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)      # the one dense NCCL all-reduce of the path
-            torch.cuda.current_stream().synchronize()
-            self.last_exchange = "dense"
+                self.scr.merge_mixture(heads[r, 2:2 + n].view(np.uint64))
+        if not sparse:
+            return self._dense()
+        n_pairs = heads[:, 0] & 0xFFFFFFFF
+        if int(n_pairs.max()) > cap:          # too many distinct hits for the record: dense all-reduce instead
+            return self._dense()
+        rows = self._all.view(self.world, n_rec)
+        for r in range(self.world):
+            if r != me and int(n_pairs[r]):
+                self.scr.counts_scatter_add(rows[r, hdr:].data_ptr(), int(n_pairs[r]))
+        self.last_exchange = "sparse"
 
     def finish(self, wta: bool = False) -> hs.ScreenResult:
         self.exchange()

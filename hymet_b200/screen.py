@@ -188,6 +188,9 @@ class Screen:
         check(_abi.load().hs_screen_counts_compact(self._h, C.c_void_p(d_pairs_ptr), cap, C.byref(n)))
         return n.value
 
+    def counts_compact_async(self, d_pairs_ptr: int, cap: int, d_n_out_ptr: int):
+        check(_abi.load().hs_screen_counts_compact_async(self._h, C.c_void_p(d_pairs_ptr), cap, C.c_void_p(d_n_out_ptr)))
+
     def counts_scatter_add(self, d_pairs_ptr: int, n_pairs: int):
         check(_abi.load().hs_screen_counts_scatter_add(self._h, C.c_void_p(d_pairs_ptr), n_pairs))
 

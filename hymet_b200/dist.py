@@ -118,6 +118,8 @@ class DistributedScreen:
         self.exchange_mode = os.environ.get("HYMET_SCREEN_EXCHANGE", exchange)
         self.last_exchange = None
         self.cap = int(min(1 << 20, max(4096, int(db.n_entries) // 8)))
+        if self.exchange_mode == "sparse":      # forced: room for every entry, never falls back
+            self.cap = int(max(4096, db.n_entries))
         self._rec = self._all = self._pin = None
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...

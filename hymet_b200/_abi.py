@@ -62,6 +62,8 @@ SIGNATURES = {
     "hs_msh_free": (None, [C.c_void_p]),
     "hs_db_from_msh": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "hs_db_load_msh": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "hs_db_from_msh_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "hs_db_segments": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), u64p, C.POINTER(C.c_uint32)]),
     "hs_db_from_arrays": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, u64p, u64p, u64p,
                                     C.POINTER(C.c_void_p)]),
     "hs_db_info": (C.c_int, [C.c_void_p, C.POINTER(DbInfo)]),
@@ -86,6 +88,7 @@ SIGNATURES = {
     "hs_screen_counts_scatter_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "hs_screen_mixture_get": (C.c_int, [C.c_void_p, u64p, u32p]),
     "hs_screen_mixture_merge": (C.c_int, [C.c_void_p, u64p, C.c_uint32]),
+    "hs_screen_segment_set_size": (C.c_int, [C.c_void_p, C.c_uint32, u64p]),
     "hs_screen_finish": (C.c_int, [C.c_void_p, C.c_int, u64p, u32p, f64p, f64p, C.POINTER(Stats)]),
     "hs_screen_reset": (C.c_int, [C.c_void_p]),
     "hs_screen_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),

@@ -269,6 +269,10 @@ struct hs_db {
     double t_parse = 0, t_build = 0;
     unsigned long long *d_bloom = nullptr;
     uint32_t bloom_mask = 0;
+    // Several .msh files screened in one pass (run_hymet_cami.sh:85-97 streams the query three times):
+    // references [seg_begin[j], seg_begin[j+1]) came from file j, whose sketch size was seg_s[j].
+    std::vector<uint64_t> seg_begin;
+    std::vector<uint32_t> seg_s;
     TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special, d_bloom, bloom_mask}; }
 };
 
@@ -375,6 +379,7 @@ int db_build(hs_db *db, const uint64_t *hashes)
     unsigned long long nd = 0;
     CU(cudaMemcpy(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost));
     db->n_distinct = nd;
+    if (db->seg_begin.empty()) { db->seg_begin = {0, N}; db->seg_s = {db->s}; }
     cudaFree(d_hashes); cudaFree(d_flags); cudaFree(d_nd);
     db->t_build = now_s() - t0;
     return HS_OK;
@@ -521,10 +526,11 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
     return fail(HS_ECUDA, "mixture threshold search did not settle");
 }
 
-uint64_t set_size_of(const std::vector<uint64_t> &mix, bool use64)
-{   // S10: (uint64) (2^W * |M| / max(M)), W = 64 or 32, in double
-    if (mix.empty()) return 0;
-    const double est = pow(2.0, use64 ? 64.0 : 32.0) * (double)mix.size() / (double)mix.back();
+uint64_t set_size_of(const std::vector<uint64_t> &mix, bool use64, uint64_t s_limit = ~0ull)
+{   // S10: (uint64) (2^W * |M| / max(M)), W = 64 or 32, in double; M = the s_limit smallest of mix
+    const uint64_t n = std::min<uint64_t>(mix.size(), s_limit);
+    if (!n) return 0;
+    const double est = pow(2.0, use64 ? 64.0 : 32.0) * (double)n / (double)mix[n - 1];
     if (!(est < 18446744073709551615.0)) return ~0ull;
     return (uint64_t)est;
 }
@@ -621,6 +627,49 @@ HS_API int hs_db_from_msh(const hs_msh *m, hs_db **out)
     int rc = db_build(db, m->d.hashes.data());
     if (rc) { hs_db_free(db); return rc; }
     *out = db;
+    return HS_OK;
+}
+
+HS_API int hs_db_from_msh_multi(const hs_msh *const *ms, uint32_t n, hs_db **out)
+{
+    if (!ms || !n || !out) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    for (uint32_t j = 0; j < n; j++) {
+        if (!ms[j]) return fail(HS_EINVAL, "null sketch handle");
+        if (ms[j]->d.k != ms[0]->d.k || ms[j]->d.seed != ms[0]->d.seed || ms[j]->d.use64 != ms[0]->d.use64)
+            return fail(HS_EUNSUPPORTED, "sketch files differ in k-mer size, seed or hash width: screen them one at a time");
+    }
+    auto *db = new hs_db();
+    db->k = ms[0]->d.k; db->seed = ms[0]->d.seed; db->use64 = ms[0]->d.use64;
+    std::vector<uint64_t> hashes;
+    db->offsets.push_back(0);
+    db->seg_begin.push_back(0);
+    for (uint32_t j = 0; j < n; j++) {
+        const MshData &d = ms[j]->d;
+        db->s = std::max(db->s, d.s);       // the mixture keeps max s; each file's set size uses its own prefix (S9, S10)
+        db->t_parse += d.t_parse_s;
+        const uint64_t base = hashes.size();
+        hashes.insert(hashes.end(), d.hashes.begin(), d.hashes.end());
+        for (size_t i = 1; i < d.offsets.size(); i++) db->offsets.push_back(base + d.offsets[i]);
+        db->names.insert(db->names.end(), d.names.begin(), d.names.end());
+        db->comments.insert(db->comments.end(), d.comments.begin(), d.comments.end());
+        db->lengths.insert(db->lengths.end(), d.lengths.begin(), d.lengths.end());
+        db->seg_begin.push_back(db->offsets.size() - 1);
+        db->seg_s.push_back(d.s);
+    }
+    db->n_refs = db->offsets.size() - 1; db->n_entries = hashes.size();
+    int rc = db_build(db, hashes.data());
+    if (rc) { hs_db_free(db); return rc; }
+    *out = db;
+    return HS_OK;
+}
+
+HS_API int hs_db_segments(const hs_db *db, uint32_t *n_segments, uint64_t *ref_begin, uint32_t *seg_s)
+{
+    if (!db || !n_segments) return fail(HS_EINVAL, "null argument");
+    *n_segments = (uint32_t)db->seg_s.size();
+    if (ref_begin) memcpy(ref_begin, db->seg_begin.data(), db->seg_begin.size() * 8);
+    if (seg_s) memcpy(seg_s, db->seg_s.data(), db->seg_s.size() * 4);
     return HS_OK;
 }
 
@@ -1031,7 +1080,7 @@ HS_API int hs_screen_flush(hs_screen *s)
     s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
     s->st.n_mix_passes = s->mix.passes;
     s->st.n_mixture = s->mixture.size();
-    s->st.set_size = set_size_of(s->mixture, s->db->use64);
+    s->st.set_size = set_size_of(s->mixture, s->db->use64, s->db->seg_s[0]);
     rc = collect_stream_ms(s);
     if (rc) return rc;
     float ms = 0;
@@ -1093,6 +1142,15 @@ HS_API int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes, uint32_t *n)
     return HS_OK;
 }
 
+HS_API int hs_screen_segment_set_size(hs_screen *s, uint32_t segment, uint64_t *set_size)
+{
+    if (!s || !set_size) return fail(HS_EINVAL, "null argument");
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    if (segment >= s->db->seg_s.size()) return fail(HS_EINVAL, "segment index out of range");
+    *set_size = set_size_of(s->mixture, s->db->use64, s->db->seg_s[segment]);
+    return HS_OK;
+}
+
 HS_API int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n)
 {
     if (!s || (!hashes && n)) return fail(HS_EINVAL, "null argument");
@@ -1103,7 +1161,7 @@ HS_API int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_
     s->mixture.erase(std::unique(s->mixture.begin(), s->mixture.end()), s->mixture.end());
     if (s->mixture.size() > s->db->s) s->mixture.resize(s->db->s);
     s->st.n_mixture = s->mixture.size();
-    s->st.set_size = set_size_of(s->mixture, s->db->use64);
+    s->st.set_size = set_size_of(s->mixture, s->db->use64, s->db->seg_s[0]);
     return HS_OK;
 }
 
@@ -1119,21 +1177,30 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
     CU(cudaEventRecord(s->red0, s->stream));
     CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
     s->st.n_launches++;
+    const size_t n_seg = db->seg_s.size();
     if (wta && E) {
         if (!s->d_winner) {
             CU(cudaMalloc((void **)&s->d_best_score, E * 8));
             CU(cudaMalloc((void **)&s->d_best_len, E * 8));
             CU(cudaMalloc((void **)&s->d_winner, E * 4));
         }
-        CU(launch_winner(db->d_offsets, N, db->d_canon, s->d_counts, s->d_shared, db->d_lengths, s->d_best_score,
-                         s->d_best_len, s->d_winner, E, g_sm, s->stream));
-        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, s->d_winner, s->d_shared, s->d_median, g_sm,
-                                s->stream));
-        s->st.n_launches += 4;
+        for (size_t j = 0; j < n_seg; j++) {   // -w is a competition among the references of one .msh (S12)
+            const uint64_t b = db->seg_begin[j], n = db->seg_begin[j + 1] - b;
+            if (!n) continue;
+            CU(launch_winner(db->d_offsets + b, n, db->d_canon, s->d_counts, s->d_shared + b, db->d_lengths + b,
+                             s->d_best_score, s->d_best_len, s->d_winner, E, g_sm, s->stream));
+            CU(launch_sketch_reduce(db->d_offsets + b, n, db->d_canon, s->d_counts, s->d_winner, s->d_shared + b,
+                                    s->d_median + b, g_sm, s->stream));
+            s->st.n_launches += 4;
+        }
     }
-    CU(launch_stats(db->k, s->st.set_size, N, s->d_shared, nullptr, db->d_offsets, nullptr, s->d_identity, s->d_pvalue,
-                    s->stream));
-    s->st.n_launches++;
+    for (size_t j = 0; j < n_seg; j++) {
+        const uint64_t b = db->seg_begin[j], n = db->seg_begin[j + 1] - b;
+        if (!n) continue;
+        CU(launch_stats(db->k, set_size_of(s->mixture, db->use64, db->seg_s[j]), n, s->d_shared + b, nullptr,
+                        db->d_offsets + b, nullptr, s->d_identity + b, s->d_pvalue + b, s->stream));
+        s->st.n_launches++;
+    }
     CU(cudaEventRecord(s->red1, s->stream));
     std::vector<uint32_t> sh(N);
     if (N) {

@@ -54,6 +54,37 @@ class Database:
         return cls(h.value, device)
 
     @classmethod
+    def load_msh_multi(cls, paths, device: int = 0) -> "Database":
+        """One table over several .msh files (row a3: run_hymet_cami.sh:85-97 screens sketch1-3.msh in
+        turn); `segments` gives each file's reference range, `segment_s` its sketch size."""
+        _abi.init(device)
+        L = _abi.load()
+        handles = []
+        try:
+            for p in paths:
+                m = C.c_void_p()
+                check(L.hs_msh_open(str(p).encode(), C.byref(m)))
+                handles.append(m)
+            arr = (C.c_void_p * len(handles))(*[m.value for m in handles])
+            h = C.c_void_p()
+            check(L.hs_db_from_msh_multi(arr, len(handles), C.byref(h)))
+        finally:
+            for m in handles:
+                L.hs_msh_free(m)
+        return cls(h.value, device)
+
+    @property
+    def segments(self):
+        """[(first reference, one past the last)] per source file."""
+        n = C.c_uint32()
+        check(_abi.load().hs_db_segments(self._h, C.byref(n), None, None))
+        rb = np.zeros(n.value + 1, np.uint64)
+        ss = np.zeros(n.value, np.uint32)
+        check(_abi.load().hs_db_segments(self._h, C.byref(n), _ptr(rb, C.c_uint64), _ptr(ss, C.c_uint32)))
+        self.segment_s = [int(x) for x in ss]
+        return [(int(rb[j]), int(rb[j + 1])) for j in range(n.value)]
+
+    @classmethod
     def from_arrays(cls, k: int, s: int, seed: int, offsets, hashes, lengths=None, device: int = 0) -> "Database":
         _abi.init(device)
         offsets = np.ascontiguousarray(offsets, np.uint64)
@@ -199,6 +230,11 @@ class Screen:
         n = C.c_uint32()
         check(_abi.load().hs_screen_mixture_get(self._h, _ptr(out, C.c_uint64), C.byref(n)))
         return out[:n.value].copy()
+
+    def segment_set_size(self, segment: int) -> int:
+        v = C.c_uint64()
+        check(_abi.load().hs_screen_segment_set_size(self._h, segment, C.byref(v)))
+        return v.value
 
     def merge_mixture(self, hashes):
         hashes = np.ascontiguousarray(hashes, np.uint64)

@@ -94,6 +94,16 @@ void hs_msh_free(hs_msh *m);
 /* ---- database on the GPU (row a5: the "Loading..." hash-table build) ------- */
 int hs_db_from_msh(const hs_msh *m, hs_db **out);
 int hs_db_load_msh(const char *path, hs_db **out); /* open + from_msh */
+/* Row a3 (run_hymet_cami.sh:85-97 screens the same contigs against data/sketch1-3.msh, one mash
+ * process each): ONE table over the references of n sketch files, in file order, so that a single
+ * pass over the query serves all of them.  Reference indices of file j are
+ * [ref_begin[j], ref_begin[j+1]) (hs_db_segments).  Counts and the mixture do not depend on the
+ * file; winner-take-all and the set size (hence p-values) are evaluated per file, with that
+ * file's sketch size.  The files must agree in k, seed and hash width (HS_EUNSUPPORTED if not). */
+int hs_db_from_msh_multi(const hs_msh *const *ms, uint32_t n, hs_db **out);
+/* n_segments = number of files the db was built from (1 for the other constructors);
+ * ref_begin[n_segments+1], seg_s[n_segments] may be NULL. */
+int hs_db_segments(const hs_db *db, uint32_t *n_segments, uint64_t *ref_begin, uint32_t *seg_s);
 /* Build from flat host arrays: offsets[n_refs+1], hashes[offsets[n_refs]] ascending per
  * reference, lengths[n_refs] (may be NULL -> 0).  Names are empty. */
 int hs_db_from_arrays(uint32_t k, uint32_t s, uint32_t seed, uint64_t n_refs, const uint64_t *offsets,
@@ -156,6 +166,8 @@ int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t cap, vo
 int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs);
 int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);
 int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n);
+/* Set size (S10) used for the p-values of one file of a multi-file db (after flush). */
+int hs_screen_segment_set_size(hs_screen *s, uint32_t segment, uint64_t *set_size);
 
 /* rows a11-a15: shared, median multiplicity, identity, p-value for every sketch, in
  * sketch order.  winner_take_all = mash's -w (S17).  Arrays have n_refs elements. */

@@ -530,3 +530,98 @@ def test_bloom_second_level_filter_is_exact():
     off, _ = compare_screen(db, odb, fasta, False, probe_filter=False)
     assert res.stats["n_hits"] == off.stats["n_hits"] and res.stats["n_probes"] < 0.2 * off.stats["n_probes"]
     assert int(res.shared[20:30].min()) > 100     # the tiny genomes in the query are found
+
+
+# ------------------------------------------------- rows a2/a3: three sketch files, one pass -------
+def _three_dbs(tmp_path, rng):
+    """sketch1-3.msh stand-ins: overlapping reference sets (a hash may live in all three), the
+    third with a different sketch size; returns paths + the genomes."""
+    genomes = [synth.random_genome(rng, 30_000) for _ in range(36)]
+    genomes += [synth.mutate(genomes[i], 0.02, rng) for i in range(6)]          # relatives: -w has work to do
+    sets = [(list(range(0, 20)) + [36, 37], 1000), (list(range(10, 30)) + [38, 39, 0], 1000),
+            (list(range(25, 36)) + [40, 41, 5, 12], 500)]
+    paths = []
+    for j, (idx, s) in enumerate(sets):
+        offsets, hashes, lengths = build_db([genomes[i] for i in idx], 21, s)
+        db = mshfmt.SketchDB(k=21, s=s, names=[synth.gcf_name(i) for i in idx], comments=["db%d genome %d" % (j, i) for i in idx],
+                             lengths=lengths - np.arange(len(idx), dtype=np.uint64) % np.uint64(3), offsets=offsets, hashes=hashes)
+        p = str(tmp_path / ("sketch%d.msh" % (j + 1)))
+        mshfmt.write_msh(p, db)
+        paths.append(p)
+    return paths, genomes
+
+
+@pytest.mark.parametrize("wta", [False, True])
+def test_multi_file_db_equals_one_screen_per_file(tmp_path, wta):
+    rng = np.random.default_rng(21)
+    paths, genomes = _three_dbs(tmp_path, rng)
+    fasta = synth.to_fasta(synth.cut_contigs(rng, genomes[:32:3] + genomes[36:40], 400_000, 0.01, median=5000.0), "q")
+    db = hs.Database.load_msh_multi(paths)
+    segs = db.segments
+    assert len(segs) == 3 and db.segment_s == [1000, 1000, 500] and db.s == 1000 and segs[-1][1] == db.n_refs
+    scr = hs.Screen(db)
+    scr.feed_text(fasta, 2)
+    res = scr.finish(wta)
+    for j, (p, (b, e)) in enumerate(zip(paths, segs)):
+        odb = orc.OracleDB.load_msh(p)
+        want = odb.screen_text(fasta, threads=2, wta=wta)
+        assert e - b == odb.n_refs
+        assert res.shared[b:e].tolist() == want.shared.tolist()
+        assert res.median[b:e].tolist() == want.median.tolist()
+        assert scr.segment_set_size(j) == want.set_size
+        assert scr.mixture()[:db.segment_s[j]].tolist() == want.mixture.tolist()
+        assert rel_close(res.identity[b:e], want.identity) and rel_close(res.pvalue[b:e], want.pvalue)
+        assert [db.names[i] for i in range(b, e)] == [odb.name(i) for i in range(odb.n_refs)]
+        if wta:
+            assert int(want.shared.sum()) > 0
+    scr.close()
+    # files that disagree in k cannot share a table
+    offsets, hashes, lengths = build_db(genomes[:3], 16, 200)
+    other = str(tmp_path / "k16.msh")
+    mshfmt.write_msh(other, mshfmt.SketchDB(k=16, s=200, names=list("abc"), comments=[""] * 3, lengths=lengths,
+                                            offsets=offsets, hashes=hashes))
+    with pytest.raises(hs.HsError, match="one at a time"):
+        hs.Database.load_msh_multi([paths[0], other])
+
+
+def test_fused_mash_stage_equals_three_reference_runs(tmp_path):
+    """bin/hymet-mash-stage (one pass over the contigs for sketch1-3) leaves the same fifteen files and
+    the same merged candidate list as run_hymet_cami.sh:85-97 = three mash.sh runs; the per-file `mash
+    screen` output comes from the oracle CLI, mash.sh:15-55 from hymet_b200.stage.select, which
+    tests/test_stage_cpu.py pins against the unmodified reference script."""
+    from hymet_b200 import stage
+    rng = np.random.default_rng(22)
+    paths, genomes = _three_dbs(tmp_path, rng)
+    indir = tmp_path / "input"; indir.mkdir()
+    (indir / "sample_0.fna").write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[:30:2], 300_000, 0.01, median=5000.0), "s"))
+    (indir / "sample_1.fna").write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[20:40], 200_000, 0.06, median=3000.0), "t"))
+    (indir / "notes.txt").write_text("not a contig file\n")
+    orc.build()
+    files, n_fna = stage.input_files(str(indir))
+    assert n_fna == 2
+    od = tmp_path / "out"; od.mkdir()
+    tags = ("", "gtdb_", "custom_")
+    outs = [[str(od / (t + f)) for f in ("screen.tab", "filtered.tab", "sorted.tab", "top_hits.tab", "selected_genomes.txt")]
+            for t in tags]
+    argv = ["--merge", "-p", "4", str(indir), "0.9"]
+    for p, o in zip(paths, outs):
+        argv += [p] + o
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "hymet-mash-stage")] + argv, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    want_sel, want_log = [], ""
+    for p, o in zip(paths, outs):
+        tab = subprocess.run([orc.BIN, "screen", "-p", "8", "-v", "0.9", p] + files, capture_output=True, check=True).stdout
+        assert tab.count(b"\n") >= 5
+        w = stage.select(tab, n_fna, "0.9")
+        assert open(o[0], "rb").read() == tab
+        for path, key in zip(o[1:4], ("filtered", "sorted", "top_hits")):
+            assert open(path, "rb").read() == w[key], path
+        want_sel.append(w["selected"])
+        want_log += w["log"]
+    assert open(outs[1][4], "rb").read() == want_sel[1] and open(outs[2][4], "rb").read() == want_sel[2]
+    assert open(outs[0][4], "rb").read() == stage.merge_selected(want_sel)       # run_hymet_cami.sh:91,96,97
+    assert r.stdout.decode() == want_log
+    # and the one-file drop-in prints what the fused pass wrote for that file
+    one = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", "-p", "8", "-v", "0.9", paths[2]] + files,
+                         capture_output=True, check=True).stdout
+    assert one == open(outs[2][0], "rb").read()

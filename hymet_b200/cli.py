@@ -91,9 +91,16 @@ def screen_main(args: List[str], stdout=None) -> int:
     from .tsv import screen_lines
 
     device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
+    import time
+    t0 = time.perf_counter()
+    marks = []
+    mark = lambda what: marks.append((what, time.perf_counter()))
     try:
+        hs._abi.init(device)
+        mark("cuda_init")
         sys.stderr.write("Loading %s...\n" % db_path)
         db = hs.Database.load_msh(db_path, device)
+        mark("load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
         sys.stderr.write("   %d distinct hashes.\n" % db.n_distinct)
         scr = hs.Screen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
         sys.stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
@@ -102,7 +109,9 @@ def screen_main(args: List[str], stdout=None) -> int:
                 _err("could not open %s for reading." % p)
                 return 1
             scr.feed_fasta(p, threads)
+        mark("feed")
         scr.flush()
+        mark("flush")
         st = scr.stats()
         if st["n_records"] == 0:
             _err("Did not find sequence records in inputs.")
@@ -115,11 +124,19 @@ def screen_main(args: List[str], stdout=None) -> int:
             sys.stderr.write("Reallocating to winners...\n")
         sys.stderr.write("Computing coverage medians...\n")
         res = scr.finish(wta)
+        mark("finish")
         sys.stderr.write("Writing output...\n")
         for ln in screen_lines(res.shared, db.sizes, res.median, res.identity, res.pvalue, db.names, db.comments,
                                imin, pmax):
             stdout.write(ln)
         stdout.flush()
+        mark("write")
+        if os.environ.get("HYMET_SCREEN_TIMING"):
+            prev = t0
+            for what, t in marks:
+                sys.stderr.write("[timing] %-40s %8.3f s\n" % (what, t - prev))
+                prev = t
+            sys.stderr.write("[timing] %-40s %8.3f s\n" % ("total inside screen_main", prev - t0))
         return 0
     except hs.HsError as e:
         _err(e.msg)

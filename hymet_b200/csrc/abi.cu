@@ -9,6 +9,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -276,6 +279,20 @@ struct hs_db {
     TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special, d_bloom, bloom_mask}; }
 };
 
+// pinned ring the file readers pread() into: two slots per reader thread
+struct FileRing {
+    char *base = nullptr;
+    size_t slot_cap = 0;
+    std::vector<cudaEvent_t> free_ev;   // recorded on the copy stream once a slot's text is in HBM
+    void release()
+    {
+        if (base) cudaFreeHost(base);
+        base = nullptr; slot_cap = 0;
+        for (auto e : free_ev) cudaEventDestroy(e);
+        free_ev.clear();
+    }
+};
+
 struct Staging {
     uint64_t *seq = nullptr;
     uint32_t *inv = nullptr;
@@ -293,6 +310,11 @@ struct hs_screen {
     uint64_t piece_positions = (uint64_t)32 << 20;  // packed host feeds are uploaded + launched in pieces
     Ingest ingest;
     int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
+    FileRing ring;
+    uint64_t file_block = (uint64_t)16 << 20;   // plain FASTA files: nominal bytes per reader block
+    int file_readers = 4;
+    std::mutex ingest_mu;                       // one thread at a time hands a span to the device parser
+    std::mutex giant_mu;                        // records larger than a ring slot take the host path, one at a time
     uint32_t *d_counts = nullptr;
     unsigned long long *d_stats = nullptr;
     MixEngine mix;
@@ -780,6 +802,8 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "chunk_bases")) s->chunk_text = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "piece_bases")) s->piece_positions = value > 8192 ? (uint64_t)value : 8192;
     else if (!strcmp(key, "ingest")) s->ingest_mode = (int)value;
+    else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
+    else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
     else return fail(HS_EINVAL, std::string("unknown option ") + key);
     return HS_OK;
@@ -843,7 +867,7 @@ int feed_host_chunk(hs_screen *s, const uint64_t *seq, const uint32_t *inv, uint
 
 // Row a6 on the GPU: upload one record-aligned span of raw FASTA text, parse + pack it on
 // the device, stream it.  Everything is enqueued; the host only waits for a free slot.
-int feed_span_device(hs_screen *s, const char *text, size_t len)
+int feed_span_device(hs_screen *s, const char *text, size_t len, cudaEvent_t host_free_ev = nullptr)
 {
     if (!len) return HS_OK;
     if (len >= ((size_t)1 << 30)) return fail(HS_EINVAL, "text chunk too large for the device parser");
@@ -866,6 +890,7 @@ int feed_span_device(hs_screen *s, const char *text, size_t len)
     CU(s->arena.alloc(alloc * 4, &dinv));
     CU(cudaMemcpyAsync(sl->raw, text, len, cudaMemcpyHostToDevice, s->copy_stream));
     CU(cudaEventRecord(sl->copied, s->copy_stream));
+    if (host_free_ev) CU(cudaEventRecord(host_free_ev, s->copy_stream));
     CU(cudaStreamWaitEvent(s->stream, sl->copied, 0));
     FaScratch sc = in.sc;
     sc.chunk_positions = d_npos;
@@ -1008,6 +1033,139 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     return HS_OK;
 }
 
+size_t pread_full(int fd, char *dst, size_t n, uint64_t off)
+{
+    size_t got = 0;
+    while (got < n) {
+        const ssize_t r = pread(fd, dst + got, n - got, (off_t)(off + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    return got;
+}
+
+// index of the first record start ('>' right after a newline) in buf[from, n), or n
+size_t find_record_start(const char *buf, size_t from, size_t n)
+{
+    if (from < 1) from = 1;
+    while (from < n) {
+        const char *p = (const char *)memchr(buf + from, '>', n - from);
+        if (!p) return n;
+        const size_t i = (size_t)(p - buf);
+        if (buf[i - 1] == '\n') return i;
+        from = i + 1;
+    }
+    return n;
+}
+
+// Row a6 for a plain FASTA file: reader threads pread() disjoint blocks of the file into a
+// pinned ring; each block is trimmed to whole records (it starts at the first record start at or
+// after its nominal begin and runs to the first record start at or after its nominal end, so
+// blocks are independent of each other) and handed to the device parser.  File -> page-cache
+// copy -> DMA -> parse/pack/hash on the GPU; no host-side parsing at all.
+int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
+{
+    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    const uint64_t B = s->file_block;
+    const uint64_t n_blocks = (size + B - 1) / B;
+    int T = std::max(1, std::min(threads, s->file_readers));
+    if ((uint64_t)T > n_blocks) T = (int)n_blocks;
+    const size_t cap = (size_t)(B + B / 2 + 4096);
+    if (s->ring.slot_cap < cap || s->ring.free_ev.size() < (size_t)2 * T) {
+        CU(cudaStreamSynchronize(s->copy_stream));
+        s->ring.release();
+        CU(cudaHostAlloc((void **)&s->ring.base, cap * 2 * T, cudaHostAllocDefault));
+        s->ring.slot_cap = cap;
+        for (int i = 0; i < 2 * T; i++) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            s->ring.free_ev.push_back(e);
+        }
+    }
+    std::atomic<uint64_t> next{0};
+    std::atomic<int> rc_all{HS_OK};
+    std::string err_all;
+    std::mutex err_mu;
+    auto reader = [&](int t) {
+        cudaSetDevice(g_device);
+        int flip = 0;
+        auto bail = [&](int rc) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (rc_all.load() == HS_OK) { rc_all = rc; err_all = g_err; }
+        };
+        for (;;) {
+            const uint64_t j = next.fetch_add(1);
+            if (j >= n_blocks || rc_all.load() != HS_OK) break;
+            const size_t slot = (size_t)t * 2 + (size_t)(flip ^= 1);
+            char *buf = s->ring.base + slot * s->ring.slot_cap;
+            if (cudaEventSynchronize(s->ring.free_ev[slot]) != cudaSuccess) { bail(fail(HS_ECUDA, "ring event")); break; }
+            const double t0 = now_s();
+            const uint64_t off0 = j ? j * B - 1 : 0;          // one byte early: is there a newline before the block?
+            const uint64_t nominal_end = std::min(size, (j + 1) * B);
+            size_t got = pread_full(fd, buf, (size_t)std::min<uint64_t>(size - off0, nominal_end - off0 + 65536), off0);
+            if (off0 + got < nominal_end) { bail(fail(HS_EIO, "short read")); break; }
+            // first record that starts inside this block (block 0 starts at the top of the file)
+            size_t b = 0;
+            if (j) {
+                b = find_record_start(buf, 1, (size_t)(nominal_end - off0));
+                if (b >= nominal_end - off0) continue;        // no record starts here: an earlier block owns these bytes
+            }
+            // first record start at or after the nominal end: read on until it shows up
+            size_t e = got, from = (size_t)(nominal_end - off0);
+            bool giant = false;
+            for (;;) {
+                e = find_record_start(buf, from, got);
+                if (e < got || off0 + got >= size) break;
+                if (got >= cap) { giant = true; break; }
+                from = got;
+                const size_t more = (size_t)std::min<uint64_t>(std::min<uint64_t>(cap - got, size - off0 - got), (uint64_t)4 << 20);
+                const size_t r = pread_full(fd, buf + got, more, off0 + got);
+                if (!r) { bail(fail(HS_EIO, "short read")); break; }
+                got += r;
+            }
+            if (rc_all.load() != HS_OK) break;
+            const double t1 = now_s();
+            int rc = HS_OK;
+            if (giant) {
+                // a record longer than a ring slot: find its end, read it into ordinary memory and let
+                // the host packer take it (rare: chromosome-sized contigs)
+                std::vector<char> tmp((size_t)1 << 20);
+                uint64_t pos = off0 + got, end = size;
+                char prev = buf[got - 1];
+                while (pos < size) {
+                    const size_t r = pread_full(fd, tmp.data(), tmp.size(), pos);
+                    if (!r) break;
+                    size_t hit = r;
+                    if (tmp[0] == '>' && prev == '\n') hit = 0; else hit = find_record_start(tmp.data(), 1, r);
+                    if (hit < r) { end = pos + hit; break; }
+                    prev = tmp[r - 1];
+                    pos += r;
+                }
+                std::vector<char> rec((size_t)(end - (off0 + b)));
+                if (pread_full(fd, rec.data(), rec.size(), off0 + b) != rec.size()) { bail(fail(HS_EIO, "short read")); break; }
+                std::lock_guard<std::mutex> lk(s->giant_mu);
+                rc = feed_text_impl(s, rec.data(), rec.size(), 1);
+            } else {
+                std::lock_guard<std::mutex> lk(s->ingest_mu);
+                rc = feed_span_device(s, buf + b, e - b, s->ring.free_ev[slot]);
+            }
+            if (g_debug_timing)
+                fprintf(stderr, "[hs] block %llu reader %d: %zu B read %.2f ms (%.2f GB/s) submit %.2f ms%s\n", (unsigned long long)j,
+                        t, got, 1e3 * (t1 - t0), got / (t1 - t0) / 1e9, 1e3 * (now_s() - t1), giant ? " [giant record: host path]" : "");
+            if (rc != HS_OK) { bail(rc); break; }
+        }
+    };
+    if (T == 1) {
+        reader(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; t++) pool.emplace_back(reader, t);
+        for (auto &th : pool) th.join();
+    }
+    if (rc_all != HS_OK) return fail(rc_all, err_all);
+    return HS_OK;
+}
+
 }  // namespace
 
 HS_API int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads)
@@ -1021,6 +1179,23 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
 {
     if (!s || !path) return fail(HS_EINVAL, "null argument");
     NEED_DEVICE();
+    // plain FASTA in a regular file: stream it through the pinned ring to the device parser
+    if (s->ingest_mode != 0 && strcmp(path, "-") != 0) {
+        const int fd = open(path, O_RDONLY);
+        struct stat sb;
+        if (fd >= 0 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
+            char head[256];
+            const size_t hn = pread_full(fd, head, sizeof head, 0);
+            size_t first = 0;
+            while (first < hn && (head[first] == '\n' || head[first] == '\r')) first++;
+            if (first < hn && head[first] == '>') {   // not gzip (1f 8b), not FASTQ
+                const int rc = feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads);
+                close(fd);
+                return rc;
+            }
+        }
+        if (fd >= 0) close(fd);
+    }
     std::vector<char> buf;
     std::string err;
     if (!slurp_file(path, buf, err)) return fail(HS_EIO, err);
@@ -1244,6 +1419,7 @@ HS_API void hs_screen_free(hs_screen *s)
     s->mix.destroy();
     s->arena.release();
     s->ingest.release();
+    s->ring.release();
     for (auto &g : s->staging) {
         if (g.seq) cudaFreeHost(g.seq);
         if (g.inv) cudaFreeHost(g.inv);

@@ -625,3 +625,42 @@ def test_fused_mash_stage_equals_three_reference_runs(tmp_path):
     one = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", "-p", "8", "-v", "0.9", paths[2]] + files,
                          capture_output=True, check=True).stdout
     assert one == open(outs[2][0], "rb").read()
+
+
+# ------------------------------------------------- row a6: plain FASTA files streamed through the pinned ring -------
+@pytest.mark.parametrize("variant", ["plain", "crlf_no_final_newline", "leading_blank_lines", "one_record"])
+def test_file_streaming_blocks_and_giant_records(tmp_path, variant):
+    """hs_screen_feed_fasta on a plain FASTA file: reader threads cut the file into blocks of whole
+    records for the device parser.  Tiny blocks (64 KiB) put hundreds of block boundaries inside the
+    file, records longer than a ring slot (the 300 kb ones) take the host path; the result must not
+    depend on any of it."""
+    rng = np.random.default_rng(33)
+    genomes = [synth.random_genome(rng, 300_000) for _ in range(6)]
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    contigs = synth.cut_contigs(rng, genomes, 3_000_000, 0.01, median=9000.0) + [genomes[2], synth.revcomp(genomes[4])]
+    order = rng.permutation(len(contigs))
+    text = synth.to_fasta([contigs[i] for i in order], "c")
+    if variant == "crlf_no_final_newline":
+        text = text.replace(b"\n", b"\r\n").rstrip(b"\r\n")
+    elif variant == "leading_blank_lines":
+        text = b"\n\n" + text
+    elif variant == "one_record":
+        text = synth.to_fasta([genomes[1]], "whole")
+    path = str(tmp_path / "contigs.fna")
+    open(path, "wb").write(text)
+    want = odb.screen_text(text, threads=2)
+    assert int(want.shared.sum()) > 1000
+    for block, readers in ((65536, 3), (1 << 20, 2), (16 << 20, 4)):
+        scr = hs.Screen(db)
+        scr.set_option("file_block_bytes", block)
+        scr.set_option("file_readers", readers)
+        scr.feed_fasta(path, 4)
+        res = scr.finish(False)
+        assert res.shared.tolist() == want.shared.tolist(), (variant, block)
+        assert res.median.tolist() == want.median.tolist()
+        assert res.set_size == want.set_size and scr.mixture().tolist() == want.mixture.tolist()
+        assert res.stats["n_valid_kmers"] == want.n_kmers
+        assert res.stats["n_records"] == text.count(b">")
+        scr.close()

@@ -87,20 +87,19 @@ def screen_main(args: List[str], stdout=None) -> int:
         _err("option value out of range")
         return 1
 
-    from . import screen as hs   # ctypes + numpy only: no torch import on the CLI path
-    from .tsv import screen_lines
-
-    device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
     import time
     t0 = time.perf_counter()
     marks = []
     mark = lambda what: marks.append((what, time.perf_counter()))
+    from . import screen as hs   # ctypes + numpy only: no torch import on the CLI path
+    from .tsv import screen_lines_db
+    mark("imports")
+
+    device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
     try:
-        hs._abi.init(device)
-        mark("cuda_init")
         sys.stderr.write("Loading %s...\n" % db_path)
-        db = hs.Database.load_msh(db_path, device)
-        mark("load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
+        db = hs.Database.load_msh(db_path, device)       # CUDA context creation overlaps the .msh parse
+        mark("cuda_init + load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
         sys.stderr.write("   %d distinct hashes.\n" % db.n_distinct)
         scr = hs.Screen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
         sys.stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
@@ -126,8 +125,7 @@ def screen_main(args: List[str], stdout=None) -> int:
         res = scr.finish(wta)
         mark("finish")
         sys.stderr.write("Writing output...\n")
-        for ln in screen_lines(res.shared, db.sizes, res.median, res.identity, res.pvalue, db.names, db.comments,
-                               imin, pmax):
+        for ln in screen_lines_db(res, db, imin, pmax):
             stdout.write(ln)
         stdout.flush()
         mark("write")

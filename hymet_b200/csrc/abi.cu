@@ -1102,7 +1102,7 @@ int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
             const double t0 = now_s();
             const uint64_t off0 = j ? j * B - 1 : 0;          // one byte early: is there a newline before the block?
             const uint64_t nominal_end = std::min(size, (j + 1) * B);
-            size_t got = pread_full(fd, buf, (size_t)std::min<uint64_t>(size - off0, nominal_end - off0 + 65536), off0);
+            size_t got = pread_full(fd, buf, (size_t)std::min<uint64_t>(size - off0, nominal_end - off0 + std::min<uint64_t>(65536, B / 4)), off0);
             if (off0 + got < nominal_end) { bail(fail(HS_EIO, "short read")); break; }
             // first record that starts inside this block (block 0 starts at the top of the file)
             size_t b = 0;

@@ -48,10 +48,38 @@ class Database:
 
     @classmethod
     def load_msh(cls, path: str, device: int = 0) -> "Database":
-        _abi.init(device)
-        h = C.c_void_p()
-        check(_abi.load().hs_db_load_msh(path.encode(), C.byref(h)))
+        """Parse the .msh on a helper thread (host only) while this thread creates the CUDA context."""
+        import threading
+        L = _abi.load()
+        m, box = C.c_void_p(), {}
+
+        def parse():
+            try:
+                check(L.hs_msh_open(path.encode(), C.byref(m)))     # hs_last_error() is thread local: check here
+            except Exception as e:                                   # noqa: BLE001
+                box["err"] = e
+
+        th = threading.Thread(target=parse)
+        th.start()
+        try:
+            _abi.init(device)
+        finally:
+            th.join()
+        if "err" in box:
+            raise box["err"]
+        try:
+            h = C.c_void_p()
+            check(L.hs_db_from_msh(m, C.byref(h)))
+        finally:
+            L.hs_msh_free(m)
         return cls(h.value, device)
+
+    def ref(self, i: int):
+        """(name, comment, length, sketch size) of reference i."""
+        nm, cm = C.c_char_p(), C.c_char_p()
+        ln, nh = C.c_uint64(), C.c_uint64()
+        check(_abi.load().hs_db_ref(self._h, i, C.byref(nm), C.byref(cm), C.byref(ln), C.byref(nh)))
+        return ((nm.value or b"").decode("utf-8", "replace"), (cm.value or b"").decode("utf-8", "replace"), ln.value, nh.value)
 
     @classmethod
     def load_msh_multi(cls, paths, device: int = 0) -> "Database":

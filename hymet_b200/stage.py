@@ -184,7 +184,7 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
     """jobs: (DB.msh, SCREEN_TAB, FILTERED, SORTED, TOP_HITS, SELECTED) per sketch file."""
     stdout = stdout or sys.stdout
     from . import screen as hs
-    from .tsv import screen_lines
+    from .tsv import screen_lines_db
 
     files, n_fna = input_files(input_dir)
     for j in jobs:
@@ -214,11 +214,8 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
                 sys.stderr.write("ERROR: Did not find sequence records in inputs.\n")
                 return 1
             res = scr.finish(False)
-            names, comments, sizes = db.names, db.comments, db.sizes
             for seg, (b, e) in zip(idx, db.segments):
-                results[seg] = "".join(screen_lines(res.shared[b:e], sizes[b:e], res.median[b:e], res.identity[b:e],
-                                                    res.pvalue[b:e], names[b:e], comments[b:e], 0.0, max_p)
-                                       ).encode("utf-8", "surrogateescape")
+                results[seg] = "".join(screen_lines_db(res, db, 0.0, max_p, b, e)).encode("utf-8", "surrogateescape")
             scr.close()
     except hs.HsError as e:
         sys.stderr.write("ERROR: %s\n" % e.msg)

@@ -56,6 +56,12 @@ def main():
                      "tsv_lines": p.stdout.count(b"\n")})
         gpu_tsv = p.stdout
     out["gpu_cli"] = runs
+    t0 = time.perf_counter()
+    subprocess.run([sys.executable, "-c", "import numpy"], check=True)
+    out["python_numpy_startup_s"] = time.perf_counter() - t0
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", "-p", str(threads), "-v", "0.9", dbp, fap],
+                       capture_output=True, env=dict(env, HYMET_SCREEN_DEBUG_TIMING="1"))
+    out["debug_feed_lines"] = [l for l in p.stderr.decode().splitlines() if l.startswith("[hs] block")][:12]
     from tests import _oracle as orc
     orc.build()
     t0 = time.perf_counter()

@@ -400,6 +400,31 @@ def run_b200(args):
                               "h2d_bytes_per_step": int(pstats[-1]["h2d_bytes"]),
                               "d2h_bytes_per_step": int(pstats[-1]["d2h_bytes"]), "ms_per_step": pms / e_steps,
                               "input": "pre-packed 2-bit + mask words in pinned host memory"}
+        # SURVEY 8d's end-to-end: the FASTA is a FILE in the page cache, read by hs_screen_feed_fasta (reader
+        # threads pread() record-aligned blocks into a pinned ring, the device parses them)
+        import tempfile
+        fdir = tempfile.mkdtemp(prefix="hs_bench_%d_" % rank)
+        fpath = os.path.join(fdir, "contigs.fna")
+        wl.fasta.numpy().tofile(fpath)
+        readers = max(1, min(8, host_threads))
+        scr.set_option("file_readers", readers)
+
+        def step_file():
+            scr.reset()
+            scr.feed_fasta(fpath, host_threads)
+            return scr.finish(args.wta)
+
+        fms, fwall, fstats, fres, _ = timed(step_file, e_steps, 2)
+        line["e2e_file"] = {"value": e_steps * total_bases / (fms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": fms / e_steps,
+                            "h2d_bytes_per_step": int(fstats[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(fstats[-1]["d2h_bytes"]),
+                            "input": "the same FASTA as a file in the page cache (%d B per GPU)" % wl.fasta.numel(),
+                            "reader_threads_per_gpu": readers,
+                            "ok": bool(fres.shared.tolist() == res.shared.tolist() and fres.set_size == res.set_size)}
+        try:
+            os.remove(fpath)
+            os.rmdir(fdir)
+        except OSError:
+            pass
         # the three entry points must agree exactly
         same = (eres.shared.tolist() == res.shared.tolist() and eres.median.tolist() == res.median.tolist()
                 and pres.shared.tolist() == res.shared.tolist() and eres.set_size == res.set_size)

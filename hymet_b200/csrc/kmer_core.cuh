@@ -98,13 +98,73 @@ HS_HD uint32_t ascii4(uint32_t b)
 }
 
 // ---- MurmurHash3_x64_128 ----------------------------------------------------
-HS_HD uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+HS_HD uint64_t rotl64(uint64_t x, int r)
+{
+#if defined(__CUDA_ARCH__)
+    // two funnel shifts; written out because the compiler otherwise builds the low word from a
+    // multiply, a shift and an OR (the kernel is bound by integer issue slots)
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    const uint32_t a = r < 32 ? lo : hi, b = r < 32 ? hi : lo;   // rotate by r mod 32 after an optional swap
+    const uint32_t nh = __funnelshift_l(a, b, (uint32_t)r), nl = __funnelshift_l(b, a, (uint32_t)r);
+    return ((uint64_t)nh << 32) | nl;
+#else
+    return (x << r) | (x >> (64 - r));
+#endif
+}
+// The streaming kernel is bound by the ALU pipe (logic, shifts, carry adds) while the multiply pipe
+// has room (ncu: 77 % vs 63 % busy).  HS_FMA_SHIFT moves work across: x >> 1 as the high half of
+// x * 2^31, and a 64-bit add as a wide multiply-add by one plus a 32-bit add.
+// Measured on B200: SLOWER (5.36 ms vs 4.83 ms per Gbp) -- mul.hi / mad.wide do not issue at the
+// rate of plain multiply-adds -- so it stays off; kept as a documented dead end.
+#ifndef HS_FMA_SHIFT
+#define HS_FMA_SHIFT 0
+#endif
+HS_HD uint32_t shr1_fma(uint32_t x)
+{
+#if defined(__CUDA_ARCH__) && HS_FMA_SHIFT
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(r) : "r"(x));
+    return r;
+#else
+    return x >> 1;
+#endif
+}
+#ifndef HS_FMA_ADD
+#define HS_FMA_ADD HS_FMA_SHIFT
+#endif
+HS_HD uint64_t add64_fma(uint64_t a, uint64_t b)
+{
+#if defined(__CUDA_ARCH__) && HS_FMA_ADD
+    uint64_t t;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(t) : "r"((uint32_t)a), "l"(b));   // b + a.lo, carry included
+    const uint32_t hi = (uint32_t)(t >> 32) + (uint32_t)(a >> 32);
+    return ((uint64_t)hi << 32) | (uint32_t)t;
+#else
+    return a + b;
+#endif
+}
+HS_HD uint64_t xorshift33(uint64_t k)  // k ^ (k >> 33): only the low word changes
+{
+    const uint32_t hi = (uint32_t)(k >> 32);
+    return ((uint64_t)hi << 32) | ((uint32_t)k ^ shr1_fma(hi));
+}
 HS_HD uint64_t fmix64(uint64_t k)
 {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
+    k = xorshift33(k); k *= 0xff51afd7ed558ccdull;
+    k = xorshift33(k); k *= 0xc4ceb9fe1a85ec53ull;
+    k = xorshift33(k);
     return k;
+}
+
+HS_HD uint64_t mul5_add(uint64_t h, uint32_t c)  // h * 5 + c
+{
+#if defined(__CUDA_ARCH__)
+    const uint64_t t = (uint64_t)(uint32_t)h * 5u + c;                       // one wide multiply-add
+    const uint32_t hi = (uint32_t)(h >> 32) * 5u + (uint32_t)(t >> 32);      // one multiply-add
+    return ((uint64_t)hi << 32) | (uint32_t)t;
+#else
+    return h * 5 + c;
+#endif
 }
 
 // h1 of MurmurHash3_x64_128 over the k (<= 32) ASCII bytes given as eight
@@ -159,6 +219,156 @@ HS_HD uint64_t hash_canonical(uint64_t cl, int k, uint32_t seed, bool use64, con
     const uint64_t h = murmur3_h1_words(w, k, seed);
     return use64 ? h : (h & 0xFFFFFFFFull);
 }
+
+// ---- the same hash from PRE-MULTIPLIED table entries ---------------------------------
+// Murmur reads the k-mer string as 64-bit lanes: lane 0 = bytes 0-7 and lane 2 = bytes 16-23 are
+// multiplied by c1 first, lanes 1 and 3 by c2.  A lane is (lo word) + (hi word << 32), so modulo
+// 2^64   lane * c = (u64)lo * c  +  ((u32)(hi * c) << 32):
+// a table of the 64-bit products of all 256 four-letter words (one per constant) turns the first
+// multiply of every lane -- 3 of the 10 64-bit multiplies at k=21, 4 of 12 at k=31 -- into one
+// 64-bit and one 32-bit load plus one add.  Table entries exist for whole words only; a lane
+// that ends inside a word sees 'A' (code 0) in the unused byte positions, whose known product
+// is subtracted.
+constexpr uint64_t kMurmurC1 = 0x87c37b91114253d5ull, kMurmurC2 = 0x4cf5ad432745937full;
+
+HS_HD uint64_t premul_entry(uint32_t b, bool second) { return (uint64_t)ascii4(b) * (second ? kMurmurC2 : kMurmurC1); }
+
+// product of the filler letters of a lane holding nb (1..8) real bytes
+HS_HD uint64_t premul_filler(int nb, bool second)
+{
+    const uint64_t c = second ? kMurmurC2 : kMurmurC1;
+    if (nb >= 8 || nb == 4) return 0;
+    if (nb > 4) return ((uint64_t)(0x41414141u & ~((1u << (8 * (nb - 4))) - 1u)) << 32) * c;
+    return (uint64_t)(0x41414141u & ~((1u << (8 * nb)) - 1u)) * c;
+}
+
+// `Pre::full(cl, i, second)`: 64-bit product of word i's letters; `Pre::low`: its low 32 bits.
+template <class Pre>
+HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use64, const Pre &pre)
+{
+    uint64_t m[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        const int nb = k - 8 * l;
+        uint64_t p = 0;
+        if (nb > 0) {
+            p = pre.full(cl, 2 * l, (l & 1) != 0);
+            if (nb > 4) {   // only the high word changes: one 32-bit add (filler folded in), no carry chain
+                const uint32_t hi = (uint32_t)(p >> 32) + pre.low(cl, 2 * l + 1, (l & 1) != 0) -
+                                    (uint32_t)(premul_filler(nb, (l & 1) != 0) >> 32);
+                p = ((uint64_t)hi << 32) | (uint32_t)p;
+            } else {
+                p -= premul_filler(nb, (l & 1) != 0);
+            }
+        }
+        m[l] = p;
+    }
+    const uint64_t c1 = kMurmurC1, c2 = kMurmurC2;
+    uint64_t h1 = seed, h2 = seed;
+    const int t = 2 * (k >> 4);  // first lane of the tail
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        if (b < (k >> 4)) {
+            uint64_t k1 = m[2 * b], k2 = m[2 * b + 1];
+            k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+            h1 = rotl64(h1, 27); h1 = add64_fma(h1, h2); h1 = mul5_add(h1, 0x52dce729u);
+            k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+            h2 = rotl64(h2, 31); h2 = add64_fma(h2, h1); h2 = mul5_add(h2, 0x38495ab5u);
+        }
+    }
+    if (k & 15) {
+        if ((k & 15) > 8) { uint64_t k2 = m[(t + 1) & 3]; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+        uint64_t k1 = m[t & 3]; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+    }
+    h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
+    h1 = add64_fma(h1, h2); h2 = add64_fma(h2, h1);
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 = add64_fma(h1, h2);
+    return use64 ? h1 : (h1 & 0xFFFFFFFFull);
+}
+
+struct PremulArith {  // host-side stand-in for the shared-memory tables (tests)
+    HS_HD uint64_t full(uint64_t cl, int i, bool second) const { return premul_entry((uint32_t)(cl >> (8 * i)) & 0xFFu, second); }
+    HS_HD uint32_t low(uint64_t cl, int i, bool second) const { return (uint32_t)full(cl, i, second); }
+};
+
+// ---- windowed canonical k-mers (first base MOST significant) ----------------------------
+// One thread owns the 64 bases (prev word, cur word).  Instead of rolling two k-mers base by
+// base, keep the 128-bit window W = prev:cur and R' = revcomp(W) >> 2(33-k) in eight 32-bit
+// registers: the forward k-mer ending at base j of cur is (W >> (62-2j)) & mask and its reverse
+// complement is (R' >> 2j) & mask -- two funnel shifts each, with the same word boundary (j = 16)
+// for both.  Halves the ALU work per k-mer spent before the hash.
+struct Win { uint32_t f0, f1, f2, f3, r0, r1, r2, r3; };  // word 0 least significant
+
+HS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s)  // low 32 bits of (hi:lo) >> s, 0 <= s <= 31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, (uint32_t)s);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> s);
+#endif
+}
+
+HS_HD Win win_init(uint64_t prev, uint64_t cur, int k)
+{
+    Win w;
+    w.f0 = (uint32_t)cur; w.f1 = (uint32_t)(cur >> 32); w.f2 = (uint32_t)prev; w.f3 = (uint32_t)(prev >> 32);
+    const uint64_t rh = pair_reverse64(~cur), rl = pair_reverse64(~prev);  // revcomp(W) = rh:rl
+    const int c = 2 * (33 - k);                                           // 2..64
+    const uint64_t lo = c >= 64 ? rh : ((rl >> c) | (rh << (64 - c)));
+    const uint64_t hi = c >= 64 ? 0ull : (rh >> c);
+    w.r0 = (uint32_t)lo; w.r1 = (uint32_t)(lo >> 32); w.r2 = (uint32_t)hi; w.r3 = (uint32_t)(hi >> 32);
+    return w;
+}
+
+// S5 for the k-mer ending at base j (0..31) of cur: min(forward, reverse complement), both read
+// first-base-most-significant (== memcmp order of the ASCII strings), right aligned in 2k bits.
+// q = j mod 16; (fa,fb,fc)/(ra,rb,rc) = the three window words of the half j lies in
+HS_HD uint64_t canonical_msb_half(uint32_t fa, uint32_t fb, uint32_t fc, uint32_t ra, uint32_t rb, uint32_t rc, int q, int k)
+{
+    const uint32_t flo = funnel_r(fa, fb, 30 - 2 * q), fhi = funnel_r(fb, fc, 30 - 2 * q);
+    const uint32_t rlo = funnel_r(ra, rb, 2 * q), rhi = funnel_r(rb, rc, 2 * q);
+    const uint64_t mask = kmer_mask(k);
+    const uint64_t fm = (((uint64_t)fhi << 32) | flo) & mask, rm = (((uint64_t)rhi << 32) | rlo) & mask;
+    return fm <= rm ? fm : rm;
+}
+
+HS_HD uint64_t canonical_msb(const Win &w, int j, int k)
+{
+    return j < 16 ? canonical_msb_half(w.f1, w.f2, w.f3, w.r0, w.r1, w.r2, j, k)
+                  : canonical_msb_half(w.f0, w.f1, w.f2, w.r1, w.r2, w.r3, j - 16, k);
+}
+
+// Table index byte of string word i (bases 4i..4i+3) of an MSB-first canonical k-mer, already
+// shifted into address position: ((byte) << 6).  The byte holds the word's first base in its top
+// two bits; a word with fewer than four bases is padded with code 0 ('A') at the end.
+HS_HD uint32_t msb_word_index64(uint64_t cm, int i, int k)
+{
+    const int sh = 2 * k - 8 * (i + 1) - 6;
+    const uint32_t x = sh >= 0 ? (uint32_t)(cm >> sh) : ((uint32_t)cm << (-sh));
+    return x & 0x3FC0u;
+}
+
+HS_HD uint32_t pair_reverse8(uint32_t b) { return ((b & 3u) << 6) | ((b & 0xCu) << 2) | ((b >> 2) & 0xCu) | ((b >> 6) & 3u); }
+HS_HD uint64_t premul_entry_msb(uint32_t b, bool second) { return premul_entry(pair_reverse8(b), second); }
+
+// hash_canonical_premul for an MSB-first k-mer.  `Pre::full(index64, second)` / `Pre::low(...)`
+// take the pre-shifted index of msb_word_index64.
+template <class Pre>
+HS_HD uint64_t hash_canonical_premul_msb(uint64_t cm, int k, uint32_t seed, bool use64, const Pre &pre)
+{
+    struct Adapter {
+        const Pre &p; int k;
+        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(msb_word_index64(c, i, k), second); }
+        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(msb_word_index64(c, i, k), second); }
+    };
+    return hash_canonical_premul(cm, k, seed, use64, Adapter{pre, k});
+}
+
+struct PremulArithMsb {  // host-side stand-in for the shared-memory tables (tests)
+    HS_HD uint64_t full(uint32_t index64, bool second) const { return premul_entry_msb(index64 >> 6, second); }
+    HS_HD uint32_t low(uint32_t index64, bool second) const { return (uint32_t)full(index64, second); }
+};
 
 struct AsciiArith {
     HS_HD uint32_t operator()(uint64_t cl, int i) const { return ascii4((uint32_t)(cl >> (8 * i)) & 0xFFu); }

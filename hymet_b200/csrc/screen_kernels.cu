@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "kmer_core.cuh"
 #include "screen_kernels.h"
 
@@ -141,8 +143,67 @@ struct SmemLut16 {
     }
 };
 
-template <int KT>
-__global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
+// Pre-multiplied variant (kmer_core.cuh: hash_canonical_premul): two tables, (u64)letters*c1 and
+// (u64)letters*c2, 256 entries x 8 lane copies x 8 B = 16 KB each, 16 KB aligned and adjacent.
+// Entry b, copy c at b*64 + c*8: a half-warp's 64-bit loads touch each bank pair once per copy, two
+// lanes share a copy (2-way conflict when their entries differ in parity).
+constexpr uint32_t kPreBytes = 256 * 8 * 8;
+static_assert(kPreBytes == 16384, "SmemPremul's loads carry this offset as an immediate");
+struct SmemPremul {
+    uint32_t base1, base2;  // table address | (lane & 7) * 8
+    __device__ __forceinline__ uint32_t addr(uint64_t cl, int i, bool second) const
+    {
+        const uint32_t w = i < 4 ? (uint32_t)cl : (uint32_t)(cl >> 32);
+        const int sh = 8 * (i & 3) - 6;
+        const uint32_t x = sh < 0 ? (w << 6) : (w >> sh);
+        return (x & 0x3FC0u) | (second ? base2 : base1);
+    }
+    // MSB-first k-mers (HS_WINDOW): the caller passes the index already in address position
+    // (the second table sits kPreBytes after the first: reached through the load's immediate offset)
+    __device__ __forceinline__ uint64_t full(uint32_t index64, bool second) const
+    {
+        uint64_t v;
+        if (second) asm("ld.shared.u64 %0, [%1+16384];" : "=l"(v) : "r"(index64 | base1));
+        else asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(index64 | base1));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t low(uint32_t index64, bool second) const
+    {
+        uint32_t v;
+        if (second) asm("ld.shared.u32 %0, [%1+16384];" : "=r"(v) : "r"(index64 | base1));
+        else asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(index64 | base1));
+        return v;
+    }
+    __device__ __forceinline__ uint64_t full(uint64_t cl, int i, bool second) const
+    {
+        uint64_t v;
+        asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr(cl, i, second)));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t low(uint64_t cl, int i, bool second) const
+    {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr(cl, i, second)));
+        return v;
+    }
+};
+
+#ifndef HS_PREMUL
+#define HS_PREMUL 1
+#endif
+#ifndef HS_WINDOW
+#define HS_WINDOW HS_PREMUL
+#endif
+#ifndef HS_ILP
+#define HS_ILP 4
+#endif
+#ifndef HS_MIN_CTAS
+#define HS_MIN_CTAS (HS_PREMUL ? 4 : 5)
+#endif
+constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
+
+template <int KT, bool EMIT>
+__global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
@@ -167,15 +228,36 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
     }
     const uint32_t dyn_addr = smem_u32(dyn_smem);
     const uint32_t lut_addr = (dyn_addr + (kLutBytes - 1)) & ~(kLutBytes - 1);
+#if HS_PREMUL
+    {
+        uint32_t dyn_size;
+        asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
+        if (lut_addr + 2 * kPreBytes > dyn_addr + dyn_size) __trap();  // launch did not leave room for the aligned tables
+        uint64_t *t = reinterpret_cast<uint64_t *>(dyn_smem + (lut_addr - dyn_addr));
+#if HS_WINDOW
+        for (uint32_t i = tid; i < 2 * 256 * 8; i += kCtaThreads) t[i] = premul_entry_msb((i >> 3) & 255u, i >= 256 * 8);
+#else
+        for (uint32_t i = tid; i < 2 * 256 * 8; i += kCtaThreads) t[i] = premul_entry((i >> 3) & 255u, i >= 256 * 8);
+#endif
+    }
+#else
     {
         uint32_t *lut = reinterpret_cast<uint32_t *>(dyn_smem + (lut_addr - dyn_addr));
         for (uint32_t i = tid; i < 256 * 16; i += kCtaThreads) lut[i] = ascii4(i >> 4);
     }
+#endif
     __syncthreads();
+#if HS_PREMUL
+    uint32_t pre1 = lut_addr | ((lane & 7u) << 3), pre2 = (lut_addr + kPreBytes) | ((lane & 7u) << 3);
+    asm volatile("mov.u32 %0, %0;" : "+r"(pre1));  // opaque per-thread registers: keeps ptxas from splitting
+    asm volatile("mov.u32 %0, %0;" : "+r"(pre2));  // them back into uniform base + lane term
+    const SmemPremul L{pre1, pre2};
+#else
     uint32_t lut_lane = lut_addr | ((lane & 15u) << 2);
     asm volatile("mov.u32 %0, %0;" : "+r"(lut_lane));  // one opaque per-thread register: keeps ptxas from
                                                         // splitting it back into uniform base + lane term
     const SmemLut16 L{lut_lane};
+#endif
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -199,6 +281,7 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
     // one compare per k-mer decides whether anything at all has to happen with its hash
     uint64_t gate = a.do_mix ? mix_tau : 0;
     if (a.do_count) gate = a.do_filter ? (a.tab.max_key > gate ? a.tab.max_key : gate) : ~0ull;
+    if (EMIT) gate = ~0ull;   // K1 parity runs want every hash
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
@@ -239,12 +322,10 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
         if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
 
         auto sink = [&](int j, uint64_t h) {
-            n_valid++;
-            if (a.emit_hash) {
+            if (EMIT) {
                 a.emit_hash[pos0 + j] = h;
                 a.emit_valid[pos0 + j] = 1;
             }
-            if (h > gate) return;
             if (a.do_mix && h <= mix_tau) {
                 n_mix++;
                 mix_insert(a.mix, mix_set, h);
@@ -266,7 +347,57 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
                 }
             }
         };
-        for_each_kmer_in_word(prev, cur, iprev, icur, k, a.seed, use64, L, sink);
+        // kIlp k-mers per trip: their hashes are computed unconditionally (invalid k-mers are rare) and
+        // independently, so the scheduler can interleave the multiply chains; validity and the gate
+        // are looked at afterwards.
+        const uint32_t ok = ~invalid_kmer_ends(iprev, icur, k);
+        n_valid += (uint32_t)__popc(ok);
+#if HS_WINDOW
+        const Win w = win_init(prev, cur, k);
+        // words whose 32 k-mers are all valid (nearly all of them) run a copy of the loop that never
+        // looks at the validity mask
+        // (measured dead ends, ms per Gbp at kIlp = 4: compile-time halves + a one-word gate pre-compare
+        // 6.22, the rare path as a __noinline__ function 5.08, this form 4.83 -- more copies of the
+        // loop and call conventions cost more than the few selects they remove)
+        auto word = [&](auto check) {
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const uint32_t fa = half ? w.f0 : w.f1, fb = half ? w.f1 : w.f2, fc = half ? w.f2 : w.f3;
+                const uint32_t ra = half ? w.r1 : w.r0, rb = half ? w.r2 : w.r1, rc = half ? w.r3 : w.r2;
+#pragma unroll 1
+                for (int q = 0; q < 16; q += kIlp) {
+                    uint64_t h[kIlp];
+#pragma unroll
+                    for (int u = 0; u < kIlp; u++)
+                        h[u] = hash_canonical_premul_msb(canonical_msb_half(fa, fb, fc, ra, rb, rc, q + u, k), k, a.seed, use64, L);
+#pragma unroll
+                    for (int u = 0; u < kIlp; u++) {
+                        const int j = half * 16 + q + u;
+                        if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u]);
+                    }
+                }
+            }
+        };
+        if (ok == ~0u) word(std::false_type{}); else word(std::true_type{});
+        continue;
+#endif
+        Roll r = roll_init(prev, k);
+#pragma unroll 1
+        for (int j = 0; j < kBasesPerWord; j += kIlp) {
+            uint64_t h[kIlp];
+#pragma unroll
+            for (int u = 0; u < kIlp; u++) {
+                roll_push(r, (uint32_t)(cur >> (62 - 2 * (j + u))) & 3u, k);
+#if HS_PREMUL
+                h[u] = hash_canonical_premul(canonical_lsb(r, k), k, a.seed, use64, L);
+#else
+                h[u] = hash_canonical(canonical_lsb(r, k), k, a.seed, use64, L);
+#endif
+            }
+#pragma unroll
+            for (int u = 0; u < kIlp; u++)
+                if (((ok >> (31 - j - u)) & 1u) && h[u] <= gate) sink(j + u, h[u]);
+        }
     }
 
     n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);
@@ -280,29 +411,43 @@ __global__ void __launch_bounds__(kCtaThreads, 5) k_stream(const StreamArgs a)
     }
 }
 
-template <int KT>
+template <int KT, bool EMIT>
 static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream_t st)
 {
     static int occ = 0;
+    static uint32_t dyn = 2 * kLutBytes;
     if (!occ) {
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT>, kCtaThreads, 2 * kLutBytes);
+        cudaError_t e;
+#if HS_PREMUL
+        // the tables need a 16 KB-aligned 32 KB window.  Dynamic shared memory starts right after the
+        // 1 KB the system reserves per CTA and the kernel's static buffers, so ask for exactly the
+        // distance to the next 16 KB boundary plus the tables (the kernel traps if that ever stops
+        // being true): 4 CTAs of 48 KB per SM instead of 3 with a full 16 KB of slack.
+        cudaFuncAttributes fa;
+        if ((e = cudaFuncGetAttributes(&fa, k_stream<KT, EMIT>)) != cudaSuccess) return e;
+        const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
+        dyn = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes;
+        if ((e = cudaFuncSetAttribute(k_stream<KT, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+#endif
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT, EMIT>, kCtaThreads, dyn);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
     }
     uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
     if (grid > a.n_tiles - a.tile_begin) grid = a.n_tiles - a.tile_begin;
     if (!grid) return cudaSuccess;
-    k_stream<KT><<<grid, kCtaThreads, 2 * kLutBytes, st>>>(a);
+    k_stream<KT, EMIT><<<grid, kCtaThreads, dyn, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st)
 {
+    if (a.emit_hash) return launch_stream_t<0, true>(a, sm_count, st);   // parity runs: generic-k instantiation
     switch (a.k) {
-    case 21: return launch_stream_t<21>(a, sm_count, st);
-    case 31: return launch_stream_t<31>(a, sm_count, st);
-    case 16: return launch_stream_t<16>(a, sm_count, st);
-    default: return launch_stream_t<0>(a, sm_count, st);
+    case 21: return launch_stream_t<21, false>(a, sm_count, st);
+    case 31: return launch_stream_t<31, false>(a, sm_count, st);
+    case 16: return launch_stream_t<16, false>(a, sm_count, st);
+    default: return launch_stream_t<0, false>(a, sm_count, st);
     }
 }
 

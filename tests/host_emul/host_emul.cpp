@@ -43,6 +43,31 @@ uint64_t emul_pack(const char *text, uint64_t n, uint64_t *seq, uint32_t *inv, u
     return nw;
 }
 
+// both hash formulations on a raw LSB-first k-mer value (bits above 2k are masked off)
+void emul_hash_both(uint64_t cl, int k, uint32_t seed, uint64_t *out)
+{
+    cl &= hs::kmer_mask(k);
+    out[0] = hs::hash_canonical(cl, k, seed, k > 16, hs::AsciiArith());
+    out[1] = hs::hash_canonical_premul(cl, k, seed, k > 16, hs::PremulArith());
+}
+
+// the 32 k-mers ending in `cur`: rolling formulation vs windowed MSB-first + pre-multiplied tables.
+// out_a/out_b[j] = hash (validity is a separate mask and not involved); returns mismatches.
+int emul_window_vs_roll(uint64_t prev, uint64_t cur, int k, uint32_t seed, uint64_t *out_a, uint64_t *out_b)
+{
+    const bool use64 = k > 16;
+    hs::Roll r = hs::roll_init(prev, k);
+    const hs::Win w = hs::win_init(prev, cur, k);
+    int bad = 0;
+    for (int j = 0; j < 32; j++) {
+        hs::roll_push(r, (uint32_t)(cur >> (62 - 2 * j)) & 3u, k);
+        out_a[j] = hs::hash_canonical(hs::canonical_lsb(r, k), k, seed, use64, hs::AsciiArith());
+        out_b[j] = hs::hash_canonical_premul_msb(hs::canonical_msb(w, j, k), k, seed, use64, hs::PremulArithMsb());
+        bad += out_a[j] != out_b[j];
+    }
+    return bad;
+}
+
 uint32_t emul_bucket_of(uint64_t h, uint32_t nb) { return hs::bucket_of(h, nb); }
 uint64_t emul_pair_reverse(uint64_t x) { return hs::pair_reverse64(x); }
 

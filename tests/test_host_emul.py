@@ -148,3 +148,41 @@ def test_split_records_preserves_kmers(emul):
     whole, _ = emul_hashes(emul, text, 21)
     parts = np.concatenate([emul_hashes(emul, text[b:e], 21)[0] for b, e in spans])
     assert np.array_equal(whole, parts)
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_premultiplied_table_hash_equals_murmur(emul, k):
+    """The streaming kernel takes the first multiply of every 64-bit murmur lane from a table of
+    pre-multiplied four-letter words (kmer_core.cuh: hash_canonical_premul).  For every k: equal to
+    the plain formulation and to the oracle's MurmurHash3 of the ASCII k-mer."""
+    emul.emul_hash_both.argtypes = [C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64)]
+    emul.emul_hash_both.restype = None
+    rng = random.Random(k)
+    out = (C.c_uint64 * 2)()
+    for t in range(300):
+        cl = rng.getrandbits(64) if t > 3 else [0, (1 << 64) - 1, 0x5555555555555555, 0xAAAAAAAAAAAAAAAA][t]
+        seed = 42 if t % 3 else rng.getrandbits(32)
+        emul.emul_hash_both(cl, k, seed, out)
+        assert out[0] == out[1], (k, hex(cl))
+        if t < 40:
+            kmer = bytes(b"ACGT"[(cl >> (2 * i)) & 3] for i in range(k))     # first base least significant
+            h1 = orc.murmur(kmer, seed)[0]
+            assert out[1] == (h1 if k > 16 else h1 & 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("k", list(range(1, 33)))
+def test_windowed_msb_canonical_equals_rolling(emul, k):
+    """k_stream's per-thread formulation (128-bit window + funnel shifts, MSB-first canonical k-mer,
+    permuted pre-multiplied tables) gives the same 32 hashes per word as the rolling LSB-first one
+    that the oracle comparison above pins."""
+    emul.emul_window_vs_roll.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    emul.emul_window_vs_roll.restype = C.c_int
+    rng = random.Random(100 + k)
+    a, b = (C.c_uint64 * 32)(), (C.c_uint64 * 32)()
+    specials = [0, (1 << 64) - 1, 0x5555555555555555, 0xAAAAAAAAAAAAAAAA, 0x1B1B1B1B1B1B1B1B, 0xE4E4E4E4E4E4E4E4]
+    for t in range(200):
+        prev = specials[t % 6] if t < 12 else rng.getrandbits(64)
+        cur = specials[(t // 2) % 6] if t < 12 else rng.getrandbits(64)
+        if t % 7 == 0:   # palindromic neighbourhoods: forward == reverse complement ties
+            cur = prev
+        assert emul.emul_window_vs_roll(prev, cur, k, 42, a, b) == 0, (k, hex(prev), hex(cur), list(a)[:4], list(b)[:4])

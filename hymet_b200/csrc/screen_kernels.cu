@@ -820,53 +820,58 @@ __device__ __forceinline__ uint32_t block_sum128(uint32_t v, uint32_t *red)
     return red[0] + red[1] + red[2] + red[3];
 }
 
-__global__ void __launch_bounds__(kReduceThreads) k_sketch_reduce(const uint64_t *offsets, uint64_t n_refs,
-                                                                  const uint32_t *canon, const uint32_t *counts,
-                                                                  const uint32_t *winner, uint32_t *shared_out,
-                                                                  uint32_t *median_out)
+// One WARP per sketch, no block barriers: 50 000 sketches of 1000 hashes are 50 000 small
+// independent reductions, and almost all of them end after the first pass (no hash present).
+// The first version used a CTA per sketch with two __syncthreads per block sum: latency bound at
+// 1.4 TB/s of a stream that is mostly sequential (canon[e] == e for keys stored once).
+__global__ void __launch_bounds__(256) k_sketch_reduce(const uint64_t *offsets, uint64_t n_refs,
+                                                       const uint32_t *canon, const uint32_t *counts,
+                                                       const uint32_t *winner, uint32_t *shared_out,
+                                                       uint32_t *median_out)
 {
-    __shared__ uint32_t cache[kReduceCache];
-    __shared__ uint32_t red[4], redmax[4];
-    for (uint64_t i = blockIdx.x; i < n_refs; i += gridDim.x) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < n_refs; i += n_warps) {
         const uint64_t beg = offsets[i], end = offsets[i + 1];
-        const bool cached = end - beg <= kReduceCache;
         auto value = [&](uint64_t e) -> uint32_t {
-            const uint32_t id = canon[e];
-            uint32_t c = counts[id];
+            const uint32_t id = __ldg(canon + e);
+            uint32_t c = __ldcg(counts + id);
             if (winner && c && winner[id] != (uint32_t)i) c = 0;
             return c;
         };
         uint32_t cnt = 0, mx = 0;
-        for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
+        uint64_t e = beg + lane;
+        for (; e + 96 < end; e += 128) {   // four independent gathers in flight per lane
+            const uint32_t c0 = value(e), c1 = value(e + 32), c2 = value(e + 64), c3 = value(e + 96);
+            cnt += (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
+            mx = max(max(mx, c0), max(max(c1, c2), c3));
+        }
+        for (; e < end; e += 32) {
             const uint32_t c = value(e);
-            if (cached) cache[e - beg] = c;
             cnt += c != 0;
             mx = max(mx, c);
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0) redmax[threadIdx.x >> 5] = mx;
-        const uint32_t S = block_sum128(cnt, red);  // barriers inside also publish cache[] and redmax[]
+        const uint32_t S = warp_sum(cnt);
         if (S == 0) {
-            if (threadIdx.x == 0) { shared_out[i] = 0; median_out[i] = 0; }
-            __syncthreads();
+            if (lane == 0) { shared_out[i] = 0; median_out[i] = 0; }
             continue;
         }
-        mx = max(max(redmax[0], redmax[1]), max(redmax[2], redmax[3]));
-        // S12: sorted_depths[S/2] by MSB-first radix selection over the non-zero counts
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        // S12: sorted_depths[S/2] by MSB-first radix selection over the non-zero counts (re-read: L2 hot)
         uint32_t kk = S / 2, prefix = 0;
         for (int bit = 31 - __clz(mx); bit >= 0; bit--) {
             const uint32_t himask = ~((2u << bit) - 1u);
             uint32_t z = 0;
-            for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
-                const uint32_t c = cached ? cache[e - beg] : value(e);
+            for (uint64_t q = beg + lane; q < end; q += 32) {
+                const uint32_t c = value(q);
                 z += (c != 0) && ((c & himask) == prefix) && !((c >> bit) & 1u);
             }
-            z = block_sum128(z, red);
+            z = warp_sum(z);
             if (kk >= z) { kk -= z; prefix |= 1u << bit; }
         }
-        if (threadIdx.x == 0) { shared_out[i] = S; median_out[i] = prefix; }
-        __syncthreads();
+        if (lane == 0) { shared_out[i] = S; median_out[i] = prefix; }
     }
 }
 
@@ -875,14 +880,14 @@ cudaError_t launch_sketch_reduce(const uint64_t *offsets, uint64_t n_refs, const
                                  int sm_count, cudaStream_t st)
 {
     if (!n_refs) return cudaSuccess;
-    const uint32_t grid = (uint32_t)((n_refs < (uint64_t)sm_count * 16) ? n_refs : (uint64_t)sm_count * 16);
-    k_sketch_reduce<<<grid, kReduceThreads, 0, st>>>(offsets, n_refs, canon, counts, winner, shared, median);
+    const uint64_t want = (n_refs + 7) / 8;   // 8 warps per CTA
+    const uint32_t grid = (uint32_t)(want < (uint64_t)sm_count * 8 ? want : (uint64_t)sm_count * 8);
+    k_sketch_reduce<<<grid, 256, 0, st>>>(offsets, n_refs, canon, counts, winner, shared, median);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
-// K5: winner-take-all (row a12, rule S17).  Three max-reductions per present key:
-// best score, then longest genome among those, then highest sketch index.
+// K5: winner-take-all (S17)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kReduceThreads) k_winner(const uint64_t *offsets, uint64_t n_refs,
                                                            const uint32_t *canon, const uint32_t *counts,
@@ -948,16 +953,22 @@ __device__ double binom_upper_tail(uint64_t x, uint64_t n, double r)
     const bool upper = (double)x > (double)n * r;  // sum the smaller side
     const uint64_t j0 = upper ? x : x - 1;         // first term of the side we sum
     // t(j0) = prod_{i=1..j0} ((n-j0+i)/i * r) * q^(n-j0)
-    double mant = 1.0;
+    // numerator and denominator as separate running products (one division at the end instead of
+    // one per factor: FP64 division is what this kernel spent its time on), renormalised every
+    // four factors -- four factors cannot move a value normalised into [0.5, 1) out of range
+    // (factor range 5e-20 .. 1e7)
+    double num = 1.0, den = 1.0;
     long long ex = 0;
     for (uint64_t i = 1; i <= j0; i++) {
-        mant *= ((double)(n - j0 + i) / (double)i) * r;
-        if (mant < 1e-250 || mant > 1e250) {
+        num *= (double)(n - j0 + i) * r;
+        den *= (double)i;
+        if ((i & 3u) == 0) {
             int e2;
-            mant = frexp(mant, &e2);
-            ex += e2;
+            num = frexp(num, &e2); ex += e2;
+            den = frexp(den, &e2); ex -= e2;
         }
     }
+    double mant = num / den;
     {
         const double e2 = (double)(n - j0) * log2(q);
         const double fl = floor(e2);

@@ -154,7 +154,7 @@ def test_ingest_modes_agree_on_pinned_text(c1_case, mode):
     scr = hs.Screen(db)
     scr.set_option("ingest", mode)
     scr.set_option("chunk_bases", 300_000)
-    scr.feed_text_ptr(pinned.data_ptr(), pinned.numel(), 3)
+    scr.feed_text_ptr(pinned.data_ptr(), pinned.numel(), 6)   # >= 6 threads: packer threads and the device parser compete in mode 2
     res = scr.finish(False)
     assert res.shared.tolist() == want.shared.tolist() and res.median.tolist() == want.median.tolist()
     assert res.set_size == want.set_size

@@ -100,7 +100,8 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
 class DistributedScreen:
     """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
-    Default ("auto"): ONE all-gather per screen.  Every rank contributes a fixed-size record
+    Default ("auto"): ONE all-gather per screen.  Every rank contributes a fixed-size record (sized
+    from the previous screen's pair counts, at most 2^20 pairs)
     [n_pairs | mixture length | <= s mixture hashes | up to `cap` non-zero (entry id, count)
     pairs]; the pairs are compacted on the device straight into the record
     (k_counts_compact), so the host synchronises once, after the collective.  Each rank then
@@ -162,7 +163,17 @@ class DistributedScreen:
         if not sparse:
             return self._dense()
         n_pairs = heads[:, 0] & 0xFFFFFFFF
-        if int(n_pairs.max()) > cap:          # too many distinct hits for the record: dense all-reduce instead
+        most = int(n_pairs.max())
+        if self.exchange_mode != "sparse":
+            # size the next record from what this one carried (every rank sees the same heads, so every
+            # rank takes the same decision): the collective moves world x cap x 8 bytes whatever is in them
+            want = 4096
+            while want < most + most // 2:
+                want <<= 1
+            want = min(want, max(4096, int(self.db.n_entries)))
+            if most > cap or want * 2 <= cap:
+                self.cap = want
+        if most > cap:                        # too many distinct hits for this record: dense all-reduce instead
             return self._dense()
         rows = self._all.view(self.world, n_rec)
         for r in range(self.world):

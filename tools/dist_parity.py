@@ -31,8 +31,15 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ok = True
-    for wta, mode in ((False, "dense"), (True, "dense"), (False, "sparse"), (True, "sparse"), (False, "auto")):
-        scr = hd.DistributedScreen(db, local, exchange=mode, stream_ptr=stream.cuda_stream)
+    runs = [(False, "dense", None), (True, "dense", None), (False, "sparse", None), (True, "sparse", None)]
+    auto = hd.DistributedScreen(db, local, exchange="auto", stream_ptr=stream.cuda_stream)
+    # the same handle three times: the record is sized from the previous screen (first: too small -> dense
+    # fallback, then sparse)
+    runs += [(False, "auto", auto), (True, "auto", auto), (False, "auto", auto)]
+    for wta, mode, handle in runs:
+        scr = handle or hd.DistributedScreen(db, local, exchange=mode, stream_ptr=stream.cuda_stream)
+        if handle:
+            scr.reset()
         b, e = hd.record_aligned_range(fasta, rank, world)
         scr.feed_text(fasta[b:e], 2)
         res = scr.finish(wta)
@@ -45,7 +52,8 @@ def main():
             print("world=%d wta=%d exchange=%s(%s) shared_total=%d parity=%s" % (world, wta, mode, scr.last_exchange,
                                                                                   int(res.shared.sum()), same), flush=True)
             ok = ok and same
-        scr.scr.close()
+        if not handle:
+            scr.scr.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()

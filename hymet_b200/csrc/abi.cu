@@ -1336,9 +1336,17 @@ HS_API int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_
 {
     if (!s || (!hashes && n)) return fail(HS_EINVAL, "null argument");
     if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
-    // union of per-rank bottom-s sets, keep the s smallest (<= G*s values: control-plane work)
-    s->mixture.insert(s->mixture.end(), hashes, hashes + n);
-    std::sort(s->mixture.begin(), s->mixture.end());
+    // union of per-rank bottom-s sets, keep the s smallest (<= G*s values: control-plane work).
+    // Both sides are normally ascending (hs_screen_mixture_get order): a linear merge, not a sort --
+    // seven sorts of 2000 values were 0.4 ms of an 8-GPU step.
+    if (std::is_sorted(hashes, hashes + n)) {
+        std::vector<uint64_t> merged(s->mixture.size() + n);
+        std::merge(s->mixture.begin(), s->mixture.end(), hashes, hashes + n, merged.begin());
+        s->mixture.swap(merged);
+    } else {
+        s->mixture.insert(s->mixture.end(), hashes, hashes + n);
+        std::sort(s->mixture.begin(), s->mixture.end());
+    }
     s->mixture.erase(std::unique(s->mixture.begin(), s->mixture.end()), s->mixture.end());
     if (s->mixture.size() > s->db->s) s->mixture.resize(s->db->s);
     s->st.n_mixture = s->mixture.size();

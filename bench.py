@@ -408,6 +408,7 @@ def run_b200(args):
         wl.fasta.numpy().tofile(fpath)
         readers = max(1, min(8, host_threads))
         scr.set_option("file_readers", readers)
+        scr.set_option("file_block_bytes", 16 << 20)
 
         def step_file():
             scr.reset()

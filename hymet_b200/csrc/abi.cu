@@ -311,7 +311,11 @@ struct hs_screen {
     Ingest ingest;
     int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
     FileRing ring;
-    uint64_t file_block = (uint64_t)16 << 20;   // plain FASTA files: nominal bytes per reader block
+    // plain FASTA files: nominal bytes per reader block and reader threads.  Pinning the ring costs
+    // ~0.5 ms per MB once per handle (measured), which a one-shot `mash screen` pays in full: the
+    // defaults keep it at 96 MB (1 GB file: ~50 ms + 40 ms); a long-lived handle is better off with
+    // 8 readers x 16 MB (28 ms per GB, bench.py's e2e_file)
+    uint64_t file_block = (uint64_t)8 << 20;
     int file_readers = 4;
     std::mutex ingest_mu;                       // one thread at a time hands a span to the device parser
     std::mutex giant_mu;                        // records larger than a ring slot take the host path, one at a time

@@ -841,17 +841,25 @@ __global__ void __launch_bounds__(256) k_sketch_reduce(const uint64_t *offsets, 
             return c;
         };
         uint32_t cnt = 0, mx = 0;
-        uint64_t e = beg + lane;
-        for (; e + 96 < end; e += 128) {   // four independent gathers in flight per lane
-            const uint32_t c0 = value(e), c1 = value(e + 32), c2 = value(e + 64), c3 = value(e + 96);
-            cnt += (c0 != 0) + (c1 != 0) + (c2 != 0) + (c3 != 0);
-            mx = max(max(mx, c0), max(max(c1, c2), c3));
-        }
-        for (; e < end; e += 32) {
-            const uint32_t c = value(e);
+        auto take = [&](uint32_t id) {
+            uint32_t c = __ldcg(counts + id);
+            if (winner && c && winner[id] != (uint32_t)i) c = 0;
             cnt += c != 0;
             mx = max(mx, c);
+        };
+        // head up to a 16-byte boundary of canon[], then 256 entries per trip: every lane holds two
+        // 128-bit loads of ids and turns them into eight independent count gathers
+        uint64_t e = beg;
+        const uint64_t head = min(end, (beg + 3) & ~(uint64_t)3);
+        if (e + lane < head) take(__ldg(canon + e + lane));
+        e = head;
+        for (; e + 256 <= end; e += 256) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(canon + e) + lane);
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(canon + e + 128) + lane);
+            take(a.x); take(a.y); take(a.z); take(a.w);
+            take(b.x); take(b.y); take(b.z); take(b.w);
         }
+        for (uint64_t q = e + lane; q < end; q += 32) take(__ldg(canon + q));
         const uint32_t S = warp_sum(cnt);
         if (S == 0) {
             if (lane == 0) { shared_out[i] = 0; median_out[i] = 0; }

@@ -120,10 +120,16 @@ int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
 /* Options: "filter" 1/0 = skip probes for hashes above the db's largest key (exact;
  * default 1); "keep_query" 1/0 = keep packed chunks in HBM until finish (default 1,
  * needed if the mixture threshold must be revisited); "chunk_bases" = host packer
- * chunk size. */
+ * chunk size; "piece_bases" = positions per upload+launch piece of packed host feeds;
+ * "ingest" 0/1/2 = host packer only / device parser only / both compete (default; packer
+ * threads join when at least six were asked for); "file_readers", "file_block_bytes" = reader
+ * threads and nominal block size of the pinned ring that streams plain FASTA files (defaults
+ * 4 x 8 MiB: sized for a one-shot process, pinning costs ~0.5 ms per MB). */
 int hs_screen_set_option(hs_screen *s, const char *key, int64_t value);
 
-/* rows a6/a7: stream FASTA/FASTQ (plain or gzip; "-" = stdin).  The host packs into
+/* rows a6/a7: stream FASTA/FASTQ (plain or gzip; "-" = stdin).  A plain FASTA file is read by
+ * up to `host_threads` reader threads (pread of record-aligned blocks into a pinned ring) and
+ * parsed, packed and hashed on the GPU; gzip, FASTQ and stdin are packed on the host into
  * pinned 2-bit buffers with `host_threads` threads while the GPU consumes. */
 int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads);
 /* Same, text already in host memory. */

@@ -664,3 +664,39 @@ def test_file_streaming_blocks_and_giant_records(tmp_path, variant):
         assert res.stats["n_valid_kmers"] == want.n_kmers
         assert res.stats["n_records"] == text.count(b">")
         scr.close()
+
+
+def test_cli_fastq_gzip_and_stdin_inputs(tmp_path):
+    """Row a6's other input forms through the drop-in: FASTQ (single- and multi-line, quality lines that
+    start with '@' / '>' / '+'), gzip, "-" = stdin, and several of them pooled into one mixture --
+    byte-identical TSV to the oracle CLI."""
+    import gzip
+    from tests.test_host_emul import make_fastq
+    rng = np.random.default_rng(41)
+    genomes = [synth.random_genome(rng, 30_000) for _ in range(12)]
+    dbp = write_db(tmp_path, genomes, 21, 1000)
+    contigs = synth.cut_contigs(rng, genomes[:7], 160_000, 0.01, median=3000.0)
+    seqs = [synth.ASCII[c].tobytes().decode() for c in contigs]
+    half = len(seqs) // 2
+    fq1, fq2 = str(tmp_path / "reads.fq"), str(tmp_path / "more.fastq.gz")
+    fa3 = str(tmp_path / "rest.fna")
+    open(fq1, "w").write(make_fastq(seqs[:half], multiline=False))
+    with gzip.open(fq2, "wb") as fh:
+        fh.write(make_fastq(seqs[half:], multiline=True, crlf=True).encode())
+    open(fa3, "wb").write(synth.to_fasta(synth.cut_contigs(rng, genomes[6:10], 90_000, 0.02, median=3000.0), "x"))
+    orc.build()
+    mash = [sys.executable, os.path.join(ROOT, "bin", "mash")]
+    for inputs, stdin in (([fq1], None), ([fq2], None), ([fq1, fq2, fa3], None), (["-"], open(fq1, "rb").read()),
+                          (["-", fa3], open(fa3, "rb").read())):
+        args = ["screen", "-p", "3", "-v", "0.9", dbp] + inputs
+        got = subprocess.run(mash + args, input=stdin, capture_output=True)
+        want = subprocess.run([orc.BIN] + args, input=stdin, capture_output=True)
+        assert got.returncode == 0 and want.returncode == 0, (inputs, got.stderr.decode()[-400:], want.stderr.decode()[-200:])
+        assert got.stdout == want.stdout, inputs
+        assert got.stdout.count(b"\n") >= 5
+    # the FASTQ of a set of sequences screens like their FASTA
+    fa1 = str(tmp_path / "reads.fna")
+    open(fa1, "w").write("".join(">r%d\n%s\n" % (i, s) for i, s in enumerate(seqs[:half])))
+    a = subprocess.run(mash + ["screen", dbp, fq1], capture_output=True).stdout
+    b = subprocess.run(mash + ["screen", dbp, fa1], capture_output=True).stdout
+    assert a == b and a

@@ -186,3 +186,47 @@ def test_windowed_msb_canonical_equals_rolling(emul, k):
         if t % 7 == 0:   # palindromic neighbourhoods: forward == reverse complement ties
             cur = prev
         assert emul.emul_window_vs_roll(prev, cur, k, 42, a, b) == 0, (k, hex(prev), hex(cur), list(a)[:4], list(b)[:4])
+
+
+def make_fastq(records, multiline=False, crlf=False, final_newline=True):
+    """FASTQ text whose quality strings contain every printable symbol, so quality lines start
+    with '@', '>' and '+' now and then (the parser must count symbols, not look at line starts)."""
+    out = []
+    for i, s in enumerate(records):
+        q = "".join(chr(33 + ((j * 7 + i * 13) % 94)) for j in range(len(s)))
+        if multiline:
+            sl = "\n".join(s[j:j + 61] for j in range(0, len(s), 61))
+            ql = "\n".join(q[j:j + 61] for j in range(0, len(q), 61))
+        else:
+            sl, ql = s, q
+        out.append("@read%d some text\n%s\n+%s\n%s\n" % (i, sl, "read%d" % i if i % 2 else "", ql))
+    t = "".join(out)
+    if not final_newline:
+        t = t.rstrip("\n")
+    if crlf:
+        t = t.replace("\n", "\r\n")
+    return t
+
+
+@pytest.mark.parametrize("multiline,crlf,final_newline", [(False, False, True), (True, False, True), (False, True, True),
+                                                          (True, True, False), (False, False, False)])
+def test_fastq_records_pack_like_fasta(emul, multiline, crlf, final_newline):
+    """Row a6 for FASTQ (kseq rules): header '@', sequence lines until '+', then as many quality
+    symbols as the sequence had.  The product packer must produce exactly the k-mers of the sequences."""
+    rng = random.Random(77)
+    recs = []
+    for r in range(40):
+        L = rng.choice([0, 1, 20, 21, 22, 60, 61, 62, 200, 1000])
+        recs.append("".join(rng.choice("ACGTacgtNn") if rng.random() < 0.03 else rng.choice("ACGT") for _ in range(L)))
+    fq = make_fastq(recs, multiline, crlf, final_newline)
+    assert any(l.startswith("@") and not l.startswith("@read") for l in fq.replace("\r", "").split("\n")) or not multiline
+    for k in (16, 21, 31):
+        got, st = emul_hashes(emul, fq.encode(), k)
+        want = [orc.hash_sequence(s.encode(), k, 42) for s in recs if len(s)]
+        want = np.concatenate([h[v] for h, v in want]) if want else np.zeros(0, np.uint64)
+        assert got.tolist() == want.tolist(), (k, multiline, crlf)
+        assert st[0] == len(recs) and st[1] == sum(len(s) for s in recs)
+    # and the oracle's own parser reads the FASTQ as it reads the equivalent FASTA
+    fa = "".join(">read%d\n%s\n" % (i, s) for i, s in enumerate(recs))
+    a, b = orc.sketch_text(fq.encode(), 21, 300), orc.sketch_text(fa.encode(), 21, 300)
+    assert a[0].tolist() == b[0].tolist() and a[1] == b[1]

@@ -693,7 +693,7 @@ def test_cli_fastq_gzip_and_stdin_inputs(tmp_path):
         want = subprocess.run([orc.BIN] + args, input=stdin, capture_output=True)
         assert got.returncode == 0 and want.returncode == 0, (inputs, got.stderr.decode()[-400:], want.stderr.decode()[-200:])
         assert got.stdout == want.stdout, inputs
-        assert got.stdout.count(b"\n") >= 5
+        assert got.stdout.count(b"\n") >= 2, (inputs, got.stdout)
     # the FASTQ of a set of sequences screens like their FASTA
     fa1 = str(tmp_path / "reads.fna")
     open(fa1, "w").write("".join(">r%d\n%s\n" % (i, s) for i, s in enumerate(seqs[:half])))

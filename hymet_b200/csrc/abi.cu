@@ -337,7 +337,7 @@ struct hs_screen {
     hs_stats_t st;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
-    cudaEvent_t red0 = nullptr, red1 = nullptr;
+    cudaEvent_t red0 = nullptr, red1 = nullptr, red2 = nullptr, red3 = nullptr;
     char *h_result = nullptr;   // pinned landing zone for the four result columns (24 B per sketch):
                                 // a D2H copy into the caller's pageable arrays costs ~0.3 ms at N = 50 000
 };
@@ -777,6 +777,8 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
     CUB(cudaMalloc((void **)&s->d_pvalue, N * 8));
     CUB(cudaEventCreate(&s->red0));
     CUB(cudaEventCreate(&s->red1));
+    CUB(cudaEventCreate(&s->red2));
+    CUB(cudaEventCreate(&s->red3));
     CUB(cudaHostAlloc((void **)&s->h_result, N * 24, cudaHostAllocDefault));
 #undef CUB
     int rc = s->mix.init(db->s);
@@ -1363,12 +1365,27 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
 {
     if (!s) return fail(HS_EINVAL, "null handle");
     NEED_DEVICE();
-    int rc = hs_screen_flush(s);
-    if (rc) return rc;
     hs_db *db = s->db;
     const uint64_t N = db->n_refs, E = db->n_entries;
+    // Single-GPU order: the per-sketch reduction needs only counts[], so it is enqueued BEFORE the
+    // mixture is settled and runs underneath the host round trips of that (flush); a caller that
+    // flushed first (multi-GPU: flush -> exchange -> finish) gets it here, after the exchange.
+    const bool early = !s->flushed;
+    if (early) {
+        CU(cudaEventRecord(s->red2, s->stream));
+        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
+        CU(cudaEventRecord(s->red3, s->stream));
+    }
+    int rc = hs_screen_flush(s);
+    if (rc) return rc;
+    if (early) {
+        float ems = 0;
+        CU(cudaEventElapsedTime(&ems, s->red2, s->red3));   // flush synchronised the stream
+        s->st.ms_reduce += ems;
+    }
     CU(cudaEventRecord(s->red0, s->stream));
-    CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
+    if (!early)
+        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
     s->st.n_launches++;
     const size_t n_seg = db->seg_s.size();
     if (wta && E) {
@@ -1450,6 +1467,8 @@ HS_API void hs_screen_free(hs_screen *s)
     for (auto &e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (s->red0) cudaEventDestroy(s->red0);
     if (s->red1) cudaEventDestroy(s->red1);
+    if (s->red2) cudaEventDestroy(s->red2);
+    if (s->red3) cudaEventDestroy(s->red3);
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }

@@ -771,10 +771,12 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
     CUB(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUB(cudaMalloc((void **)&s->d_counts, E * 4));
     CUB(cudaMalloc((void **)&s->d_stats, 2 * ST_COUNT * sizeof(unsigned long long)));
-    CUB(cudaMalloc((void **)&s->d_shared, N * 4));
-    CUB(cudaMalloc((void **)&s->d_median, N * 4));
-    CUB(cudaMalloc((void **)&s->d_identity, N * 8));
-    CUB(cudaMalloc((void **)&s->d_pvalue, N * 8));
+    // the four result columns share one allocation (identity | p-value | shared | median) so that
+    // they travel to the host in a single copy
+    CUB(cudaMalloc((void **)&s->d_identity, N * 24));
+    s->d_pvalue = s->d_identity + N;
+    s->d_shared = reinterpret_cast<uint32_t *>(s->d_pvalue + N);
+    s->d_median = s->d_shared + N;
     CUB(cudaEventCreate(&s->red0));
     CUB(cudaEventCreate(&s->red1));
     CUB(cudaEventCreate(&s->red2));
@@ -1412,20 +1414,16 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
         s->st.n_launches++;
     }
     CU(cudaEventRecord(s->red1, s->stream));
-    double *h_id = reinterpret_cast<double *>(s->h_result), *h_pv = h_id + N;
-    uint32_t *h_sh = reinterpret_cast<uint32_t *>(h_pv + N), *h_md = h_sh + N;
-    if (N) {
-        CU(cudaMemcpyAsync(h_sh, s->d_shared, N * 4, cudaMemcpyDeviceToHost, s->stream));
-        if (median) CU(cudaMemcpyAsync(h_md, s->d_median, N * 4, cudaMemcpyDeviceToHost, s->stream));
-        if (identity) CU(cudaMemcpyAsync(h_id, s->d_identity, N * 8, cudaMemcpyDeviceToHost, s->stream));
-        if (pvalue) CU(cudaMemcpyAsync(h_pv, s->d_pvalue, N * 8, cudaMemcpyDeviceToHost, s->stream));
-    }
+    const uint64_t NA = std::max<uint64_t>(N, 1);   // layout of the allocation (hs_screen_new)
+    double *h_id = reinterpret_cast<double *>(s->h_result), *h_pv = h_id + NA;
+    uint32_t *h_sh = reinterpret_cast<uint32_t *>(h_pv + NA), *h_md = h_sh + NA;
+    if (N) CU(cudaMemcpyAsync(s->h_result, s->d_identity, NA * 24, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     if (shared) for (uint64_t i = 0; i < N; i++) shared[i] = h_sh[i];
     if (median && N) memcpy(median, h_md, N * 4);
     if (identity && N) memcpy(identity, h_id, N * 8);
     if (pvalue && N) memcpy(pvalue, h_pv, N * 8);
-    s->st.d2h_bytes += N * (4 + (median ? 4 : 0) + (identity ? 8 : 0) + (pvalue ? 8 : 0));
+    s->st.d2h_bytes += N * 24;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
     s->st.ms_reduce += ms;
@@ -1453,8 +1451,9 @@ HS_API void hs_screen_free(hs_screen *s)
     if (!s) return;
     if (g_device >= 0) cudaSetDevice(g_device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_counts); cudaFree(s->d_stats); cudaFree(s->d_shared); cudaFree(s->d_median);
-    cudaFree(s->d_identity); cudaFree(s->d_pvalue); cudaFree(s->d_best_score); cudaFree(s->d_best_len); cudaFree(s->d_winner);
+    cudaFree(s->d_counts); cudaFree(s->d_stats);
+    cudaFree(s->d_identity);   // one block: identity | p-value | shared | median
+    cudaFree(s->d_best_score); cudaFree(s->d_best_len); cudaFree(s->d_winner);
     s->mix.destroy();
     s->arena.release();
     s->ingest.release();

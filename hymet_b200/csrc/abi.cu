@@ -193,6 +193,7 @@ struct MixEngine {
     MixState *h_state = nullptr;  // pinned mirror, valid after sync_state()
     MixState *h_init = nullptr;   // pinned source for resets
     uint64_t *d_cand = nullptr, *d_scratch = nullptr;
+    uint64_t *h_cand = nullptr;   // pinned: the settled mixture travels with the state, one sync for both
     bool auto_tau = true;  // first pass: cap tau per launch so expected offers stay <= cap/8
     uint32_t passes = 1;
 
@@ -209,6 +210,7 @@ struct MixEngine {
         CU(cudaHostAlloc((void **)&h_init, sizeof(MixState), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
         CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
+        CU(cudaHostAlloc((void **)&h_cand, (size_t)s * 8, cudaHostAllocDefault));
         return HS_OK;
     }
     void destroy()
@@ -217,6 +219,7 @@ struct MixEngine {
         cudaFree(d_state); cudaFree(d_cand); cudaFree(d_scratch);
         if (h_state) cudaFreeHost(h_state);
         if (h_init) cudaFreeHost(h_init);
+        if (h_cand) cudaFreeHost(h_cand);
     }
     uint32_t *field(size_t off) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(d_state) + off); }
     int reset(cudaStream_t st, uint64_t new_tau = ~0ull, bool automatic = true)
@@ -338,6 +341,7 @@ struct hs_screen {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
     cudaEvent_t red0 = nullptr, red1 = nullptr, red2 = nullptr, red3 = nullptr;
+    unsigned long long *h_stats = nullptr;   // pinned: [0, ST_COUNT) kernel counters, then 4 device-parser totals
     char *h_result = nullptr;   // pinned landing zone for the four result columns (24 B per sketch):
                                 // a D2H copy into the caller's pageable arrays costs ~0.3 ms at N = 50 000
 };
@@ -542,11 +546,12 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
         if (M) {
             CU(launch_sort_unique(m.d_cand, M, m.d_scratch, m.field(offsetof(MixState, n_unique)), st));
             n_launches++;
+            const uint32_t take = std::min(M, m.s);   // >= what is kept (n_unique <= M)
+            CU(cudaMemcpyAsync(m.h_cand, m.d_cand, (size_t)take * 8, cudaMemcpyDeviceToHost, st));
             rc = m.sync_state(st);
             if (rc) return rc;
-            const uint32_t nu = std::min(m.h_state->n_unique, m.s);
-            out.resize(nu);
-            CU(cudaMemcpy(out.data(), m.d_cand, (size_t)nu * 8, cudaMemcpyDeviceToHost));
+            const uint32_t nu = std::min(m.h_state->n_unique, take);
+            out.assign(m.h_cand, m.h_cand + nu);
         }
         if (m.h_state->has_max && out.size() < m.s) out.push_back(~0ull);  // hash == 2^64-1 present
         return HS_OK;
@@ -782,6 +787,7 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
     CUB(cudaEventCreate(&s->red2));
     CUB(cudaEventCreate(&s->red3));
     CUB(cudaHostAlloc((void **)&s->h_result, N * 24, cudaHostAllocDefault));
+    CUB(cudaHostAlloc((void **)&s->h_stats, (ST_COUNT + 4) * sizeof(unsigned long long), cudaHostAllocDefault));
 #undef CUB
     int rc = s->mix.init(db->s);
     if (rc) return bail(rc);
@@ -1246,6 +1252,15 @@ HS_API int hs_screen_flush(hs_screen *s)
     if (s->flushed) return HS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaEventRecord(s->red0, s->stream));
+    // the counters are final once the streaming launches are (re-offer passes count elsewhere): fetch
+    // them with the first synchronisation of the mixture finaliser instead of one of their own
+    unsigned long long *h = s->h_stats, *t = s->h_stats + ST_COUNT;
+    const bool parsed = s->ingest.ready && s->ingest.counters_used;
+    CU(cudaMemcpyAsync(h, s->d_stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    if (parsed) {
+        CU(cudaMemcpyAsync(t, s->ingest.d_totals, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemsetAsync(s->ingest.d_totals, 0, 4 * sizeof(unsigned long long), s->stream));  // folded: do not fold twice
+    }
     int rc = mix_finalize(s->mix, s->stream, s->mixture, s->st.n_launches, [&]() -> int {
         for (const Chunk &c : s->chunks) {
             int r = launch_chunk(s, c, false, true);
@@ -1256,15 +1271,8 @@ HS_API int hs_screen_flush(hs_screen *s)
     });
     if (rc) return rc;
     CU(cudaEventRecord(s->red1, s->stream));
-    unsigned long long h[ST_COUNT];
-    CU(cudaMemcpyAsync(h, s->d_stats, sizeof h, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    if (s->ingest.ready && s->ingest.counters_used) {
-        unsigned long long t[4];
-        CU(cudaMemcpy(t, s->ingest.d_totals, sizeof t, cudaMemcpyDeviceToHost));
-        s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2];
-        CU(cudaMemsetAsync(s->ingest.d_totals, 0, sizeof t, s->stream));  // folded: do not fold twice
-    }
+    CU(cudaEventSynchronize(s->red1));   // mix_finalize ended on a synchronisation: nothing is left to wait for
+    if (parsed) { s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2]; }
     s->st.n_valid_kmers = h[ST_VALID]; s->st.n_probes = h[ST_PROBES]; s->st.n_bucket_reads = h[ST_BUCKETS];
     s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
     s->st.n_mix_passes = s->mix.passes;
@@ -1469,6 +1477,7 @@ HS_API void hs_screen_free(hs_screen *s)
     if (s->red2) cudaEventDestroy(s->red2);
     if (s->red3) cudaEventDestroy(s->red3);
     if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->h_stats) cudaFreeHost(s->h_stats);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     for (auto &e : s->copy_evs) cudaEventDestroy(e);

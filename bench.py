@@ -168,8 +168,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "c2: CAMI-shaped contigs vs %d-sketch db (k=21,s=1000); bounded CPU sample" % args.sketches,
-                   "query_mbp_per_step": args.cpu_mbp, "sketches": args.sketches},
+        # same workload name and keys as the CUDA arm's line; the sample this arm timed is in cpu_baseline.sample
+        "config": {"workload": "c2: synthetic %d Mbp CAMI-shaped contig set per GPU vs %d-sketch db (k=%d, s=%d)"
+                               % (args.mbp, args.sketches, k, s), "k": k, "s": s,
+                   "query_mbp_per_gpu": args.mbp, "sketches": args.sketches, "mutation_rate": 0.01,
+                   "winner_take_all": bool(args.wta),
+                   "cpu_sample_mbp_per_step": args.cpu_mbp,
+                   "timing": "host wall clock around the oracle's screen call, all host threads"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "table_build_s": t_table,
                          "note": "oracle/mash_screen_oracle.c (mash-semantics restatement); real mash is absent from this image"},

@@ -1411,7 +1411,7 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
                              s->d_best_score, s->d_best_len, s->d_winner, E, g_sm, s->stream));
             CU(launch_sketch_reduce(db->d_offsets + b, n, db->d_canon, s->d_counts, s->d_winner, s->d_shared + b,
                                     s->d_median + b, g_sm, s->stream));
-            s->st.n_launches += 4;
+            s->st.n_launches += 5;   // k_winner x4 (clear, score, length, index) + the reduction
         }
     }
     for (size_t j = 0; j < n_seg; j++) {

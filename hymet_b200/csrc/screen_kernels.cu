@@ -729,7 +729,7 @@ cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st)
 
 // Single-CTA bitonic sort + unique.  work = shared memory (n_pad <= kSortSmemMax) or a
 // global scratch buffer.  Padding value kEmptyKey sorts last and is never a real key.
-constexpr uint32_t kSortSmemMax = 8192;
+constexpr uint32_t kSortSmemMax = 16384;   // 128 KB of the 227 KB a CTA may have: covers sketch sizes up to ~10 000
 
 __device__ void bitonic_sort_block(uint64_t *w, uint32_t n_pad)
 {
@@ -915,7 +915,9 @@ __global__ void __launch_bounds__(kReduceThreads) k_winner(const uint64_t *offse
         for (uint64_t e = beg + threadIdx.x; e < end; e += kReduceThreads) {
             const uint32_t id = canon[e];
             if (!counts[id]) continue;
-            if (pass == 0) {
+            if (pass < 0) {   // clear only what the later passes will touch (E x 20 bytes of memset otherwise)
+                best_score[id] = 0; best_len[id] = 0; winner[id] = 0;
+            } else if (pass == 0) {
                 atomicMax(best_score + id, sbits);
             } else if (pass == 1) {
                 if (best_score[id] == sbits) atomicMax(best_len + id, len);
@@ -933,11 +935,9 @@ cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32
 {
     if (!n_refs) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(best_score, 0, n_entries * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(best_len, 0, n_entries * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(winner, 0, n_entries * 4, st)) != cudaSuccess) return e;
+    (void)n_entries;
     const uint32_t grid = (uint32_t)((n_refs < (uint64_t)sm_count * 16) ? n_refs : (uint64_t)sm_count * 16);
-    for (int pass = 0; pass < 3; pass++) {
+    for (int pass = -1; pass < 3; pass++) {
         k_winner<<<grid, kReduceThreads, 0, st>>>(offsets, n_refs, canon, counts, shared, lengths, best_score,
                                                   best_len, winner, pass);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;

@@ -842,7 +842,9 @@ __global__ void __launch_bounds__(256) k_sketch_reduce(const uint64_t *offsets, 
         };
         uint32_t cnt = 0, mx = 0;
         auto take = [&](uint32_t id) {
-            uint32_t c = __ldcg(counts + id);
+            // through L1: a lane's four ids are usually consecutive (keys stored once have canon[e] == e),
+            // so the four gathers of a 128-bit id load fall into the same sectors
+            uint32_t c = __ldg(counts + id);
             if (winner && c && winner[id] != (uint32_t)i) c = 0;
             cnt += c != 0;
             mx = max(mx, c);

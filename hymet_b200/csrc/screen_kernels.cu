@@ -874,10 +874,16 @@ __global__ void __launch_bounds__(256) k_sketch_reduce(const uint64_t *offsets, 
         for (int bit = 31 - __clz(mx); bit >= 0; bit--) {
             const uint32_t himask = ~((2u << bit) - 1u);
             uint32_t z = 0;
-            for (uint64_t q = beg + lane; q < end; q += 32) {
-                const uint32_t c = value(q);
-                z += (c != 0) && ((c & himask) == prefix) && !((c >> bit) & 1u);
+            auto below = [&](uint32_t c) { z += (c != 0) && ((c & himask) == prefix) && !((c >> bit) & 1u); };
+            uint64_t q = beg + lane;
+            for (; q + 7 * 32 < end; q += 8 * 32) {   // eight dependent-load chains in flight: only the few
+                uint32_t c[8];                         // sketches with hits get here, and they are the tail
+#pragma unroll
+                for (int u = 0; u < 8; u++) c[u] = value(q + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 8; u++) below(c[u]);
             }
+            for (; q < end; q += 32) below(value(q));
             z = warp_sum(z);
             if (kk >= z) { kk -= z; prefix |= 1u << bit; }
         }

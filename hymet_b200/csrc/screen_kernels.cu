@@ -959,7 +959,12 @@ cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32
 // P[Binomial(n, r) >= x], summed term by term from the term at x.  The leading term
 // C(n,x) r^x (1-r)^(n-x) is built as a running product with an explicit binary
 // exponent, so nothing large is ever exponentiated: relative error ~ sqrt(x) ulp.
-__device__ double binom_upper_tail(uint64_t x, uint64_t n, double r)
+// One WARP per sketch: the lanes split the factors of the leading term between them (a sketch with
+// 10 000 shared hashes has a 10 000-factor product, and the few hundred sketches with hits used to
+// be the whole run time of the kernel as 16 fully divergent warps), combine the partial products
+// in a butterfly (multiplication commutes, so every lane ends with the same bits) and then all
+// evaluate the short geometric-like tail redundantly.
+__device__ double binom_upper_tail_warp(uint64_t x, uint64_t n, double r, uint32_t lane)
 {
     if (x == 0) return 1.0;
     if (x > n) return 0.0;
@@ -968,21 +973,35 @@ __device__ double binom_upper_tail(uint64_t x, uint64_t n, double r)
     const double q = 1.0 - r;
     const bool upper = (double)x > (double)n * r;  // sum the smaller side
     const uint64_t j0 = upper ? x : x - 1;         // first term of the side we sum
-    // t(j0) = prod_{i=1..j0} ((n-j0+i)/i * r) * q^(n-j0)
-    // numerator and denominator as separate running products (one division at the end instead of
-    // one per factor: FP64 division is what this kernel spent its time on), renormalised every
-    // four factors -- four factors cannot move a value normalised into [0.5, 1) out of range
-    // (factor range 5e-20 .. 1e7)
+    // t(j0) = prod_{i=1..j0} ((n-j0+i)/i * r) * q^(n-j0): numerator and denominator as separate
+    // running products (one division at the end: FP64 division is slow), renormalised every four
+    // factors -- four factors cannot move a value normalised into [0.5, 1) out of range (5e-20 .. 1e7)
     double num = 1.0, den = 1.0;
     long long ex = 0;
-    for (uint64_t i = 1; i <= j0; i++) {
+    uint32_t since = 0;
+    for (uint64_t i = 1 + lane; i <= j0; i += 32) {
         num *= (double)(n - j0 + i) * r;
         den *= (double)i;
-        if ((i & 3u) == 0) {
+        if (++since == 4) {
             int e2;
             num = frexp(num, &e2); ex += e2;
             den = frexp(den, &e2); ex -= e2;
+            since = 0;
         }
+    }
+    {
+        int e2;
+        num = frexp(num, &e2); ex += e2;
+        den = frexp(den, &e2); ex -= e2;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        num *= __shfl_xor_sync(0xffffffffu, num, o);
+        den *= __shfl_xor_sync(0xffffffffu, den, o);
+        ex += __shfl_xor_sync(0xffffffffu, ex, o);
+        int e2;
+        num = frexp(num, &e2); ex += e2;
+        den = frexp(den, &e2); ex -= e2;
     }
     double mant = num / den;
     {
@@ -1015,22 +1034,27 @@ __device__ double binom_upper_tail(uint64_t x, uint64_t n, double r)
     return upper ? side : 1.0 - side;
 }
 
-__global__ void k_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
-                        const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes, double *identity,
-                        double *pvalue)
+__global__ void __launch_bounds__(256) k_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
+                                               const uint64_t *shared64, const uint64_t *offsets,
+                                               const uint64_t *sizes, double *identity, double *pvalue)
 {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t x = shared32 ? (uint64_t)shared32[i] : shared64[i];
-    const uint64_t size = offsets ? offsets[i + 1] - offsets[i] : sizes[i];
-    double id;
-    if (x == size) id = 1.0;
-    else if (x == 0) id = 0.0;
-    else id = pow((double)x / (double)size, 1.0 / (double)k);
-    identity[i] = id;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const double kmer_space = ldexp(1.0, 2 * (int)k);  // 4^k
     const double r = 1.0 / (1.0 + kmer_space / (double)set_size);
-    pvalue[i] = binom_upper_tail(x, size, r);
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint64_t x = shared32 ? (uint64_t)shared32[i] : shared64[i];
+        const uint64_t size = offsets ? offsets[i + 1] - offsets[i] : sizes[i];
+        const double p = binom_upper_tail_warp(x, size, r, lane);
+        if (lane == 0) {
+            double id;
+            if (x == size) id = 1.0;
+            else if (x == 0) id = 0.0;
+            else id = pow((double)x / (double)size, 1.0 / (double)k);
+            identity[i] = id;
+            pvalue[i] = p;
+        }
+    }
 }
 
 cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
@@ -1038,8 +1062,9 @@ cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32
                          double *identity, double *pvalue, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_stats<<<(uint32_t)((n + 127) / 128), 128, 0, st>>>(k, set_size, n, shared32, shared64, offsets, sizes, identity,
-                                                        pvalue);
+    const uint64_t want = (n + 7) / 8;   // 8 warps per CTA, one sketch per warp and trip
+    k_stats<<<(uint32_t)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(k, set_size, n, shared32, shared64, offsets,
+                                                                          sizes, identity, pvalue);
     return cudaGetLastError();
 }
 

@@ -700,3 +700,16 @@ def test_cli_fastq_gzip_and_stdin_inputs(tmp_path):
     a = subprocess.run(mash + ["screen", dbp, fq1], capture_output=True).stdout
     b = subprocess.run(mash + ["screen", dbp, fa1], capture_output=True).stdout
     assert a == b and a
+
+
+@pytest.mark.parametrize("extra,name", [([], "zymo_screen.tsv"), (["-w"], "zymo_screen_w.tsv")])
+def test_real_genome_golden_tsv(golden_dir, extra, name):
+    """Real sequence instead of random bases: 25 RefSeq assemblies of the reference's Zymo case study
+    (strain triplets, plasmids, rRNA repeats, soft-masked and N bases), sketched and screened by the
+    oracle in the build container (tests/golden/make_zymo_golden.py).  The drop-in prints the committed
+    TSV byte for byte, with and without -w."""
+    msh, q = os.path.join(golden_dir, "zymo25.msh"), os.path.join(golden_dir, "zymo_query.fna.gz")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", "-p", "4", "-v", "0.9"] + extra + [msh, q],
+                       capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stdout == open(os.path.join(golden_dir, name), "rb").read()

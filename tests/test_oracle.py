@@ -132,3 +132,20 @@ def test_counts_wrap_and_multiplicity():
     r = db.screen_text(fa)
     assert int(r.shared[0]) == len(sk) and int(r.median[0]) == 3 and r.identity[0] == 1.0
     assert set(r.counts_per_entry.tolist()) == {3}
+
+
+def test_zymo_real_genome_golden_is_reproduced_by_the_oracle(golden_dir):
+    """tests/golden/zymo_*: 25 real RefSeq assemblies from the reference's own case study, sketched
+    and screened by tests/golden/make_zymo_golden.py.  The oracle must keep reproducing the committed
+    TSVs from the committed sketch file and query (the GPU test compares the CUDA path with the same files)."""
+    import subprocess
+    orc.build()
+    msh, q = os.path.join(golden_dir, "zymo25.msh"), os.path.join(golden_dir, "zymo_query.fna.gz")
+    for extra, name in (([], "zymo_screen.tsv"), (["-w"], "zymo_screen_w.tsv")):
+        r = subprocess.run([orc.BIN, "screen", "-p", "3", "-v", "0.9"] + extra + [msh, q], capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        want = open(os.path.join(golden_dir, name), "rb").read()
+        assert r.stdout == want and want.count(b"\n") >= 10
+    db = orc.OracleDB.load_msh(msh)
+    assert db.n_refs == 25 and db.k == 21 and db.s == 1000
+    assert db.name(0).startswith("GCF_") and db.name(0).endswith("_genomic.fna")

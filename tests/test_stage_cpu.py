@@ -154,3 +154,19 @@ def test_select_equals_unmodified_reference_mash_sh(tmp_path, seed, n_genomes, n
     r = stage.select(got[0], n_find, thr)
     assert [r["filtered"], r["sorted"], r["top_hits"], r["selected"]] == got[1:]
     assert r["log"] == p.stdout.decode()
+
+
+def test_select_on_real_genome_golden():
+    """tests/golden/zymo_mash_sh.json = what the unmodified scripts/mash.sh left behind for the real-genome
+    fixture (made by tests/golden/make_zymo_mash_sh_golden.py where /root/reference exists): the restated
+    post-processing reproduces it on any box, including the threshold that had to step down."""
+    import json
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    want = json.load(open(os.path.join(g, "zymo_mash_sh.json")))
+    tab = open(os.path.join(g, "zymo_screen.tsv"), "rb").read()
+    for thr, w in want.items():
+        r = stage.select(tab, 1, thr)
+        for key in ("filtered", "sorted", "top_hits", "selected"):
+            assert r[key] == w[key].encode(), (thr, key)
+        assert r["log"] == w["log"]
+    assert want["0.9"]["log"].count("Testing threshold") > 1      # 0.9 is not reached by five sketches: the loop steps

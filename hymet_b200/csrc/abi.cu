@@ -108,6 +108,7 @@ struct Ingest {
     struct Slot { uint8_t *raw = nullptr, *codes = nullptr; size_t cap = 0; cudaEvent_t done = nullptr, copied = nullptr; };
     Slot slots[kSlots];
     int next = 0;
+    int n_slots = kSlots;   // how many of them rotate (option "ingest_slots")
     FaScratch sc{};
     size_t tile_cap = 0;
     std::vector<unsigned long long *> counter_blocks;   // per-chunk position counters (512 per block)
@@ -147,7 +148,7 @@ struct Ingest {
     int slot_for(size_t bytes, Slot **out)
     {
         Slot &sl = slots[next];
-        next = (next + 1) % kSlots;
+        next = (next + 1) % n_slots;
         CU(cudaEventSynchronize(sl.done));  // throttle: at most kSlots chunks of raw text in flight
         if (sl.cap < bytes) {
             cudaFree(sl.raw); cudaFree(sl.codes);
@@ -313,6 +314,7 @@ struct hs_screen {
     uint64_t piece_positions = (uint64_t)32 << 20;  // packed host feeds are uploaded + launched in pieces
     Ingest ingest;
     int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
+    int ingest_batch = 0;  // spans per device-ingest submission (0 = 3 next to packer threads, 4 alone)
     FileRing ring;
     // plain FASTA files: nominal bytes per reader block and reader threads.  Pinning the ring costs
     // ~0.5 ms per MB once per handle (measured), which a one-shot `mash screen` pays in full: the
@@ -819,6 +821,8 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "chunk_bases")) s->chunk_text = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "piece_bases")) s->piece_positions = value > 8192 ? (uint64_t)value : 8192;
     else if (!strcmp(key, "ingest")) s->ingest_mode = (int)value;
+    else if (!strcmp(key, "ingest_slots")) s->ingest.n_slots = value < 1 ? 1 : (value > Ingest::kSlots ? Ingest::kSlots : (int)value);
+    else if (!strcmp(key, "ingest_batch")) s->ingest_batch = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
     else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
     else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
@@ -1017,7 +1021,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
         cudaSetDevice(g_device);
         // consecutive spans are contiguous text: take a few at a time so that the parser and
         // stream kernels run on >= 48 MB launches (fewer, fuller waves; fewer host wake-ups)
-        const size_t batch = threads > 0 ? 3 : 4;
+        const size_t batch = s->ingest_batch ? (size_t)s->ingest_batch : (threads > 0 ? 3 : 4);
         for (;;) {
             const size_t i = next.fetch_add(batch);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;

@@ -365,6 +365,72 @@ HS_HD uint64_t hash_canonical_premul_msb(uint64_t cm, int k, uint32_t seed, bool
     return hash_canonical_premul(cm, k, seed, use64, Adapter{pre, k});
 }
 
+// ---- the same, TOP-aligned: k-mers sit in the most significant 2k bits of 64 -------------------
+// With F'' = W << (66-2k) and R'' = revcomp(W) >> 2, the forward k-mer ending at base j is the top
+// of F'' << 2j and its reverse complement the bottom 64 bits of R'' >> 2j.  Whatever lies below the
+// 2k bits (later bases) only matters when forward == reverse complement, and then either choice is
+// the same k-mer: no masks before the compare.  String word i is byte (7-i) of the value for
+// every k, so index shifts never straddle a register; a last word with fewer than four bases drops
+// the bases that are not its own through the mask of the address computation.
+HS_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, int s)  // high 32 bits of (hi:lo) << s, 0 <= s <= 31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, (uint32_t)s);
+#else
+    return (uint32_t)(((((uint64_t)hi << 32) | lo) << s) >> 32);
+#endif
+}
+
+HS_HD Win win_init_top(uint64_t prev, uint64_t cur, int k)
+{
+    Win w;
+    const int c = 66 - 2 * k;   // 2..64
+    const uint64_t fh = c >= 64 ? cur : ((prev << c) | (cur >> (64 - c)));
+    const uint64_t fl = c >= 64 ? 0ull : (cur << c);
+    w.f0 = (uint32_t)fl; w.f1 = (uint32_t)(fl >> 32); w.f2 = (uint32_t)fh; w.f3 = (uint32_t)(fh >> 32);
+    const uint64_t rh = pair_reverse64(~cur), rl = pair_reverse64(~prev);  // revcomp(W) = rh:rl
+    const uint64_t lo = (rl >> 2) | (rh << 62), hi = rh >> 2;
+    w.r0 = (uint32_t)lo; w.r1 = (uint32_t)(lo >> 32); w.r2 = (uint32_t)hi; w.r3 = (uint32_t)(hi >> 32);
+    return w;
+}
+
+// q = j mod 16; forward words (fa, fb, fc) = (f1, f2, f3) for j < 16 else (f0, f1, f2); reverse words
+// (ra, rb, rc) = (r0, r1, r2) for j < 16 else (r1, r2, r3)
+HS_HD uint64_t canonical_top_half(uint32_t fa, uint32_t fb, uint32_t fc, uint32_t ra, uint32_t rb, uint32_t rc, int q)
+{
+    const uint32_t flo = funnel_l(fa, fb, 2 * q), fhi = funnel_l(fb, fc, 2 * q);
+    const uint32_t rlo = funnel_r(ra, rb, 2 * q), rhi = funnel_r(rb, rc, 2 * q);
+    const uint64_t fm = ((uint64_t)fhi << 32) | flo, rm = ((uint64_t)rhi << 32) | rlo;
+    return fm <= rm ? fm : rm;
+}
+
+HS_HD uint64_t canonical_top(const Win &w, int j)
+{
+    return j < 16 ? canonical_top_half(w.f1, w.f2, w.f3, w.r0, w.r1, w.r2, j)
+                  : canonical_top_half(w.f0, w.f1, w.f2, w.r1, w.r2, w.r3, j - 16);
+}
+
+HS_HD uint32_t top_word_index64(uint64_t ct, int i, int k)
+{
+    const uint32_t w = i < 4 ? (uint32_t)(ct >> 32) : (uint32_t)ct;
+    const int sh = 18 - 8 * (i & 3);
+    const uint32_t x = sh >= 0 ? (w >> sh) : (w << (-sh));
+    const int nb = k - 4 * i;   // bases of this word that belong to the k-mer
+    const uint32_t keep = nb >= 4 ? 0x3FC0u : ((0xFFu << (8 - 2 * nb)) & 0xFFu) << 6;
+    return x & keep;
+}
+
+template <class Pre>
+HS_HD uint64_t hash_canonical_premul_top(uint64_t ct, int k, uint32_t seed, bool use64, const Pre &pre)
+{
+    struct Adapter {
+        const Pre &p; int k;
+        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(top_word_index64(c, i, k), second); }
+        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(top_word_index64(c, i, k), second); }
+    };
+    return hash_canonical_premul(ct, k, seed, use64, Adapter{pre, k});
+}
+
 struct PremulArithMsb {  // host-side stand-in for the shared-memory tables (tests)
     HS_HD uint64_t full(uint32_t index64, bool second) const { return premul_entry_msb(index64 >> 6, second); }
     HS_HD uint32_t low(uint32_t index64, bool second) const { return (uint32_t)full(index64, second); }

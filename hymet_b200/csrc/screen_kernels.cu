@@ -194,6 +194,9 @@ struct SmemPremul {
 #ifndef HS_WINDOW
 #define HS_WINDOW HS_PREMUL
 #endif
+#ifndef HS_TOP
+#define HS_TOP 1   // top-aligned canonical k-mers (no masks before the compare); 0 = right-aligned
+#endif
 #ifndef HS_ILP
 #define HS_ILP 4
 #endif
@@ -353,7 +356,11 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
         const uint32_t ok = ~invalid_kmer_ends(iprev, icur, k);
         n_valid += (uint32_t)__popc(ok);
 #if HS_WINDOW
+#if HS_TOP
+        const Win w = win_init_top(prev, cur, k);
+#else
         const Win w = win_init(prev, cur, k);
+#endif
         // words whose 32 k-mers are all valid (nearly all of them) run a copy of the loop that never
         // looks at the validity mask
         // (measured dead ends, ms per Gbp at kIlp = 4: compile-time halves + a one-word gate pre-compare
@@ -369,7 +376,11 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
                     uint64_t h[kIlp];
 #pragma unroll
                     for (int u = 0; u < kIlp; u++)
+#if HS_TOP
+                        h[u] = hash_canonical_premul_top(canonical_top_half(fa, fb, fc, ra, rb, rc, q + u), k, a.seed, use64, L);
+#else
                         h[u] = hash_canonical_premul_msb(canonical_msb_half(fa, fb, fc, ra, rb, rc, q + u, k), k, a.seed, use64, L);
+#endif
 #pragma unroll
                     for (int u = 0; u < kIlp; u++) {
                         const int j = half * 16 + q + u;

@@ -64,6 +64,8 @@ int emul_window_vs_roll(uint64_t prev, uint64_t cur, int k, uint32_t seed, uint6
         out_a[j] = hs::hash_canonical(hs::canonical_lsb(r, k), k, seed, use64, hs::AsciiArith());
         out_b[j] = hs::hash_canonical_premul_msb(hs::canonical_msb(w, j, k), k, seed, use64, hs::PremulArithMsb());
         bad += out_a[j] != out_b[j];
+        const hs::Win wt = hs::win_init_top(prev, cur, k);   // top-aligned variant: same hashes again
+        bad += out_a[j] != hs::hash_canonical_premul_top(hs::canonical_top(wt, j), k, seed, use64, hs::PremulArithMsb());
     }
     return bad;
 }

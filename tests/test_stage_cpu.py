@@ -170,3 +170,25 @@ def test_select_on_real_genome_golden():
             assert r[key] == w[key].encode(), (thr, key)
         assert r["log"] == w["log"]
     assert want["0.9"]["log"].count("Testing threshold") > 1      # 0.9 is not reached by five sketches: the loop steps
+
+
+def test_stage_cli_usage_and_no_silent_cpu_result(tmp_path):
+    exe = [sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bin", "hymet-mash-stage")]
+    r = subprocess.run(exe + ["input", "0.9", "db.msh"], capture_output=True, text=True)
+    assert r.returncode == 2 and "hymet-mash-stage" in r.stderr
+    r = subprocess.run(exe + ["-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and "THRESHOLD" in r.stdout
+    outs = [str(tmp_path / f) for f in ("a", "b", "c", "d", "e")]
+    r = subprocess.run(exe + [str(tmp_path), "0.9", "notasketch.txt"] + outs, capture_output=True, text=True)
+    assert r.returncode == 1 and "does not look like a sketch" in r.stderr
+    r = subprocess.run(exe + [str(tmp_path), "abc", "x.msh"] + outs, capture_output=True, text=True)
+    assert r.returncode == 1 and "threshold" in r.stderr
+    import torch
+    if not torch.cuda.is_available():      # without a B200 the stage fails loudly and writes nothing
+        db = mshfmt.SketchDB(k=21, s=10, names=["a"], comments=[""], lengths=np.array([5], np.uint64),
+                             offsets=np.array([0, 2], np.uint64), hashes=np.array([1, 2], np.uint64))
+        p = str(tmp_path / "d.msh")
+        mshfmt.write_msh(p, db)
+        (tmp_path / "x.fna").write_text(">a\nACGT\n")
+        r = subprocess.run(exe + [str(tmp_path), "0.9", p] + outs, capture_output=True, text=True)
+        assert r.returncode == 1 and "ERROR" in r.stderr and not any(os.path.exists(o) for o in outs)

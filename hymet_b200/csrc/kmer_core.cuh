@@ -111,42 +111,13 @@ HS_HD uint64_t rotl64(uint64_t x, int r)
     return (x << r) | (x >> (64 - r));
 #endif
 }
-// The streaming kernel is bound by the ALU pipe (logic, shifts, carry adds) while the multiply pipe
-// has room (ncu: 77 % vs 63 % busy).  HS_FMA_SHIFT moves work across: x >> 1 as the high half of
-// x * 2^31, and a 64-bit add as a wide multiply-add by one plus a 32-bit add.
-// Measured on B200: SLOWER (5.36 ms vs 4.83 ms per Gbp) -- mul.hi / mad.wide do not issue at the
-// rate of plain multiply-adds -- so it stays off; kept as a documented dead end.
-#ifndef HS_FMA_SHIFT
-#define HS_FMA_SHIFT 0
-#endif
-HS_HD uint32_t shr1_fma(uint32_t x)
-{
-#if defined(__CUDA_ARCH__) && HS_FMA_SHIFT
-    uint32_t r;
-    asm("mul.hi.u32 %0, %1, 0x80000000;" : "=r"(r) : "r"(x));
-    return r;
-#else
-    return x >> 1;
-#endif
-}
-#ifndef HS_FMA_ADD
-#define HS_FMA_ADD HS_FMA_SHIFT
-#endif
-HS_HD uint64_t add64_fma(uint64_t a, uint64_t b)
-{
-#if defined(__CUDA_ARCH__) && HS_FMA_ADD
-    uint64_t t;
-    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(t) : "r"((uint32_t)a), "l"(b));   // b + a.lo, carry included
-    const uint32_t hi = (uint32_t)(t >> 32) + (uint32_t)(a >> 32);
-    return ((uint64_t)hi << 32) | (uint32_t)t;
-#else
-    return a + b;
-#endif
-}
+// (Tried on B200 and dropped: x >> 1 as mul.hi by 2^31 and 64-bit adds as mad.wide by one, to move work
+// from the busy ALU pipe to the multiply pipe -- 11 % slower, those forms do not issue at the plain
+// multiply-add rate.)
 HS_HD uint64_t xorshift33(uint64_t k)  // k ^ (k >> 33): only the low word changes
 {
     const uint32_t hi = (uint32_t)(k >> 32);
-    return ((uint64_t)hi << 32) | ((uint32_t)k ^ shr1_fma(hi));
+    return ((uint64_t)hi << 32) | ((uint32_t)k ^ (hi >> 1));
 }
 HS_HD uint64_t fmix64(uint64_t k)
 {
@@ -271,9 +242,9 @@ HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use
         if (b < (k >> 4)) {
             uint64_t k1 = m[2 * b], k2 = m[2 * b + 1];
             k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
-            h1 = rotl64(h1, 27); h1 = add64_fma(h1, h2); h1 = mul5_add(h1, 0x52dce729u);
+            h1 = rotl64(h1, 27); h1 += h2; h1 = mul5_add(h1, 0x52dce729u);
             k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
-            h2 = rotl64(h2, 31); h2 = add64_fma(h2, h1); h2 = mul5_add(h2, 0x38495ab5u);
+            h2 = rotl64(h2, 31); h2 += h1; h2 = mul5_add(h2, 0x38495ab5u);
         }
     }
     if (k & 15) {
@@ -281,9 +252,9 @@ HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use
         uint64_t k1 = m[t & 3]; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
     }
     h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
-    h1 = add64_fma(h1, h2); h2 = add64_fma(h2, h1);
+    h1 += h2; h2 += h1;
     h1 = fmix64(h1); h2 = fmix64(h2);
-    h1 = add64_fma(h1, h2);
+    h1 += h2;
     return use64 ? h1 : (h1 & 0xFFFFFFFFull);
 }
 
@@ -292,12 +263,10 @@ struct PremulArith {  // host-side stand-in for the shared-memory tables (tests)
     HS_HD uint32_t low(uint64_t cl, int i, bool second) const { return (uint32_t)full(cl, i, second); }
 };
 
-// ---- windowed canonical k-mers (first base MOST significant) ----------------------------
-// One thread owns the 64 bases (prev word, cur word).  Instead of rolling two k-mers base by
-// base, keep the 128-bit window W = prev:cur and R' = revcomp(W) >> 2(33-k) in eight 32-bit
-// registers: the forward k-mer ending at base j of cur is (W >> (62-2j)) & mask and its reverse
-// complement is (R' >> 2j) & mask -- two funnel shifts each, with the same word boundary (j = 16)
-// for both.  Halves the ALU work per k-mer spent before the hash.
+// ---- windowed canonical k-mers ------------------------------------------------------------
+// One thread owns the 64 bases (prev word, cur word).  Instead of rolling two k-mers base by base,
+// keep the 128-bit window W = prev:cur and its reverse complement in eight 32-bit registers and cut
+// every k-mer out of them with funnel shifts (below: TOP-aligned).
 struct Win { uint32_t f0, f1, f2, f3, r0, r1, r2, r3; };  // word 0 least significant
 
 HS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s)  // low 32 bits of (hi:lo) >> s, 0 <= s <= 31
@@ -309,63 +278,12 @@ HS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int s)  // low 32 bits of (hi:
 #endif
 }
 
-HS_HD Win win_init(uint64_t prev, uint64_t cur, int k)
-{
-    Win w;
-    w.f0 = (uint32_t)cur; w.f1 = (uint32_t)(cur >> 32); w.f2 = (uint32_t)prev; w.f3 = (uint32_t)(prev >> 32);
-    const uint64_t rh = pair_reverse64(~cur), rl = pair_reverse64(~prev);  // revcomp(W) = rh:rl
-    const int c = 2 * (33 - k);                                           // 2..64
-    const uint64_t lo = c >= 64 ? rh : ((rl >> c) | (rh << (64 - c)));
-    const uint64_t hi = c >= 64 ? 0ull : (rh >> c);
-    w.r0 = (uint32_t)lo; w.r1 = (uint32_t)(lo >> 32); w.r2 = (uint32_t)hi; w.r3 = (uint32_t)(hi >> 32);
-    return w;
-}
-
-// S5 for the k-mer ending at base j (0..31) of cur: min(forward, reverse complement), both read
-// first-base-most-significant (== memcmp order of the ASCII strings), right aligned in 2k bits.
-// q = j mod 16; (fa,fb,fc)/(ra,rb,rc) = the three window words of the half j lies in
-HS_HD uint64_t canonical_msb_half(uint32_t fa, uint32_t fb, uint32_t fc, uint32_t ra, uint32_t rb, uint32_t rc, int q, int k)
-{
-    const uint32_t flo = funnel_r(fa, fb, 30 - 2 * q), fhi = funnel_r(fb, fc, 30 - 2 * q);
-    const uint32_t rlo = funnel_r(ra, rb, 2 * q), rhi = funnel_r(rb, rc, 2 * q);
-    const uint64_t mask = kmer_mask(k);
-    const uint64_t fm = (((uint64_t)fhi << 32) | flo) & mask, rm = (((uint64_t)rhi << 32) | rlo) & mask;
-    return fm <= rm ? fm : rm;
-}
-
-HS_HD uint64_t canonical_msb(const Win &w, int j, int k)
-{
-    return j < 16 ? canonical_msb_half(w.f1, w.f2, w.f3, w.r0, w.r1, w.r2, j, k)
-                  : canonical_msb_half(w.f0, w.f1, w.f2, w.r1, w.r2, w.r3, j - 16, k);
-}
-
-// Table index byte of string word i (bases 4i..4i+3) of an MSB-first canonical k-mer, already
-// shifted into address position: ((byte) << 6).  The byte holds the word's first base in its top
-// two bits; a word with fewer than four bases is padded with code 0 ('A') at the end.
-HS_HD uint32_t msb_word_index64(uint64_t cm, int i, int k)
-{
-    const int sh = 2 * k - 8 * (i + 1) - 6;
-    const uint32_t x = sh >= 0 ? (uint32_t)(cm >> sh) : ((uint32_t)cm << (-sh));
-    return x & 0x3FC0u;
-}
-
+// Table entries for k-mers whose first base is MOST significant: the index byte holds a word's first
+// letter in its top two bits.
 HS_HD uint32_t pair_reverse8(uint32_t b) { return ((b & 3u) << 6) | ((b & 0xCu) << 2) | ((b >> 2) & 0xCu) | ((b >> 6) & 3u); }
 HS_HD uint64_t premul_entry_msb(uint32_t b, bool second) { return premul_entry(pair_reverse8(b), second); }
 
-// hash_canonical_premul for an MSB-first k-mer.  `Pre::full(index64, second)` / `Pre::low(...)`
-// take the pre-shifted index of msb_word_index64.
-template <class Pre>
-HS_HD uint64_t hash_canonical_premul_msb(uint64_t cm, int k, uint32_t seed, bool use64, const Pre &pre)
-{
-    struct Adapter {
-        const Pre &p; int k;
-        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(msb_word_index64(c, i, k), second); }
-        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(msb_word_index64(c, i, k), second); }
-    };
-    return hash_canonical_premul(cm, k, seed, use64, Adapter{pre, k});
-}
-
-// ---- the same, TOP-aligned: k-mers sit in the most significant 2k bits of 64 -------------------
+// ---- TOP-aligned: k-mers sit in the most significant 2k bits of 64 ------------------------------
 // With F'' = W << (66-2k) and R'' = revcomp(W) >> 2, the forward k-mer ending at base j is the top
 // of F'' << 2j and its reverse complement the bottom 64 bits of R'' >> 2j.  Whatever lies below the
 // 2k bits (later bases) only matters when forward == reverse complement, and then either choice is

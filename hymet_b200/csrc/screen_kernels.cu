@@ -123,85 +123,41 @@ struct __align__(16) TileBuf {
 };
 static_assert(sizeof(TileBuf) % 16 == 0, "tile buffers must keep 16-byte alignment");
 
-// 256 x 4-base ASCII expansions, 16 lane copies each (entry b, copy c at b*64 + c*4 bytes), at a
-// 16 KB-ALIGNED shared address: the address of a lookup is then
-//     ((k-mer >> s) & 0x3FC0) | (table base | (lane & 15) * 4)
-// i.e. one shift + one LOP3 instead of shift/and/or/lea -- the kernel is ALU-pipe bound (ncu),
-// and this removes 12 of its ~87 ALU instructions per k-mer.  Lanes l and l+16 share a bank:
-// a 2-way conflict on 6 loads per k-mer, invisible next to ~170 ALU cycles.
-constexpr uint32_t kLutBytes = 256 * 16 * 4;
-struct SmemLut16 {
-    uint32_t base;  // 16 KB-aligned shared-window address of the table | (lane & 15) * 4
-    __device__ __forceinline__ uint32_t operator()(uint64_t cl, int i) const
-    {
-        const uint32_t w = i < 4 ? (uint32_t)cl : (uint32_t)(cl >> 32);
-        const int sh = 8 * (i & 3) - 6;
-        const uint32_t x = sh < 0 ? (w << 6) : (w >> sh);
-        uint32_t v;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((x & 0x3FC0u) | base));
-        return v;
-    }
-};
-
-// Pre-multiplied variant (kmer_core.cuh: hash_canonical_premul): two tables, (u64)letters*c1 and
-// (u64)letters*c2, 256 entries x 8 lane copies x 8 B = 16 KB each, 16 KB aligned and adjacent.
-// Entry b, copy c at b*64 + c*8: a half-warp's 64-bit loads touch each bank pair once per copy, two
-// lanes share a copy (2-way conflict when their entries differ in parity).
+// Pre-multiplied murmur tables (kmer_core.cuh: hash_canonical_premul): (u64)letters*c1 and
+// (u64)letters*c2 for all 256 four-letter words, 8 lane copies each (entry b, copy c at
+// b*64 + c*8 bytes) = 16 KB per table, adjacent, at a 16 KB-ALIGNED shared address, so that the
+// address of a lookup is
+//     (index byte << 6, taken from the k-mer with one shift and the AND below) | (table base | (lane & 7) * 8)
+// i.e. one shift + one LOP3 instead of shift/and/or/lea -- the kernel is ALU-pipe bound (ncu).  A
+// half-warp's 64-bit loads touch each bank pair once per copy; two lanes share a copy (2-way conflict
+// when their entries differ in parity).  The second table is reached through the load's immediate
+// offset.  (First version: a 16-copy table of the ASCII letters and the multiply done in registers.)
+constexpr uint32_t kLutBytes = 16384;   // alignment and size of one table
 constexpr uint32_t kPreBytes = 256 * 8 * 8;
-static_assert(kPreBytes == 16384, "SmemPremul's loads carry this offset as an immediate");
+static_assert(kPreBytes == 16384 && kPreBytes == kLutBytes, "SmemPremul's loads carry this offset as an immediate");
 struct SmemPremul {
-    uint32_t base1, base2;  // table address | (lane & 7) * 8
-    __device__ __forceinline__ uint32_t addr(uint64_t cl, int i, bool second) const
-    {
-        const uint32_t w = i < 4 ? (uint32_t)cl : (uint32_t)(cl >> 32);
-        const int sh = 8 * (i & 3) - 6;
-        const uint32_t x = sh < 0 ? (w << 6) : (w >> sh);
-        return (x & 0x3FC0u) | (second ? base2 : base1);
-    }
-    // MSB-first k-mers (HS_WINDOW): the caller passes the index already in address position
-    // (the second table sits kPreBytes after the first: reached through the load's immediate offset)
+    uint32_t base;  // table address | (lane & 7) * 8
     __device__ __forceinline__ uint64_t full(uint32_t index64, bool second) const
     {
         uint64_t v;
-        if (second) asm("ld.shared.u64 %0, [%1+16384];" : "=l"(v) : "r"(index64 | base1));
-        else asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(index64 | base1));
+        if (second) asm("ld.shared.u64 %0, [%1+16384];" : "=l"(v) : "r"(index64 | base));
+        else asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(index64 | base));
         return v;
     }
     __device__ __forceinline__ uint32_t low(uint32_t index64, bool second) const
     {
         uint32_t v;
-        if (second) asm("ld.shared.u32 %0, [%1+16384];" : "=r"(v) : "r"(index64 | base1));
-        else asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(index64 | base1));
-        return v;
-    }
-    __device__ __forceinline__ uint64_t full(uint64_t cl, int i, bool second) const
-    {
-        uint64_t v;
-        asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr(cl, i, second)));
-        return v;
-    }
-    __device__ __forceinline__ uint32_t low(uint64_t cl, int i, bool second) const
-    {
-        uint32_t v;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr(cl, i, second)));
+        if (second) asm("ld.shared.u32 %0, [%1+16384];" : "=r"(v) : "r"(index64 | base));
+        else asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(index64 | base));
         return v;
     }
 };
 
-#ifndef HS_PREMUL
-#define HS_PREMUL 1
-#endif
-#ifndef HS_WINDOW
-#define HS_WINDOW HS_PREMUL
-#endif
-#ifndef HS_TOP
-#define HS_TOP 1   // top-aligned canonical k-mers (no masks before the compare); 0 = right-aligned
-#endif
 #ifndef HS_ILP
 #define HS_ILP 4
 #endif
 #ifndef HS_MIN_CTAS
-#define HS_MIN_CTAS (HS_PREMUL ? 4 : 5)
+#define HS_MIN_CTAS 4   // 48 KB of shared memory per CTA
 #endif
 constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
 
@@ -231,36 +187,18 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
     }
     const uint32_t dyn_addr = smem_u32(dyn_smem);
     const uint32_t lut_addr = (dyn_addr + (kLutBytes - 1)) & ~(kLutBytes - 1);
-#if HS_PREMUL
     {
         uint32_t dyn_size;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
         if (lut_addr + 2 * kPreBytes > dyn_addr + dyn_size) __trap();  // launch did not leave room for the aligned tables
         uint64_t *t = reinterpret_cast<uint64_t *>(dyn_smem + (lut_addr - dyn_addr));
-#if HS_WINDOW
         for (uint32_t i = tid; i < 2 * 256 * 8; i += kCtaThreads) t[i] = premul_entry_msb((i >> 3) & 255u, i >= 256 * 8);
-#else
-        for (uint32_t i = tid; i < 2 * 256 * 8; i += kCtaThreads) t[i] = premul_entry((i >> 3) & 255u, i >= 256 * 8);
-#endif
     }
-#else
-    {
-        uint32_t *lut = reinterpret_cast<uint32_t *>(dyn_smem + (lut_addr - dyn_addr));
-        for (uint32_t i = tid; i < 256 * 16; i += kCtaThreads) lut[i] = ascii4(i >> 4);
-    }
-#endif
     __syncthreads();
-#if HS_PREMUL
-    uint32_t pre1 = lut_addr | ((lane & 7u) << 3), pre2 = (lut_addr + kPreBytes) | ((lane & 7u) << 3);
-    asm volatile("mov.u32 %0, %0;" : "+r"(pre1));  // opaque per-thread registers: keeps ptxas from splitting
-    asm volatile("mov.u32 %0, %0;" : "+r"(pre2));  // them back into uniform base + lane term
-    const SmemPremul L{pre1, pre2};
-#else
-    uint32_t lut_lane = lut_addr | ((lane & 15u) << 2);
+    uint32_t lut_lane = lut_addr | ((lane & 7u) << 3);
     asm volatile("mov.u32 %0, %0;" : "+r"(lut_lane));  // one opaque per-thread register: keeps ptxas from
                                                         // splitting it back into uniform base + lane term
-    const SmemLut16 L{lut_lane};
-#endif
+    const SmemPremul L{lut_lane};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -355,12 +293,7 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
         // are looked at afterwards.
         const uint32_t ok = ~invalid_kmer_ends(iprev, icur, k);
         n_valid += (uint32_t)__popc(ok);
-#if HS_WINDOW
-#if HS_TOP
         const Win w = win_init_top(prev, cur, k);
-#else
-        const Win w = win_init(prev, cur, k);
-#endif
         // words whose 32 k-mers are all valid (nearly all of them) run a copy of the loop that never
         // looks at the validity mask
         // (measured dead ends, ms per Gbp at kIlp = 4: compile-time halves + a one-word gate pre-compare
@@ -376,11 +309,7 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
                     uint64_t h[kIlp];
 #pragma unroll
                     for (int u = 0; u < kIlp; u++)
-#if HS_TOP
                         h[u] = hash_canonical_premul_top(canonical_top_half(fa, fb, fc, ra, rb, rc, q + u), k, a.seed, use64, L);
-#else
-                        h[u] = hash_canonical_premul_msb(canonical_msb_half(fa, fb, fc, ra, rb, rc, q + u, k), k, a.seed, use64, L);
-#endif
 #pragma unroll
                     for (int u = 0; u < kIlp; u++) {
                         const int j = half * 16 + q + u;
@@ -390,25 +319,6 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
             }
         };
         if (ok == ~0u) word(std::false_type{}); else word(std::true_type{});
-        continue;
-#endif
-        Roll r = roll_init(prev, k);
-#pragma unroll 1
-        for (int j = 0; j < kBasesPerWord; j += kIlp) {
-            uint64_t h[kIlp];
-#pragma unroll
-            for (int u = 0; u < kIlp; u++) {
-                roll_push(r, (uint32_t)(cur >> (62 - 2 * (j + u))) & 3u, k);
-#if HS_PREMUL
-                h[u] = hash_canonical_premul(canonical_lsb(r, k), k, a.seed, use64, L);
-#else
-                h[u] = hash_canonical(canonical_lsb(r, k), k, a.seed, use64, L);
-#endif
-            }
-#pragma unroll
-            for (int u = 0; u < kIlp; u++)
-                if (((ok >> (31 - j - u)) & 1u) && h[u] <= gate) sink(j + u, h[u]);
-        }
     }
 
     n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);
@@ -429,7 +339,6 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
     static uint32_t dyn = 2 * kLutBytes;
     if (!occ) {
         cudaError_t e;
-#if HS_PREMUL
         // the tables need a 16 KB-aligned 32 KB window.  Dynamic shared memory starts right after the
         // 1 KB the system reserves per CTA and the kernel's static buffers, so ask for exactly the
         // distance to the next 16 KB boundary plus the tables (the kernel traps if that ever stops
@@ -439,7 +348,6 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
         const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
         dyn = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes;
         if ((e = cudaFuncSetAttribute(k_stream<KT, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
-#endif
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT, EMIT>, kCtaThreads, dyn);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;

@@ -51,21 +51,19 @@ void emul_hash_both(uint64_t cl, int k, uint32_t seed, uint64_t *out)
     out[1] = hs::hash_canonical_premul(cl, k, seed, k > 16, hs::PremulArith());
 }
 
-// the 32 k-mers ending in `cur`: rolling formulation vs windowed MSB-first + pre-multiplied tables.
+// the 32 k-mers ending in `cur`: rolling formulation vs windowed top-aligned k-mers + pre-multiplied tables.
 // out_a/out_b[j] = hash (validity is a separate mask and not involved); returns mismatches.
 int emul_window_vs_roll(uint64_t prev, uint64_t cur, int k, uint32_t seed, uint64_t *out_a, uint64_t *out_b)
 {
     const bool use64 = k > 16;
     hs::Roll r = hs::roll_init(prev, k);
-    const hs::Win w = hs::win_init(prev, cur, k);
+    const hs::Win wt = hs::win_init_top(prev, cur, k);
     int bad = 0;
     for (int j = 0; j < 32; j++) {
         hs::roll_push(r, (uint32_t)(cur >> (62 - 2 * j)) & 3u, k);
         out_a[j] = hs::hash_canonical(hs::canonical_lsb(r, k), k, seed, use64, hs::AsciiArith());
-        out_b[j] = hs::hash_canonical_premul_msb(hs::canonical_msb(w, j, k), k, seed, use64, hs::PremulArithMsb());
+        out_b[j] = hs::hash_canonical_premul_top(hs::canonical_top(wt, j), k, seed, use64, hs::PremulArithMsb());
         bad += out_a[j] != out_b[j];
-        const hs::Win wt = hs::win_init_top(prev, cur, k);   // top-aligned variant: same hashes again
-        bad += out_a[j] != hs::hash_canonical_premul_top(hs::canonical_top(wt, j), k, seed, use64, hs::PremulArithMsb());
     }
     return bad;
 }

@@ -12,6 +12,7 @@
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
@@ -314,6 +315,7 @@ struct hs_screen {
     uint64_t piece_positions = (uint64_t)32 << 20;  // packed host feeds are uploaded + launched in pieces
     Ingest ingest;
     int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
+    uint64_t text_chunk = (uint64_t)256 << 20;   // gzip / stdin input: bytes inflated per hand-over to the packers
     int ingest_batch = 0;  // spans per device-ingest submission (0 = 3 next to packer threads, 4 alone)
     FileRing ring;
     // plain FASTA files: nominal bytes per reader block and reader threads.  Pinning the ring costs
@@ -823,6 +825,7 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "ingest")) s->ingest_mode = (int)value;
     else if (!strcmp(key, "ingest_slots")) s->ingest.n_slots = value < 1 ? 1 : (value > Ingest::kSlots ? Ingest::kSlots : (int)value);
     else if (!strcmp(key, "ingest_batch")) s->ingest_batch = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
+    else if (!strcmp(key, "text_chunk_bytes")) s->text_chunk = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
     else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
@@ -1220,10 +1223,45 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
         }
         if (fd >= 0) close(fd);
     }
+    // gzip / stdin / FASTQ: decompress on this thread in chunks of whole FASTA records and hand every
+    // chunk to the host packer threads, so memory stays bounded and the GPU works on chunk i while
+    // chunk i+1 is being inflated.  FASTQ cannot be cut safely ('@' also starts quality lines): it is
+    // read to the end first, as before.
+    gzFile f = strcmp(path, "-") == 0 ? gzdopen(0, "rb") : gzopen(path, "rb");
+    if (!f) return fail(HS_EIO, std::string("could not open ") + path);
+    gzbuffer(f, 1 << 20);
+    const size_t chunk = (size_t)s->text_chunk;
     std::vector<char> buf;
-    std::string err;
-    if (!slurp_file(path, buf, err)) return fail(HS_EIO, err);
-    return feed_text_impl(s, buf.data(), buf.size(), host_threads);
+    size_t len = 0, target = chunk;
+    bool fastq = false, first = true, eof = false;
+    int rc = HS_OK;
+    while (!eof && rc == HS_OK) {
+        while (len < target || fastq) {   // fill up to one chunk (everything, for FASTQ)
+            if (buf.size() - len < ((size_t)1 << 22)) buf.resize(std::max(buf.size() * 2, len + ((size_t)1 << 23)));
+            const int r = gzread(f, buf.data() + len, 1u << 22);
+            if (r < 0) { gzclose(f); return fail(HS_EIO, std::string("read error on ") + path); }
+            if (r == 0) { eof = true; break; }
+            len += (size_t)r;
+            if (first) {
+                size_t q = 0;
+                while (q < len && (buf[q] == '\n' || buf[q] == '\r')) q++;
+                if (q < len) { fastq = buf[q] == '@'; first = false; }
+            }
+        }
+        size_t cut = len;
+        if (!eof) {   // last record start in the buffer: everything before it is whole records
+            cut = 0;
+            for (size_t i = len - 1; i > 0; i--)
+                if (buf[i] == '>' && buf[i - 1] == '\n') { cut = i; break; }
+            if (!cut) { target = len + chunk; continue; }   // one record larger than the chunk: keep reading
+        }
+        rc = feed_text_impl(s, buf.data(), cut, host_threads);
+        memmove(buf.data(), buf.data() + cut, len - cut);
+        len -= cut;
+        target = chunk;
+    }
+    gzclose(f);
+    return rc;
 }
 
 HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases)

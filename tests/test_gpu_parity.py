@@ -713,3 +713,29 @@ def test_real_genome_golden_tsv(golden_dir, extra, name):
                        capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
     assert r.stdout == open(os.path.join(golden_dir, name), "rb").read()
+
+
+def test_gzip_input_is_inflated_in_chunks_of_whole_records(tmp_path):
+    """gzip (and stdin) FASTA is inflated chunk by chunk and handed to the packers in whole records:
+    tiny chunks (records larger than a chunk included) give the result of the plain file."""
+    import gzip
+    rng = np.random.default_rng(52)
+    genomes = [synth.random_genome(rng, 150_000) for _ in range(5)]
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    contigs = synth.cut_contigs(rng, genomes, 1_200_000, 0.01, median=6000.0) + [genomes[3]]   # one 150 kb record
+    text = synth.to_fasta([contigs[i] for i in rng.permutation(len(contigs))], "c")
+    path = str(tmp_path / "c.fna.gz")
+    with gzip.open(path, "wb") as fh:
+        fh.write(text)
+    want = odb.screen_text(text, threads=2)
+    for chunk in (4096, 100_000, 1 << 28):
+        scr = hs.Screen(db)
+        scr.set_option("text_chunk_bytes", chunk)
+        scr.feed_fasta(path, 3)
+        res = scr.finish(False)
+        assert res.shared.tolist() == want.shared.tolist() and res.median.tolist() == want.median.tolist(), chunk
+        assert res.set_size == want.set_size and res.stats["n_valid_kmers"] == want.n_kmers
+        assert res.stats["n_records"] == text.count(b">")
+        scr.close()

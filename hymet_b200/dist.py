@@ -97,6 +97,45 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
+# ---- the exchange record: [n_pairs | mixture length | <= s mixture hashes | up to cap (id << 32 | count) pairs] ----
+def record_header(mixture: np.ndarray, s: int) -> np.ndarray:
+    """First 2 + s int64 words of a rank's record (slot 0, the pair count, is filled in later)."""
+    h = np.zeros(2 + s, np.int64)
+    n = len(mixture)
+    h[1] = n
+    if n:
+        h[2:2 + n] = np.asarray(mixture, np.uint64).view(np.int64)
+    return h
+
+
+def parse_heads(heads: np.ndarray):
+    """heads[world, 2 + s] (int64) -> (pair count per rank, list of mixture arrays)."""
+    n_pairs = (heads[:, 0] & 0xFFFFFFFF).astype(np.int64)
+    mixtures = [heads[r, 2:2 + int(heads[r, 1])].view(np.uint64) for r in range(heads.shape[0])]
+    return n_pairs, mixtures
+
+
+def next_cap(most: int, cap: int, n_entries: int) -> int:
+    """Capacity (pairs) of the next record given the largest pair count just seen: the next power of
+    two above 1.5 x that, never more than one pair per entry; unchanged unless this record
+    overflowed or the next one could be half the size.  Every rank computes it from the same heads."""
+    want = 4096
+    while want < most + most // 2:
+        want <<= 1
+    want = min(want, max(4096, int(n_entries)))
+    return want if (most > cap or want * 2 <= cap) else cap
+
+
+def pack_pairs(ids: np.ndarray, counts: np.ndarray) -> np.ndarray:
+    """What k_counts_compact writes: (entry id << 32) | count, as int64 words."""
+    return ((np.asarray(ids, np.uint64) << np.uint64(32)) | np.asarray(counts, np.uint64)).view(np.int64)
+
+
+def unpack_pairs(pairs: np.ndarray):
+    p = np.asarray(pairs).view(np.uint64)
+    return (p >> np.uint64(32)).astype(np.int64), (p & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+
+
 class DistributedScreen:
     """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
@@ -147,32 +186,23 @@ class DistributedScreen:
             self._rec = torch.zeros(n_rec, dtype=torch.int64, device=dev)
             self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
             self._pin = torch.zeros(hdr, dtype=torch.int64, pin_memory=True)
-        local = self.scr.mixture()
-        self._pin[1] = len(local)
-        if len(local):
-            self._pin[2:2 + len(local)] = torch.from_numpy(local.view(np.int64).copy())
+        self._pin.copy_(torch.from_numpy(record_header(self.scr.mixture(), s)))
         self._rec[:hdr].copy_(self._pin, non_blocking=True)     # slot 0 (pair count) is rewritten by the kernel
         if sparse:
             self.scr.counts_compact_async(self._rec[hdr:].data_ptr(), cap, self._rec.data_ptr())
         dist.all_gather_into_tensor(self._all, self._rec)
         heads = self._all.view(self.world, n_rec)[:, :hdr].cpu().numpy()   # the one host sync of the exchange
+        n_pairs, mixtures = parse_heads(heads)
         for r in range(self.world):
-            n = int(heads[r, 1])
-            if r != me and n:
-                self.scr.merge_mixture(heads[r, 2:2 + n].view(np.uint64))
+            if r != me and len(mixtures[r]):
+                self.scr.merge_mixture(mixtures[r])
         if not sparse:
             return self._dense()
-        n_pairs = heads[:, 0] & 0xFFFFFFFF
         most = int(n_pairs.max())
         if self.exchange_mode != "sparse":
-            # size the next record from what this one carried (every rank sees the same heads, so every
-            # rank takes the same decision): the collective moves world x cap x 8 bytes whatever is in them
-            want = 4096
-            while want < most + most // 2:
-                want <<= 1
-            want = min(want, max(4096, int(self.db.n_entries)))
-            if most > cap or want * 2 <= cap:
-                self.cap = want
+            # size the next record from what this one carried: the collective moves world x cap x 8
+            # bytes whatever is in them
+            self.cap = next_cap(most, cap, self.db.n_entries)
         if most > cap:                        # too many distinct hits for this record: dense all-reduce instead
             return self._dense()
         rows = self._all.view(self.world, n_rec)

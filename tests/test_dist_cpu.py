@@ -47,6 +47,88 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _record_worker(rank, world, port, q):
+    """The sparse exchange of hymet_b200.dist.DistributedScreen with CPU stand-ins for the two device
+    kernels (compaction, scatter-add): same record layout, same helpers, same capacity policy."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, w, _ = hd.init_from_env("gloo")
+    offsets, hashes, lengths, fasta = _case()
+    s, E = 200, len(hashes)
+    db = orc.OracleDB.from_arrays(21, s, 42, offsets, hashes, lengths)
+    b, e = hd.record_aligned_range(fasta, r, w)
+    local = db.screen_text(fasta[b:e])
+    cap, log = 16, []                      # far too small: the first screen must fall back to the dense sum
+    for step in range(3):
+        counts = local.counts_per_entry.astype(np.uint32).copy()
+        ids = np.nonzero(counts)[0]
+        rec = np.zeros(2 + s + cap, np.int64)
+        rec[:2 + s] = hd.record_header(local.mixture, s)
+        rec[0] = len(ids)                                               # k_counts_compact: count, then <= cap pairs
+        rec[2 + s:2 + s + min(cap, len(ids))] = hd.pack_pairs(ids[:cap], counts[ids[:cap]])
+        out = torch.empty(w * len(rec), dtype=torch.int64)
+        dist.all_gather_into_tensor(out, torch.from_numpy(rec))
+        rows = out.numpy().reshape(w, len(rec))
+        n_pairs, mixtures = hd.parse_heads(rows[:, :2 + s])
+        merged = hd.merge_bottom_s(mixtures, s)
+        most = int(n_pairs.max())
+        new_cap = hd.next_cap(most, cap, E)
+        if most > cap:
+            t = torch.from_numpy(counts.view(np.int32))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            mode = "dense"
+        else:
+            for rr in range(w):
+                if rr != r:
+                    i2, c2 = hd.unpack_pairs(rows[rr, 2 + s:2 + s + int(n_pairs[rr])])
+                    np.add.at(counts, i2, c2)                                   # k_counts_scatter_add
+            mode = "sparse"
+        log.append((mode, cap, counts.copy(), merged))
+        cap = new_cap
+    q.put((r, log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sparse_record_exchange_protocol_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_record_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    offsets, hashes, lengths, fasta = _case()
+    whole = orc.OracleDB.from_arrays(21, 200, 42, offsets, hashes, lengths).screen_text(fasta)
+    for r in range(world):
+        modes = [m for m, _, _, _ in got[r]]
+        assert modes == ["dense", "sparse", "sparse"]                 # overflow -> fallback, then the adapted record
+        assert got[r][1][1] >= 4096 and got[r][2][1] == got[r][1][1]  # capacity settles
+        for mode, cap, counts, merged in got[r]:
+            assert np.array_equal(counts, whole.counts_per_entry), mode
+            assert np.array_equal(merged, whole.mixture)
+    assert [c for _, c, _, _ in got[0]] == [c for _, c, _, _ in got[1]]   # both ranks take the same decisions
+
+
+def test_record_helpers():
+    assert hd.next_cap(0, 4096, 10 ** 6) == 4096
+    assert hd.next_cap(276_000, 1 << 20, 5 * 10 ** 7) == 1 << 19          # C2: a quarter million pairs -> 4 MB records
+    assert hd.next_cap(276_000, 1 << 19, 5 * 10 ** 7) == 1 << 19          # stays
+    assert hd.next_cap(600_000, 1 << 19, 5 * 10 ** 7) == 1 << 20          # overflow: grows
+    assert hd.next_cap(10 ** 6, 4096, 5000) == 5000                        # never more than one pair per entry
+    ids = np.array([0, 7, 2 ** 31 + 5], np.int64); cnt = np.array([1, 2 ** 32 - 1, 9], np.uint32)
+    i2, c2 = hd.unpack_pairs(hd.pack_pairs(ids, cnt))
+    assert i2.tolist() == ids.tolist() and c2.tolist() == cnt.tolist()
+    mix = np.array([3, 2 ** 63 + 1], np.uint64)
+    n, m = hd.parse_heads(np.stack([hd.record_header(mix, 4), hd.record_header(np.zeros(0, np.uint64), 4)]))
+    assert m[0].tolist() == mix.tolist() and len(m[1]) == 0 and n.tolist() == [0, 0]
+
+
 @pytest.mark.timeout(120)
 def test_sharded_counts_and_mixture_equal_single_process():
     world = 2

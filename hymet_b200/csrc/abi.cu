@@ -1355,7 +1355,8 @@ HS_API int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t 
 {
     if (!s || !d_pairs || !d_n_out) return fail(HS_EINVAL, "null argument");
     NEED_DEVICE();
-    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    // no flush needed: counts[] is final, in stream order, as soon as the last feed has been enqueued
+    // (the mixture finaliser never touches it), so the exchange can start underneath hs_screen_flush
     CU(cudaMemsetAsync(d_n_out, 0, sizeof(uint32_t), s->stream));
     CU(launch_counts_compact(s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, (uint32_t *)d_n_out, s->stream));
     s->st.n_launches++;

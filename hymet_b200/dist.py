@@ -139,20 +139,27 @@ def unpack_pairs(pairs: np.ndarray):
 class DistributedScreen:
     """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
-    Default ("auto"): ONE all-gather per screen.  Every rank contributes a fixed-size record (sized
-    from the previous screen's pair counts, at most 2^20 pairs)
-    [n_pairs | mixture length | <= s mixture hashes | up to `cap` non-zero (entry id, count)
-    pairs]; the pairs are compacted on the device straight into the record
-    (k_counts_compact), so the host synchronises once, after the collective.  Each rank then
-    merges the other mixtures and scatter-adds the other ranks' pairs into its counts[].  A
-    metagenome touches a tiny part of a 50 000-genome table, so the pairs are a few MB where
-    the dense vector is hundreds.  If any rank has more than `cap` non-zero counts the exchange
-    falls back to the north star's single dense NCCL all-reduce of counts[E]
-    (`exchange="dense"` forces it).  Both are exact integer sums.
+    Default ("auto"): every rank compacts its non-zero (entry id, count) pairs on the device
+    (k_counts_compact) into a fixed-size record [pair count | up to `cap` pairs] -- sized from the
+    previous screen's pair counts, at most 2^20 pairs -- and an asynchronous all-gather of the records
+    starts BEFORE the mixture is settled (counts[] is final once the feeds are enqueued), so the
+    big collective runs underneath hs_screen_flush.  A second, tiny all-gather carries every rank's
+    <= s mixture hashes.  The host synchronises once, after both; each rank then merges the other
+    mixtures and scatter-adds the other ranks' pairs into its counts[].  A metagenome touches a
+    tiny part of a 50 000-genome table, so the pairs are a few MB where the dense vector is
+    hundreds.  If any rank has more than `cap` non-zero counts the exchange falls back to the north
+    star's single dense NCCL all-reduce of counts[E] (`exchange="dense"` forces it).  Both are
+    exact integer sums.
     """
 
     def __init__(self, db: hs.Database, device: int, exchange: str = "auto", **kw):
         self.db, self.device = db, device
+        # the library's kernels and torch's collectives must be ordered on ONE stream
+        if kw.get("stream_ptr"):
+            self._tstream = torch.cuda.ExternalStream(kw["stream_ptr"], device=torch.device("cuda", device))
+        else:
+            self._tstream = torch.cuda.Stream(device=torch.device("cuda", device))
+            kw["stream_ptr"] = self._tstream.cuda_stream
         self.scr = hs.Screen(db, **kw)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.exchange_mode = os.environ.get("HYMET_SCREEN_EXCHANGE", exchange)
@@ -160,55 +167,70 @@ class DistributedScreen:
         self.cap = int(min(1 << 20, max(4096, int(db.n_entries) // 8)))
         if self.exchange_mode == "sparse":      # forced: room for every entry, never falls back
             self.cap = int(max(4096, db.n_entries))
-        self._rec = self._all = self._pin = None
+        self._rec = self._all = self._pin = self._hdr = self._hdr_all = None
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
         return getattr(self.scr, name)
 
     def _dense(self):
         t = counts_tensor(self.scr, self.device)
-        torch.cuda.current_stream().synchronize()
+        self._tstream.synchronize()
         if t.numel():
             dist.all_reduce(t, op=dist.ReduceOp.SUM)      # the one dense NCCL all-reduce of the path
-        torch.cuda.current_stream().synchronize()
+        self._tstream.synchronize()
         self.last_exchange = "dense"
 
     def exchange(self):
-        self.scr.flush()
         if self.world == 1:
+            self.scr.flush()
             return
+        with torch.cuda.stream(self._tstream):
+            self._exchange()
+
+    def _exchange(self):
         dev = torch.device("cuda", self.device)
         s, cap, me = self.db.s, self.cap, dist.get_rank()
         sparse = self.exchange_mode != "dense"
         hdr = 2 + s
-        n_rec = hdr + (cap if sparse else 0)
-        if self._rec is None or self._rec.numel() != n_rec:
-            self._rec = torch.zeros(n_rec, dtype=torch.int64, device=dev)
-            self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
+        if self._hdr is None:
+            self._hdr = torch.zeros(hdr, dtype=torch.int64, device=dev)
+            self._hdr_all = torch.empty(self.world * hdr, dtype=torch.int64, device=dev)
             self._pin = torch.zeros(hdr, dtype=torch.int64, pin_memory=True)
-        self._pin.copy_(torch.from_numpy(record_header(self.scr.mixture(), s)))
-        self._rec[:hdr].copy_(self._pin, non_blocking=True)     # slot 0 (pair count) is rewritten by the kernel
+        work = None
         if sparse:
-            self.scr.counts_compact_async(self._rec[hdr:].data_ptr(), cap, self._rec.data_ptr())
-        dist.all_gather_into_tensor(self._all, self._rec)
-        heads = self._all.view(self.world, n_rec)[:, :hdr].cpu().numpy()   # the one host sync of the exchange
-        n_pairs, mixtures = parse_heads(heads)
+            n_rec = 1 + cap                               # [pair count | pairs]
+            if self._rec is None or self._rec.numel() != n_rec:
+                self._rec = torch.zeros(n_rec, dtype=torch.int64, device=dev)
+                self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
+            # counts[] is final once the feeds are enqueued: compact and start the big collective now,
+            # asynchronously, so that it runs underneath the mixture finaliser's host round trips
+            self.scr.counts_compact_async(self._rec[1:].data_ptr(), cap, self._rec.data_ptr())
+            work = dist.all_gather_into_tensor(self._all, self._rec, async_op=True)
+        self.scr.flush()
+        self._pin.copy_(torch.from_numpy(record_header(self.scr.mixture(), s)))
+        self._hdr.copy_(self._pin, non_blocking=True)
+        dist.all_gather_into_tensor(self._hdr_all, self._hdr)             # 8 x (2 + s) words
+        if work is not None:
+            work.wait()                                                   # stream-level wait, the host does not block
+        heads = self._hdr_all.view(self.world, hdr).cpu().numpy()         # the one host sync after the collectives
+        _, mixtures = parse_heads(heads)
         for r in range(self.world):
             if r != me and len(mixtures[r]):
                 self.scr.merge_mixture(mixtures[r])
         if not sparse:
             return self._dense()
+        rows = self._all.view(self.world, 1 + cap)
+        n_pairs = (rows[:, 0].cpu().numpy() & 0xFFFFFFFF).astype(np.int64)
         most = int(n_pairs.max())
         if self.exchange_mode != "sparse":
             # size the next record from what this one carried: the collective moves world x cap x 8
-            # bytes whatever is in them
+            # bytes whatever is in them (every rank sees the same counts, so takes the same decision)
             self.cap = next_cap(most, cap, self.db.n_entries)
         if most > cap:                        # too many distinct hits for this record: dense all-reduce instead
             return self._dense()
-        rows = self._all.view(self.world, n_rec)
         for r in range(self.world):
             if r != me and int(n_pairs[r]):
-                self.scr.counts_scatter_add(rows[r, hdr:].data_ptr(), int(n_pairs[r]))
+                self.scr.counts_scatter_add(rows[r, 1:].data_ptr(), int(n_pairs[r]))
         self.last_exchange = "sparse"
 
     def finish(self, wta: bool = False) -> hs.ScreenResult:

@@ -170,7 +170,9 @@ int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n);
  * counts[] (pairs whose id is >= n_entries are padding and ignored). */
 int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, uint32_t *n);
 /* Same compaction, enqueued on the screen's stream without waiting: the pair count goes to the
- * uint32 at d_n_out (device memory), so a whole exchange needs a single host synchronisation. */
+ * uint32 at d_n_out (device memory), so a whole exchange needs a single host synchronisation.
+ * May be called before hs_screen_flush (after the last feed): counts[] no longer changes, and the
+ * collective that carries the pairs can then run underneath the flush. */
 int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t cap, void *d_n_out);
 int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs);
 int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);

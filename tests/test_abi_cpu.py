@@ -137,3 +137,37 @@ def test_msh_rejects_what_it_cannot_screen(tmp_path):
     assert lib.hs_msh_open(str(tmp_path / "missing.msh").encode(), C.byref(h)) == -4
     open(p, "wb").write(b"\x00" * 4096)   # all-zero file: null root
     assert lib.hs_msh_open(p.encode(), C.byref(h)) == -5
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """The boundary is a C ABI: include/hymet_screen.h must compile as C99 (no C++ types) and a C
+    program must link against libhymet_screen.so and call it (host-only entry points here)."""
+    import subprocess
+    from hymet_b200 import build as b
+    lib = b.build()
+    src = tmp_path / "abi_demo.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "hymet_screen.h"
+int main(void) {
+    hs_db_info_t info; hs_stats_t st; uint64_t seq[16]; uint32_t inv[16]; uint64_t n = 0;
+    const char *fa = ">r\nACGTNACGT\n";
+    memset(&info, 0, sizeof info);
+    if (!hs_version() || !hs_last_error()) return 2;
+    if (hs_packed_words(1) < 1) return 3;
+    if (hs_pack_text(fa, strlen(fa), seq, inv, 16, &n, &st) != 0) return 4;
+    if (n != 10 || st.n_records != 1) return 5;            /* separator + 9 bases */
+    if (hs_init(0) == 0) return 0;                          /* a B200 is present: fine */
+    printf("%s\n", hs_last_error());
+    return hs_db_load_msh("nonexistent.msh", (hs_db **)&info) == 0 ? 6 : 0;   /* no device: an error, never a result */
+}
+''')
+    exe = tmp_path / "abi_demo"
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe),
+                        "-L", os.path.dirname(lib), "-l:libhymet_screen.so", "-Wl,-rpath," + os.path.dirname(lib)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)

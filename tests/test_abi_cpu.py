@@ -3,6 +3,7 @@ header declares, refuses to run without a B200 (no CPU fallback), and its host-o
 entry points (FASTA packer, .msh parser) work."""
 import ctypes as C
 import os
+import sys
 import re
 
 import numpy as np
@@ -171,3 +172,96 @@ int main(void) {
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+
+
+def test_msh_reader_survives_corrupted_files(tmp_path, golden_dir):
+    """.msh files come from outside: truncated or bit-flipped input must end in an error code (or a
+    clean parse), never in a crash or an out-of-bounds read.  Run in a child process so that a crash
+    would be seen as a non-zero exit status."""
+    import subprocess
+    script = tmp_path / "fuzz.py"
+    script.write_text(r'''
+import ctypes as C, os, random, sys
+sys.path.insert(0, %r)
+from hymet_b200 import _abi
+L = _abi.load()
+data = bytearray(open(%r, "rb").read())
+rng = random.Random(7)
+out = os.path.join(%r, "m.msh")
+ok = bad = 0
+for t in range(400):
+    d = bytearray(data)
+    kind = t %% 4
+    if kind == 0:
+        d = d[:rng.randrange(0, len(d))]                                   # truncation
+    elif kind == 1:
+        for _ in range(rng.randrange(1, 8)):
+            d[rng.randrange(0, min(len(d), 4096))] = rng.randrange(256)    # header / pointer area
+    elif kind == 2:
+        for _ in range(rng.randrange(1, 64)):
+            d[rng.randrange(0, len(d))] ^= 1 << rng.randrange(8)           # anywhere
+    else:
+        p = rng.randrange(0, len(d) - 8) & ~7                              # a whole word: far pointers, list sizes
+        d[p:p + 8] = rng.getrandbits(64).to_bytes(8, "little")
+    open(out, "wb").write(d)
+    m = C.c_void_p()
+    rc = L.hs_msh_open(out.encode(), C.byref(m))
+    if rc == 0:
+        info = _abi.DbInfo()
+        L.hs_msh_info(m, C.byref(info))
+        L.hs_msh_free(m)
+        ok += 1
+    else:
+        assert L.hs_last_error(), "error code without a message"
+        bad += 1
+print(ok, bad)
+''' % (ROOT, os.path.join(golden_dir, "zymo25.msh"), str(tmp_path)))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    ok, bad = map(int, r.stdout.split())
+    assert ok + bad == 400 and bad > 100
+
+
+def test_host_parsers_under_address_sanitizer(tmp_path, golden_dir):
+    """The .msh reader on 600 corrupted copies of a real sketch file and the FASTA packer / splitter on
+    10 000 random texts, compiled with -fsanitize=address,undefined (tests/host_emul/fuzz_asan.cpp)."""
+    import random
+    import subprocess
+    exe = str(tmp_path / "fuzz_asan")
+    csrc = os.path.join(ROOT, "hymet_b200", "csrc")
+    r = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17",
+                        os.path.join(ROOT, "tests", "host_emul", "fuzz_asan.cpp"), os.path.join(csrc, "msh_capnp.cpp"),
+                        os.path.join(csrc, "fasta_pack.cpp"), "-lz", "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0 and "asan" in r.stderr.lower():
+        pytest.skip("no sanitizer runtime in this image")
+    assert r.returncode == 0, r.stderr[-2000:]
+    data = bytearray(open(os.path.join(golden_dir, "zymo25.msh"), "rb").read())
+    rng = random.Random(11)
+    files = []
+    for t in range(600):
+        d = bytearray(data)
+        kind = t % 5
+        if kind == 0:
+            d = d[:rng.randrange(0, len(d))]
+        elif kind == 1:
+            for _ in range(rng.randrange(1, 8)):
+                d[rng.randrange(0, min(len(d), 4096))] = rng.randrange(256)
+        elif kind == 2:
+            for _ in range(rng.randrange(1, 64)):
+                d[rng.randrange(0, len(d))] ^= 1 << rng.randrange(8)
+        elif kind == 3:
+            p = rng.randrange(0, len(d) - 8) & ~7
+            d[p:p + 8] = rng.getrandbits(64).to_bytes(8, "little")
+        else:
+            p = rng.randrange(0, min(len(d) - 8, 2048)) & ~7
+            d[p:p + 8] = rng.choice([0, 2 ** 64 - 1, 2 ** 63, 2 ** 32, 2 ** 31, 1, 2, 3, 4]).to_bytes(8, "little")
+        f = str(tmp_path / ("m%d.msh" % t))
+        open(f, "wb").write(d)
+        files.append(f)
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([exe, "msh"] + files, capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ok, bad = map(int, r.stdout.split())
+    assert ok + bad == 600 and bad > 100
+    r = subprocess.run([exe, "pack", "10000"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("ok "), (r.stdout, r.stderr[-3000:])

@@ -728,17 +728,6 @@ cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, ui
 // K4: per-sketch shared count + median multiplicity (rows a11, a13)
 // ---------------------------------------------------------------------------
 constexpr int kReduceThreads = 128;
-constexpr uint32_t kReduceCache = 10240;  // counts of one sketch kept in shared memory (40 KB)
-
-__device__ __forceinline__ uint32_t block_sum128(uint32_t v, uint32_t *red)
-{
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    return red[0] + red[1] + red[2] + red[3];
-}
-
 // One WARP per sketch, no block barriers: 50 000 sketches of 1000 hashes are 50 000 small
 // independent reductions, and almost all of them end after the first pass (no hash present).
 // The first version used a CTA per sketch with two __syncthreads per block sum: latency bound at

@@ -739,3 +739,14 @@ def test_gzip_input_is_inflated_in_chunks_of_whole_records(tmp_path):
         assert res.set_size == want.set_size and res.stats["n_valid_kmers"] == want.n_kmers
         assert res.stats["n_records"] == text.count(b">")
         scr.close()
+
+
+@pytest.mark.parametrize("k,s", [(21, 1000), (31, 5000), (16, 400)])
+def test_gpu_sketch_of_real_sequence(golden_dir, k, s):
+    """`mash sketch` on the GPU against the oracle on real contigs (60 records of the Zymo fixture:
+    soft-masked stretches, rRNA repeats, a few N): same bottom-s hashes, same total length."""
+    import gzip
+    text = gzip.open(os.path.join(golden_dir, "zymo_query.fna.gz"), "rb").read()
+    h, total = hs.sketch_text(text, k, s)
+    want, wtotal = orc.sketch_text(text, k, s, threads=2)
+    assert h.tolist() == want.tolist() and total == wtotal and len(h) == s

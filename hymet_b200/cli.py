@@ -91,17 +91,16 @@ def screen_main(args: List[str], stdout=None) -> int:
     t0 = time.perf_counter()
     marks = []
     mark = lambda what: marks.append((what, time.perf_counter()))
-    from . import screen as hs   # ctypes + numpy only: no torch import on the CLI path
-    from .tsv import screen_lines_db
+    from . import _lite as hs    # ctypes only: neither torch nor numpy on the one-shot CLI path
     mark("imports")
 
     device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
     try:
         sys.stderr.write("Loading %s...\n" % db_path)
-        db = hs.Database.load_msh(db_path, device)       # CUDA context creation overlaps the .msh parse
+        db = hs.LiteDb(db_path, device)                  # CUDA context creation overlaps the .msh parse
         mark("cuda_init + load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
         sys.stderr.write("   %d distinct hashes.\n" % db.n_distinct)
-        scr = hs.Screen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
+        scr = hs.LiteScreen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
         sys.stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
         for p in inputs:
             if p != "-" and not os.path.exists(p):
@@ -122,10 +121,13 @@ def screen_main(args: List[str], stdout=None) -> int:
         if wta:
             sys.stderr.write("Reallocating to winners...\n")
         sys.stderr.write("Computing coverage medians...\n")
-        res = scr.finish(wta)
+        lines = scr.finish_lines(wta, imin, pmax)
+        first = next(lines, None)                 # the reduction runs on the first pull
         mark("finish")
         sys.stderr.write("Writing output...\n")
-        for ln in screen_lines_db(res, db, imin, pmax):
+        if first is not None:
+            stdout.write(first)
+        for ln in lines:
             stdout.write(ln)
         stdout.flush()
         mark("write")

@@ -17,15 +17,20 @@ from ._abi import HsError, check  # noqa: F401  (re-exported)
 
 
 class LiteDb:
-    def __init__(self, path: str, device: int):
-        """Parse the .msh on a helper thread (host only) while this thread creates the CUDA context."""
+    def __init__(self, path, device: int):
+        """`path`: one .msh, or a list of them for one table over several files (hs_db_from_msh_multi).
+        The files are parsed on a helper thread (host only) while this thread creates the CUDA context."""
         L = _abi.load()
-        m, box = C.c_void_p(), {}
+        paths = [path] if isinstance(path, str) else list(path)
+        handles, box = [], {}
 
         def parse():
             try:
-                check(L.hs_msh_open(path.encode(), C.byref(m)))   # hs_last_error() is thread local: check here
-            except Exception as e:                                 # noqa: BLE001
+                for p in paths:
+                    m = C.c_void_p()
+                    check(L.hs_msh_open(p.encode(), C.byref(m)))   # hs_last_error() is thread local: check here
+                    handles.append(m)
+            except Exception as e:                                  # noqa: BLE001
                 box["err"] = e
 
         th = threading.Thread(target=parse)
@@ -34,17 +39,32 @@ class LiteDb:
             _abi.init(device)
         finally:
             th.join()
-        if "err" in box:
-            raise box["err"]
         self._h = C.c_void_p()
         try:
-            check(L.hs_db_from_msh(m, C.byref(self._h)))
+            if "err" in box:
+                raise box["err"]
+            if isinstance(path, str):
+                check(L.hs_db_from_msh(handles[0], C.byref(self._h)))
+            else:
+                arr = (C.c_void_p * len(handles))(*[m.value for m in handles])
+                check(L.hs_db_from_msh_multi(arr, len(handles), C.byref(self._h)))
         finally:
-            L.hs_msh_free(m)
+            for m in handles:
+                L.hs_msh_free(m)
         self.info = _abi.DbInfo()
         check(L.hs_db_info(self._h, C.byref(self.info)))
         self.n_refs = int(self.info.n_refs)
         self.n_distinct = int(self.info.n_distinct)
+
+    @property
+    def segments(self):
+        """[(first reference, one past the last)] per source file."""
+        L = _abi.load()
+        n = C.c_uint32()
+        check(L.hs_db_segments(self._h, C.byref(n), None, None))
+        rb = (C.c_uint64 * (n.value + 1))()
+        check(L.hs_db_segments(self._h, C.byref(n), rb, None))
+        return [(int(rb[j]), int(rb[j + 1])) for j in range(n.value)]
 
     def ref(self, i: int):
         nm, cm = C.c_char_p(), C.c_char_p()
@@ -56,6 +76,7 @@ class LiteDb:
 class LiteScreen:
     def __init__(self, db: LiteDb, probe_filter: bool = True):
         self.db = db
+        self._cols = None
         self._h = C.c_void_p()
         check(_abi.load().hs_screen_new(db._h, C.byref(self._h)))
         if not probe_filter:
@@ -72,17 +93,17 @@ class LiteScreen:
         check(_abi.load().hs_screen_stats(self._h, C.byref(st)))
         return st.asdict()
 
-    def finish_lines(self, wta: bool, min_identity: float, max_pvalue: float) -> Iterator[str]:
-        """Rows a11-a16: reduce, then the TSV lines in sketch order (S15: keep iff (shared > 0 or -i < 0)
-        and identity >= -i and p <= -v; numbers as C `%g`)."""
-        n = max(self.db.n_refs, 1)
-        shared = (C.c_uint64 * n)()
-        median = (C.c_uint32 * n)()
-        identity = (C.c_double * n)()
-        pvalue = (C.c_double * n)()
-        check(_abi.load().hs_screen_finish(self._h, int(wta), shared, median, identity, pvalue, None))
+    def finish_lines(self, wta: bool, min_identity: float, max_pvalue: float, begin: int = 0, end: int = None) -> Iterator[str]:
+        """Rows a11-a16: reduce (once), then the TSV lines of references [begin, end) in sketch order
+        (S15: keep iff (shared > 0 or -i < 0) and identity >= -i and p <= -v; numbers as C `%g`)."""
+        if self._cols is None:
+            n = max(self.db.n_refs, 1)
+            cols = ((C.c_uint64 * n)(), (C.c_uint32 * n)(), (C.c_double * n)(), (C.c_double * n)())
+            check(_abi.load().hs_screen_finish(self._h, int(wta), cols[0], cols[1], cols[2], cols[3], None))
+            self._cols = cols
+        shared, median, identity, pvalue = self._cols
         all_rows = min_identity < 0.0
-        for i in range(self.db.n_refs):
+        for i in range(begin, self.db.n_refs if end is None else end):
             sh = shared[i]
             if not sh and not all_rows:
                 continue

@@ -183,8 +183,7 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
               merge: bool = False, device: int = 0, stdout=None) -> int:
     """jobs: (DB.msh, SCREEN_TAB, FILTERED, SORTED, TOP_HITS, SELECTED) per sketch file."""
     stdout = stdout or sys.stdout
-    from . import screen as hs
-    from .tsv import screen_lines_db
+    from . import _lite as hs          # ctypes only: this is a one-shot process, numpy would be 15 % of it
 
     files, n_fna = input_files(input_dir)
     for j in jobs:
@@ -193,17 +192,16 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
             return 1
     try:
         try:
-            db = hs.Database.load_msh_multi([j[0] for j in jobs], device)
-            groups = [(db, list(range(len(jobs))))]
+            groups = [(hs.LiteDb([j[0] for j in jobs], device), list(range(len(jobs))))]
         except hs.HsError as e:
             if "one at a time" not in e.msg:
                 raise
             groups = None                      # sketch files with different k / seed: one table each
         if groups is None:
-            groups = [(hs.Database.load_msh(j[0], device), [i]) for i, j in enumerate(jobs)]
+            groups = [(hs.LiteDb(j[0], device), [i]) for i, j in enumerate(jobs)]
         results: Dict[int, bytes] = {}
         for db, idx in groups:
-            scr = hs.Screen(db)
+            scr = hs.LiteScreen(db)
             if not files:                      # the shell would hand mash the unexpanded pattern
                 sys.stderr.write("ERROR: could not open %s for reading.\n" % os.path.join(input_dir, "*.fna"))
                 return 1
@@ -213,10 +211,8 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
             if scr.stats()["n_records"] == 0:
                 sys.stderr.write("ERROR: Did not find sequence records in inputs.\n")
                 return 1
-            res = scr.finish(False)
             for seg, (b, e) in zip(idx, db.segments):
-                results[seg] = "".join(screen_lines_db(res, db, 0.0, max_p, b, e)).encode("utf-8", "surrogateescape")
-            scr.close()
+                results[seg] = "".join(scr.finish_lines(False, 0.0, max_p, b, e)).encode("utf-8", "surrogateescape")
     except hs.HsError as e:
         sys.stderr.write("ERROR: %s\n" % e.msg)
         return 1

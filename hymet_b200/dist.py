@@ -182,8 +182,7 @@ class DistributedScreen:
 
     def exchange(self):
         if self.world == 1:
-            self.scr.flush()
-            return
+            return          # nothing to exchange; finish() settles the mixture underneath the per-sketch reduction
         with torch.cuda.stream(self._tstream):
             self._exchange()
 

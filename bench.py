@@ -297,8 +297,9 @@ def run_b200(args):
     peak, peak_src = measured_peak_gbs()
     ms_stream = sum(s["ms_stream"] for s in stats) / len(stats)
     ms_reduce = sum(s["ms_reduce"] for s in stats) / len(stats)
-    alg_bytes = st["n_positions"] * 3 / 8 + 32 * st["n_bucket_reads"] + 64 * st["n_hits"]
-    sem_bytes = st["n_positions"] * 3 / 8 + 32 * st["n_valid_kmers"] + 64 * st["n_hits"]
+    ms_reset = sum(s["ms_reset"] for s in stats) / len(stats)
+    alg_bytes = st["n_positions"] * 3 / 8 + 128 * st["n_bucket_reads"] + 64 * st["n_hits"]
+    sem_bytes = st["n_positions"] * 3 / 8 + 128 * st["n_valid_kmers"] + 64 * st["n_hits"]
     achieved = alg_bytes / (ms_stream * 1e-3) / 1e9
     traffic = None
     try:
@@ -334,13 +335,17 @@ def run_b200(args):
         "roofline": roofline,
         "gpu_launches": launches,
         "clocks": clocks,
-        "step_breakdown_ms": {"stream_kernel": ms_stream, "mixture_and_reduce": ms_reduce,
+        "step_breakdown_ms": {"stream_kernel": ms_stream, "mixture_and_reduce": ms_reduce, "reset": ms_reset,
+                              "host_gaps_and_result_copy": ms / args.steps - ms_stream - ms_reduce - ms_reset,
                               "step_total": ms / args.steps, "wall_per_step": 1e3 * wall / args.steps},
+        "reduce": {"path": "dense O(stored hashes)" if st["reduce_path"] else "sparse O(present hashes)",
+                   "present_hashes": st["n_touched"], "refs_with_hits": st["n_hit_refs"], "pairs_walked": st["n_pairs"]},
         "counters": {k_: st[k_] for k_ in ("n_positions", "n_valid_kmers", "n_probes", "n_bucket_reads", "n_hits",
                                           "n_mix_inserts", "n_mix_passes", "set_size")},
         "db": {"distinct_hashes": int(db.n_distinct), "table_mb": db.info.device_bytes / 1e6,
                "tiny_genome_sketches": args.tiny, "bloom_mb": db.info.bloom_bytes / 1e6,
                "range_filter_pass_fraction": db.info.max_key / 2.0 ** 64,
+               "dense_range_fraction": db.info.dense_max / 2.0 ** 64, "keys_in_bloom_tier": int(db.info.bloom_keys),
                "table_build_s": db.info.t_build_s},
         "setup_s": t_setup,
     }
@@ -354,24 +359,28 @@ def run_b200(args):
             hits, reads, pms = db.probe_device(hq.data_ptr(), n_probe)
             best = pms if best is None else min(best, pms)
         # what this GPU delivers for raw random 32-byte sector reads (no hashing), same footprint
-        gbuf = torch.empty(int(db.info.n_buckets) * 4, dtype=torch.int64, device=dev)
+        gbuf = torch.empty(int(db.info.n_buckets) * 16, dtype=torch.int64, device=dev)
         g_ms = min(hs.gather_bench(gbuf.data_ptr(), gbuf.numel() * 8, n_probe) for _ in range(3))
         del gbuf
-        p_traffic = None
+        p_traffic, p_src = None, None
         try:
-            ent = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_probe", {})
+            ent = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_probe_r02", {})
             if ent.get("probes") == n_probe and ent.get("sketches") == args.sketches:
-                p_traffic = ent.get("dram_bytes_per_launch")
+                p_traffic, p_src = ent.get("dram_bytes_per_launch"), "static: " + ent.get("source", "profiles/")
         except Exception:
             pass
-        gbs = (32.0 * reads + 8.0 * n_probe) / (best * 1e-3) / 1e9
-        line["probe_kernel"] = {"kernel": "k_probe", "probes": n_probe, "bucket_reads": int(reads), "ms": best,
-                                "probes_per_s": n_probe / (best * 1e-3), "achieved": gbs, "peak": peak, "unit": "GB/s",
-                                "frac": gbs / peak, "bytes": "32 B bucket sector per read + 8 B hash read per probe",
-                                "traffic": p_traffic,
+        gbs = (128.0 * reads + 8.0 * n_probe) / (best * 1e-3) / 1e9
+        line["probe_kernel"] = {"kernel": "k_probe (warp-cooperative, 8 lanes per 128-byte bucket)", "probes": n_probe,
+                                "bucket_reads": int(reads), "ms": best,
+                                "probes_per_s": n_probe / (best * 1e-3), "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                "frac": gbs / peak,
+                                "bytes": "128 B bucket line per read (10 keys + their ids + overflow flag: everything a probe "
+                                         "needs, hit or miss) + 8 B hash read per probe",
+                                "traffic": p_traffic, "traffic_source": p_src,
                                 "dram_frac_with_measured_traffic": (p_traffic / (best * 1e-3) / 1e9 / peak) if p_traffic else None,
-                                "note": "B200 serves each random 32-byte bucket read as a 128-byte DRAM fetch (ncu: 3.8 sectors per "
-                                        "read), so the kernel runs at the DRAM roofline while a quarter of the moved bytes are useful",
+                                "table_bytes_per_key": db.info.n_buckets * 128.0 / max(1, db.info.n_entries),
+                                "round1_layout": "32 B buckets of 4 keys + ids in a second array: 4.0e10 probes/s, 0.25 of peak in "
+                                                 "useful bytes, 0.78 in moved bytes (B200 fills 128 B per 32 B read), 36 B per key",
                                 "random_sector_reads_per_s_of_this_gpu": n_probe / (g_ms * 1e-3),
                                 "frac_of_random_sector_rate": (reads / (best * 1e-3)) / (n_probe / (g_ms * 1e-3))}
         del hq

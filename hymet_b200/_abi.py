@@ -33,7 +33,8 @@ class DbInfo(C.Structure):
                 ("n_refs", C.c_uint64), ("n_entries", C.c_uint64), ("n_distinct", C.c_uint64),
                 ("n_buckets", C.c_uint64), ("max_key", C.c_uint64), ("device_bytes", C.c_uint64),
                 ("bloom_bytes", C.c_uint64),
-                ("t_parse_s", C.c_double), ("t_build_s", C.c_double)]
+                ("t_parse_s", C.c_double), ("t_build_s", C.c_double),
+                ("dense_max", C.c_uint64), ("bloom_keys", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -42,7 +43,9 @@ class Stats(C.Structure):
                 ("n_hits", C.c_uint64), ("n_mix_inserts", C.c_uint64), ("set_size", C.c_uint64),
                 ("n_mixture", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("n_launches", C.c_uint32), ("n_mix_passes", C.c_uint32),
-                ("ms_stream", C.c_float), ("ms_reduce", C.c_float)]
+                ("ms_stream", C.c_float), ("ms_reduce", C.c_float), ("ms_reset", C.c_float),
+                ("reduce_path", C.c_uint32), ("n_touched", C.c_uint32), ("n_hit_refs", C.c_uint32),
+                ("n_pairs", C.c_uint32), ("exchange_overflow", C.c_uint32), ("exchange_max_pairs", C.c_uint32)]
 
     def asdict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -86,7 +89,10 @@ SIGNATURES = {
     "hs_screen_counts_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
     "hs_screen_counts_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "hs_screen_counts_scatter_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "hs_screen_counts_absorb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "hs_screen_mixture_get": (C.c_int, [C.c_void_p, u64p, u32p]),
+    "hs_screen_mixture_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hs_screen_mixture_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "hs_screen_mixture_merge": (C.c_int, [C.c_void_p, u64p, C.c_uint32]),
     "hs_screen_segment_set_size": (C.c_int, [C.c_void_p, C.c_uint32, u64p]),
     "hs_screen_finish": (C.c_int, [C.c_void_p, C.c_int, u64p, u32p, f64p, f64p, C.POINTER(Stats)]),

@@ -49,11 +49,27 @@ int fail(int code, const std::string &msg)
         cudaError_t e_ = (x);                                                                         \
         if (e_ != cudaSuccess) return fail(HS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+// Entry points without a handle run on the device of the latest hs_init(); handles remember the
+// device they were created on (one process may drive several GPUs, one db + screen per GPU).
 #define NEED_DEVICE()                                                                                      \
     do {                                                                                                   \
         if (g_device < 0) return fail(HS_ENODEV, "hs_init() has not bound an sm_100 device (no CPU fallback)"); \
         CU(cudaSetDevice(g_device));                                                                       \
     } while (0)
+#define ON_DEVICE(dev) CU(cudaSetDevice(dev))
+
+// device allocations of a build step: freed on every return path unless released to their owner
+struct DevBufs {
+    std::vector<void *> p;
+    template <class T> cudaError_t alloc(T **out, size_t bytes)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, bytes ? bytes : 1);
+        if (e == cudaSuccess) { p.push_back(q); *out = (T *)q; }
+        return e;
+    }
+    ~DevBufs() { for (void *q : p) cudaFree(q); }
+};
 
 double now_s()
 {
@@ -117,11 +133,13 @@ struct Ingest {
     unsigned long long *d_totals = nullptr;             // [0] positions [1] bases [2] records
     bool ready = false;
 
-    int ensure(size_t bytes)
+    int ensure(size_t bytes, cudaStream_t st)
     {
         if (!ready) {
             CU(cudaMalloc((void **)&d_totals, 4 * sizeof(unsigned long long)));
-            CU(cudaMemset(d_totals, 0, 4 * sizeof(unsigned long long)));
+            // on the stream that will accumulate into it: the legacy default stream is not ordered
+            // against a non-blocking stream
+            CU(cudaMemsetAsync(d_totals, 0, 4 * sizeof(unsigned long long), st));
             for (auto &sl : slots) {
                 CU(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming | cudaEventBlockingSync));
                 CU(cudaEventCreateWithFlags(&sl.copied, cudaEventDisableTiming));
@@ -190,18 +208,19 @@ struct Ingest {
 // at flush.  Exactness: a value is dropped only when >= s smaller distinct values stay.
 struct MixEngine {
     uint32_t s = 0, cap = 0, cand_cap = 0;
+    bool use64 = true;     // 32-bit hashes (k <= 16) live in [0, 2^32): caps and tau start there
     uint64_t *d_set[2] = {nullptr, nullptr};
     MixState *d_state = nullptr;
     MixState *h_state = nullptr;  // pinned mirror, valid after sync_state()
-    MixState *h_init = nullptr;   // pinned source for resets
     uint64_t *d_cand = nullptr, *d_scratch = nullptr;
     uint64_t *h_cand = nullptr;   // pinned: the settled mixture travels with the state, one sync for both
     bool auto_tau = true;  // first pass: cap tau per launch so expected offers stay <= cap/8
     uint32_t passes = 1;
 
-    int init(uint32_t s_)
+    int init(uint32_t s_, bool use64_ = true)
     {
         s = s_ ? s_ : 1;
+        use64 = use64_;
         cap = 1u << 20;
         while ((uint64_t)cap < 64ull * s) cap <<= 1;
         cand_cap = 8192;
@@ -209,7 +228,6 @@ struct MixEngine {
         for (int i = 0; i < 2; i++) CU(cudaMalloc((void **)&d_set[i], (size_t)cap * 8));
         CU(cudaMalloc((void **)&d_state, sizeof(MixState)));
         CU(cudaHostAlloc((void **)&h_state, sizeof(MixState), cudaHostAllocDefault));
-        CU(cudaHostAlloc((void **)&h_init, sizeof(MixState), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
         CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
         CU(cudaHostAlloc((void **)&h_cand, (size_t)s * 8, cudaHostAllocDefault));
@@ -220,25 +238,23 @@ struct MixEngine {
         for (int i = 0; i < 2; i++) cudaFree(d_set[i]);
         cudaFree(d_state); cudaFree(d_cand); cudaFree(d_scratch);
         if (h_state) cudaFreeHost(h_state);
-        if (h_init) cudaFreeHost(h_init);
         if (h_cand) cudaFreeHost(h_cand);
     }
     uint32_t *field(size_t off) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(d_state) + off); }
     int reset(cudaStream_t st, uint64_t new_tau = ~0ull, bool automatic = true)
     {
-        CU(cudaStreamSynchronize(st));  // h_init may still be the source of an earlier reset
-        memset(h_init, 0, sizeof(MixState));
-        h_init->tau = new_tau;
         CU(cudaMemsetAsync(d_set[0], 0xFF, (size_t)cap * 8, st));
-        CU(cudaMemcpyAsync(d_state, h_init, sizeof(MixState), cudaMemcpyHostToDevice, st));
+        CU(launch_mix_state_init(d_state, new_tau, st));
         auto_tau = automatic;  // a re-offer pass runs at exactly the tau the finaliser chose
         return HS_OK;
     }
     // cap for a launch over n positions: expected offers <= capacity/8
     uint64_t launch_cap(uint64_t n) const
     {
-        const uint64_t budget = cap / 8;
-        return (auto_tau && n > budget) ? (~0ull / n) * budget : ~0ull;
+        const uint64_t budget = cap / 8, space = use64 ? ~0ull : 0xFFFFFFFFull;
+        if (!auto_tau || n <= budget) return ~0ull;
+        const uint64_t c = (uint64_t)((unsigned __int128)space * budget / n);
+        return c < 256 ? 256 : c;
     }
     MixView view(uint64_t tau_cap) const
     {
@@ -263,25 +279,28 @@ struct MixEngine {
 struct hs_msh { MshData d; };
 
 struct hs_db {
+    int device = 0, sm = 0;
     uint32_t k = 0, s = 0, seed = 42;
     bool use64 = true;
-    uint64_t n_refs = 0, n_entries = 0, n_distinct = 0, max_key = 0;
+    uint64_t n_refs = 0, n_entries = 0, n_distinct = 0, max_key = 0, dense_max = 0;
     std::vector<std::string> names, comments;
     std::vector<uint64_t> lengths, offsets;
-    uint64_t *d_keys = nullptr;
-    uint32_t *d_vals = nullptr;
+    uint64_t *d_buckets = nullptr;           // n_buckets x 128 bytes: keys | canonical entry ids | overflow flag
     uint32_t n_buckets = 0, special = kNoEntry;
-    uint32_t *d_canon = nullptr;
-    uint64_t *d_offsets = nullptr, *d_lengths = nullptr;
+    uint32_t *d_canon = nullptr;             // per stored hash: canonical entry id of its key (reference -> hashes, dense path)
+    uint32_t *d_next = nullptr;              // per stored hash: next entry holding the same key (hash -> references, sparse path)
+    uint64_t *d_offsets = nullptr, *d_lengths = nullptr, *d_seg_begin = nullptr;
+    uint32_t *d_seg_s = nullptr;
     uint64_t device_bytes = 0;
     double t_parse = 0, t_build = 0;
-    unsigned long long *d_bloom = nullptr;
+    uint32_t *d_bloom = nullptr;
     uint32_t bloom_mask = 0;
+    uint64_t bloom_keys = 0;                 // keys above dense_max (what the Bloom filter holds)
     // Several .msh files screened in one pass (run_hymet_cami.sh:85-97 streams the query three times):
     // references [seg_begin[j], seg_begin[j+1]) came from file j, whose sketch size was seg_s[j].
     std::vector<uint64_t> seg_begin;
     std::vector<uint32_t> seg_s;
-    TableView view() const { return TableView{d_keys, d_vals, n_buckets, max_key, special, d_bloom, bloom_mask}; }
+    TableView view() const { return TableView{d_buckets, n_buckets, max_key, special, d_bloom, bloom_mask, d_bloom ? dense_max : max_key}; }
 };
 
 // pinned ring the file readers pread() into: two slots per reader thread
@@ -328,6 +347,21 @@ struct hs_screen {
     std::mutex giant_mu;                        // records larger than a ring slot take the host path, one at a time
     uint32_t *d_counts = nullptr;
     unsigned long long *d_stats = nullptr;
+    // O(present hashes) bookkeeping (SparseState): ids of the non-zero counts, references with hits,
+    // their depth segments.  touched_valid: the list covers every non-zero count as far as the HOST
+    // knows (a dense all-reduce into counts[] invalidates it; the device flags overflow and wraps).
+    SparseState *d_sparse = nullptr, *h_sparse = nullptr;
+    uint32_t *d_touched = nullptr, *d_hit = nullptr, *d_seg_start = nullptr, *d_seg_fill = nullptr, *d_plain = nullptr;
+    uint32_t *d_depths = nullptr;
+    uint32_t touched_cap = 0, pair_cap = 0;
+    bool touched_valid = true, sparse_enabled = true;
+    uint32_t last_reduce_dense = 0;
+    // multi-GPU: mixture merged on the device (hs_screen_mixture_merge_device)
+    uint64_t *d_mixture = nullptr, *d_merge_work = nullptr, *d_merge_scratch = nullptr, *h_mixture = nullptr;
+    uint32_t merge_cap = 0;
+    bool mixture_on_device = false;
+    cudaEvent_t rst0 = nullptr, rst1 = nullptr;
+    bool rst_pending = false;
     MixEngine mix;
     std::vector<uint64_t> mixture;  // settled s smallest distinct hashes, ascending
     bool flushed = false;
@@ -340,6 +374,7 @@ struct hs_screen {
     std::vector<Staging> staging;
     std::mutex mu;  // serialises arena + launches when packer threads feed concurrently
     bool filter = true;
+    int batch_bloom = 1;
     uint64_t chunk_text = (uint64_t)16 << 20;
     hs_stats_t st;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -352,14 +387,56 @@ struct hs_screen {
 
 namespace {
 
+// Two-tier pre-filter: where does the dense range end?  Sketches of ordinary genomes keep hashes
+// below ~2^64 * s / genome k-mers; sketches of genomes with fewer than ~s k-mers (viruses, plasmids)
+// reach up to 2^64.  Probing directly costs a DRAM line per k-mer <= T, the Bloom tier an L2 word per
+// k-mer in (T, max_key] plus a probe per false positive.  T runs over the references' largest hashes;
+// keys above T are estimated per reference as size * (1 - T / max) (uniform below its own max).
+struct FilterPlan { uint64_t dense_max; uint64_t words; double keys_above; bool bloom; };
+
+FilterPlan plan_filter(const hs_db *db, const uint64_t *hashes)
+{
+    FilterPlan best{db->max_key, 0, 0.0, false};
+    const double kSpace = 18446744073709551616.0, kProbeCost = 8.0, kBloomCost = 1.0, kMaxBits = 64.0 * 8 * 1048576;
+    struct R { double mx, size; };
+    std::vector<R> r;
+    for (uint64_t i = 0; i < db->n_refs; i++)
+        if (db->offsets[i + 1] > db->offsets[i])
+            r.push_back({(double)hashes[db->offsets[i + 1] - 1], (double)(db->offsets[i + 1] - db->offsets[i])});
+    if (r.empty()) return best;
+    std::sort(r.begin(), r.end(), [](const R &a, const R &b) { return a.mx < b.mx; });
+    double suf_size = 0, suf_ratio = 0;   // over references whose max lies above the candidate
+    double best_cost = (double)db->max_key / kSpace * kProbeCost;   // no Bloom tier: probe everything in range
+    std::vector<double> ss(r.size() + 1, 0.0), sr(r.size() + 1, 0.0);
+    for (size_t i = r.size(); i-- > 0;) {
+        suf_size += r[i].size; suf_ratio += r[i].size / std::max(r[i].mx, 1.0);
+        ss[i] = suf_size; sr[i] = suf_ratio;
+    }
+    const size_t step = std::max<size_t>(1, r.size() / 4096);
+    for (size_t i = 0; i + 1 < r.size(); i += step) {
+        const double T = r[i].mx;
+        const double above = std::max(0.0, ss[i + 1] - T * sr[i + 1]);
+        double bits = 4096.0 * 32;
+        while (bits < above * 24.0 && bits < kMaxBits) bits *= 2;
+        const double fp = pow(1.0 - exp(-3.0 * above / bits), 3.0) * 1.5;   // blocked filter: somewhat worse than the textbook rate
+        const double p_direct = T / kSpace, p_bloom = ((double)db->max_key - T) / kSpace;
+        const double cost = p_direct * kProbeCost + p_bloom * (kBloomCost + fp * kProbeCost);
+        if (cost < best_cost) { best_cost = cost; best = FilterPlan{(uint64_t)T, (uint64_t)(bits / 32), above, true}; }
+    }
+    return best;
+}
+
 int db_build(hs_db *db, const uint64_t *hashes)
 {
     const double t0 = now_s();
     const uint64_t E = db->n_entries, N = db->n_refs;
+    db->device = g_device; db->sm = g_sm;
     if (E > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "more than 2^32 stored hashes");
+    if (N > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "more than 2^32 references");
     if (db->k == 0 || db->k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
-    uint64_t nb = (E * 3 + 3) / 4;  // 4 slots per bucket -> load factor <= 1/3
+    uint64_t nb = (E + 5) / 6 + 1;  // 10 slots per bucket -> load factor <= 0.6
     if (nb < 16) nb = 16;
+    if (nb > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "hash table too large");
     db->n_buckets = (uint32_t)nb;
     db->max_key = 0;
     for (uint64_t i = 0; i < N; i++)
@@ -367,56 +444,67 @@ int db_build(hs_db *db, const uint64_t *hashes)
     for (uint64_t i = 0; i < N; i++)  // ascending order is part of the format; verify instead of trusting
         for (uint64_t e = db->offsets[i] + 1; e < db->offsets[i + 1]; e++)
             if (hashes[e] <= hashes[e - 1]) return fail(HS_EFORMAT, "sketch hashes are not strictly ascending");
+    if (db->seg_begin.empty()) { db->seg_begin = {0, N}; db->seg_s = {db->s}; }
+    if (db->seg_s.size() > 8) return fail(HS_EUNSUPPORTED, "more than 8 sketch files in one table");
 
+    DevBufs tmp;   // build scratch: released on every path out of here
     uint64_t *d_hashes = nullptr;
     uint32_t *d_flags = nullptr;
     unsigned long long *d_nd = nullptr;
-    CU(cudaMalloc((void **)&db->d_keys, nb * 32));
-    CU(cudaMalloc((void **)&db->d_vals, nb * 16));
+    // the handle owns what it was given so far: hs_db_free() releases it if a later step fails
+    CU(cudaMalloc((void **)&db->d_buckets, nb * kBucketWords * 8));
     CU(cudaMalloc((void **)&db->d_canon, std::max<uint64_t>(E, 1) * 4));
+    CU(cudaMalloc((void **)&db->d_next, std::max<uint64_t>(E, 1) * 4));
     CU(cudaMalloc((void **)&db->d_offsets, (N + 1) * 8));
     CU(cudaMalloc((void **)&db->d_lengths, std::max<uint64_t>(N, 1) * 8));
-    CU(cudaMalloc((void **)&d_hashes, std::max<uint64_t>(E, 1) * 8));
-    CU(cudaMalloc((void **)&d_flags, 2 * sizeof(uint32_t)));
-    CU(cudaMalloc((void **)&d_nd, sizeof(unsigned long long)));
-    db->device_bytes = nb * 48 + E * 4 + (N + 1) * 8 + N * 8;
-    CU(cudaMemset(db->d_keys, 0xFF, nb * 32));
-    CU(cudaMemset(db->d_vals, 0xFF, nb * 16));
+    CU(cudaMalloc((void **)&db->d_seg_begin, db->seg_begin.size() * 8));
+    CU(cudaMalloc((void **)&db->d_seg_s, db->seg_s.size() * 4));
+    CU(tmp.alloc(&d_hashes, E * 8));
+    CU(tmp.alloc(&d_flags, 2 * sizeof(uint32_t)));
+    CU(tmp.alloc(&d_nd, sizeof(unsigned long long)));
+    db->device_bytes = nb * kBucketWords * 8 + E * 8 + (N + 1) * 8 + N * 8;
+    CU(cudaMemset(db->d_next, 0xFF, std::max<uint64_t>(E, 1) * 4));   // kNoEntry = end of chain
     CU(cudaMemset(d_flags, 0xFF, sizeof(uint32_t)));      // [0] special = kNoEntry
     CU(cudaMemset(d_flags + 1, 0, sizeof(uint32_t)));     // [1] fail
     CU(cudaMemset(d_nd, 0, sizeof(unsigned long long)));
     if (E) CU(cudaMemcpy(d_hashes, hashes, E * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(db->d_offsets, db->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
     if (N) CU(cudaMemcpy(db->d_lengths, db->lengths.data(), N * 8, cudaMemcpyHostToDevice));
-    CU(launch_table_insert(db->d_keys, db->d_vals, db->n_buckets, d_hashes, E, d_flags, nullptr, d_flags + 1, 0));
+    CU(cudaMemcpy(db->d_seg_begin, db->seg_begin.data(), db->seg_begin.size() * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db->d_seg_s, db->seg_s.data(), db->seg_s.size() * 4, cudaMemcpyHostToDevice));
+    CU(launch_table_insert(db->d_buckets, db->n_buckets, d_hashes, E, d_flags, d_flags + 1, 0));
     uint32_t flags[2];
     CU(cudaMemcpy(flags, d_flags, sizeof flags, cudaMemcpyDeviceToHost));
     if (flags[1]) return fail(HS_ECUDA, "hash table build failed (table full)");
     db->special = flags[0];
     if (db->special != kNoEntry) db->max_key = ~0ull;
+    db->dense_max = db->max_key;
     {
-        // Bloom second level: worth it when the range test lets more than ~1 % of uniformly
-        // distributed query hashes through, and only while >= 8 bits per key still fit in ~64 MB
-        // (beyond that it would neither filter nor stay in L2).  HYMET_SCREEN_BLOOM=0/1 overrides.
+        // Second tier: worth it when the range test lets more than ~1 % of uniformly distributed query
+        // hashes through.  HYMET_SCREEN_BLOOM=0/1 overrides.
         const double pass = (double)db->max_key / 18446744073709551615.0;
-        uint64_t words = 1;
-        while (words * 64 < E * 12 && words < ((uint64_t)1 << 23)) words <<= 1;
-        bool want = pass > 0.01 && words * 64 >= E * 8;
-        if (const char *e = getenv("HYMET_SCREEN_BLOOM")) want = atoi(e) != 0 && E > 0;
+        FilterPlan plan = plan_filter(db, hashes);
+        bool want = pass > 0.01 && plan.bloom;
+        if (const char *e = getenv("HYMET_SCREEN_BLOOM")) {
+            want = atoi(e) != 0 && E > 0;
+            if (want && !plan.bloom) plan = FilterPlan{0, std::min<uint64_t>((uint64_t)1 << 24, std::max<uint64_t>(4096, E)), (double)E, true};
+        }
         if (want && E) {
-            CU(cudaMalloc((void **)&db->d_bloom, words * 8));
-            CU(cudaMemset(db->d_bloom, 0, words * 8));
+            uint64_t words = 4096;
+            while (words < plan.words) words <<= 1;
+            CU(cudaMalloc((void **)&db->d_bloom, words * 4));
+            CU(cudaMemset(db->d_bloom, 0, words * 4));
             db->bloom_mask = (uint32_t)(words - 1);
-            CU(launch_bloom_build(db->d_bloom, db->bloom_mask, d_hashes, E, 0));
-            db->device_bytes += words * 8;
+            db->dense_max = plan.dense_max;
+            db->bloom_keys = (uint64_t)plan.keys_above;
+            CU(launch_bloom_build(db->d_bloom, db->bloom_mask, db->dense_max, db->use64, d_hashes, E, 0));
+            db->device_bytes += words * 4;
         }
     }
-    CU(launch_table_canon(db->view(), d_hashes, E, db->d_canon, d_nd, 0));
+    CU(launch_table_canon(db->view(), d_hashes, E, db->d_canon, db->d_next, d_nd, 0));
     unsigned long long nd = 0;
     CU(cudaMemcpy(&nd, d_nd, sizeof nd, cudaMemcpyDeviceToHost));
     db->n_distinct = nd;
-    if (db->seg_begin.empty()) { db->seg_begin = {0, N}; db->seg_s = {db->s}; }
-    cudaFree(d_hashes); cudaFree(d_flags); cudaFree(d_nd);
     db->t_build = now_s() - t0;
     return HS_OK;
 }
@@ -427,7 +515,9 @@ void fill_info(const hs_db *db, hs_db_info_t *o)
     o->k = db->k; o->s = db->s; o->seed = db->seed; o->use64 = db->use64;
     o->n_refs = db->n_refs; o->n_entries = db->n_entries; o->n_distinct = db->n_distinct;
     o->n_buckets = db->n_buckets; o->max_key = db->max_key; o->device_bytes = db->device_bytes;
-    o->bloom_bytes = db->d_bloom ? ((uint64_t)db->bloom_mask + 1) * 8 : 0;
+    o->bloom_bytes = db->d_bloom ? ((uint64_t)db->bloom_mask + 1) * 4 : 0;
+    o->dense_max = db->d_bloom ? db->dense_max : db->max_key;
+    o->bloom_keys = db->bloom_keys;
     o->t_parse_s = db->t_parse; o->t_build_s = db->t_build;
 }
 
@@ -453,6 +543,8 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
     a.tile_begin = (uint32_t)tile_begin; a.n_tiles = (uint32_t)tile_end;
     a.do_count = count; a.do_filter = s->filter; a.do_mix = mix;
     a.tab = s->db->view(); a.counts = s->d_counts;
+    a.batch_bloom = s->batch_bloom;
+    if (count && s->sparse_enabled) a.sparse = SparseView{s->d_touched, s->touched_cap, s->d_sparse};
     const uint64_t launch_positions = (tile_end - tile_begin) * kTileWords * 32;
     a.mix = s->mix.view(mix ? s->mix.launch_cap(launch_positions) : ~0ull);
     a.stats = count ? s->d_stats : s->d_stats + ST_COUNT;  // re-offer passes must not double count
@@ -463,7 +555,7 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
     }
     auto &ev = s->ev_pool[s->ev_used++];
     CU(cudaEventRecord(ev.first, s->stream));
-    CU(launch_stream(a, g_sm, s->stream));
+    CU(launch_stream(a, s->db->sm, s->stream));
     CU(cudaEventRecord(ev.second, s->stream));
     s->st.n_launches++;
     if (mix) {
@@ -475,12 +567,27 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
     return HS_OK;
 }
 
+SparseView sparse_view(const hs_screen *s) { return SparseView{s->sparse_enabled ? s->d_touched : nullptr, s->touched_cap, s->d_sparse}; }
+
 int screen_zero(hs_screen *s)
 {
-    CU(cudaMemsetAsync(s->d_counts, 0, std::max<uint64_t>(s->db->n_entries, 1) * 4, s->stream));
+    CU(cudaEventRecord(s->rst0, s->stream));
+    if (s->sparse_enabled && s->touched_valid) {
+        // counts[] back to zero in O(touched); if the list overflowed on the device, the conditional
+        // dense clear does the work instead (both are enqueued, one of them returns at once)
+        CU(launch_sparse_reset(sparse_view(s), s->d_counts, s->db->sm, s->stream));
+        CU(launch_counts_clear_if_overflow(sparse_view(s), s->d_counts, s->db->n_entries, s->stream));
+    } else {
+        CU(cudaMemsetAsync(s->d_counts, 0, std::max<uint64_t>(s->db->n_entries, 1) * 4, s->stream));
+    }
+    CU(cudaMemsetAsync(s->d_sparse, 0, sizeof(SparseState), s->stream));
+    s->touched_valid = true;
+    s->mixture_on_device = false;
     CU(cudaMemsetAsync(s->d_stats, 0, 2 * ST_COUNT * sizeof(unsigned long long), s->stream));
     int rc = s->mix.reset(s->stream);
     if (rc) return rc;
+    CU(cudaEventRecord(s->rst1, s->stream));
+    s->rst_pending = true;
     s->mix.passes = 1;
     s->mixture.clear();
     s->flushed = false;
@@ -538,7 +645,7 @@ int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint
         if (M < m.s && tau != ~0ull) {
             // complete below tau but fewer than s distinct values there (very repetitive
             // input): raise tau and re-offer everything
-            const uint64_t nt = (tau > (~0ull >> 4)) ? ~0ull : (tau << 4);
+            const uint64_t nt = (tau > (~0ull >> 4)) ? ~0ull : (tau ? tau << 4 : 16);
             rc = m.reset(st, nt, false);
             if (rc) return rc;
             m.passes++;
@@ -757,9 +864,9 @@ HS_API int hs_db_ref(const hs_db *db, uint64_t i, const char **name, const char 
 HS_API void hs_db_free(hs_db *db)
 {
     if (!db) return;
-    if (g_device >= 0) cudaSetDevice(g_device);
-    cudaFree(db->d_keys); cudaFree(db->d_vals); cudaFree(db->d_canon); cudaFree(db->d_offsets); cudaFree(db->d_lengths);
-    cudaFree(db->d_bloom);
+    cudaSetDevice(db->device);
+    cudaFree(db->d_buckets); cudaFree(db->d_canon); cudaFree(db->d_next); cudaFree(db->d_offsets); cudaFree(db->d_lengths);
+    cudaFree(db->d_seg_begin); cudaFree(db->d_seg_s); cudaFree(db->d_bloom);
     delete db;
 }
 
@@ -769,16 +876,18 @@ HS_API void hs_db_free(hs_db *db)
 HS_API int hs_screen_new(hs_db *db, hs_screen **out)
 {
     if (!db || !out) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(db->device);
     auto *s = new hs_screen();
     s->db = db;
     const uint64_t N = std::max<uint64_t>(db->n_refs, 1), E = std::max<uint64_t>(db->n_entries, 1);
+    const uint64_t E4 = (E + 3) / 4 * 4;
     auto bail = [&](int rc) { hs_screen_free(s); return rc; };
 #define CUB(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(HS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); return bail(HS_ECUDA); } } while (0)
     CUB(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
     CUB(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-    CUB(cudaMalloc((void **)&s->d_counts, E * 4));
+    CUB(cudaMalloc((void **)&s->d_counts, E4 * 4));
+    CUB(cudaMemsetAsync(s->d_counts, 0, E4 * 4, s->stream));
     CUB(cudaMalloc((void **)&s->d_stats, 2 * ST_COUNT * sizeof(unsigned long long)));
     // the four result columns share one allocation (identity | p-value | shared | median) so that
     // they travel to the host in a single copy
@@ -786,15 +895,33 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
     s->d_pvalue = s->d_identity + N;
     s->d_shared = reinterpret_cast<uint32_t *>(s->d_pvalue + N);
     s->d_median = s->d_shared + N;
+    // sparse bookkeeping: room for one hash in eight to be present (a metagenome touches a small part
+    // of a RefSeq-sized table); beyond that the dense kernels take over
+    s->touched_cap = (uint32_t)std::min<uint64_t>(E, std::max<uint64_t>((uint64_t)1 << 22, E / 8));
+    s->pair_cap = (uint32_t)std::min<uint64_t>(E, std::max<uint64_t>((uint64_t)1 << 23, E / 4));
+    if (const char *e = getenv("HYMET_SCREEN_TOUCHED_CAP")) s->touched_cap = (uint32_t)std::max(1ll, atoll(e));   // tests: force the fallbacks
+    if (const char *e = getenv("HYMET_SCREEN_PAIR_CAP")) s->pair_cap = (uint32_t)std::max(1ll, atoll(e));
+    if (const char *e = getenv("HYMET_SCREEN_SPARSE")) s->sparse_enabled = atoi(e) != 0;
+    CUB(cudaMalloc((void **)&s->d_sparse, sizeof(SparseState)));
+    CUB(cudaMemsetAsync(s->d_sparse, 0, sizeof(SparseState), s->stream));
+    CUB(cudaHostAlloc((void **)&s->h_sparse, sizeof(SparseState), cudaHostAllocDefault));
+    CUB(cudaMalloc((void **)&s->d_touched, (size_t)s->touched_cap * 4));
+    CUB(cudaMalloc((void **)&s->d_depths, (size_t)s->pair_cap * 4));
+    CUB(cudaMalloc((void **)&s->d_hit, N * 16));   // hit | seg_start | seg_fill | plain
+    s->d_seg_start = s->d_hit + N; s->d_seg_fill = s->d_seg_start + N; s->d_plain = s->d_seg_fill + N;
     CUB(cudaEventCreate(&s->red0));
     CUB(cudaEventCreate(&s->red1));
     CUB(cudaEventCreate(&s->red2));
     CUB(cudaEventCreate(&s->red3));
+    CUB(cudaEventCreate(&s->rst0));
+    CUB(cudaEventCreate(&s->rst1));
     CUB(cudaHostAlloc((void **)&s->h_result, N * 24, cudaHostAllocDefault));
     CUB(cudaHostAlloc((void **)&s->h_stats, (ST_COUNT + 4) * sizeof(unsigned long long), cudaHostAllocDefault));
+    CUB(cudaHostAlloc((void **)&s->h_mixture, ((size_t)db->s + 1) * 8, cudaHostAllocDefault));
 #undef CUB
-    int rc = s->mix.init(db->s);
+    int rc = s->mix.init(db->s, db->use64);
     if (rc) return bail(rc);
+    s->touched_valid = false;   // nothing recorded yet and counts[] was just cleared: screen_zero need not walk a list
     rc = screen_zero(s);
     if (rc) return bail(rc);
     *out = s;
@@ -804,7 +931,7 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
 HS_API int hs_screen_set_stream(hs_screen *s, void *cuda_stream)
 {
     if (!s) return fail(HS_EINVAL, "null handle");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     CU(cudaStreamSynchronize(s->stream));
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     if (cuda_stream) {
@@ -828,6 +955,8 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "text_chunk_bytes")) s->text_chunk = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
     else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
+    else if (!strcmp(key, "batch_bloom")) s->batch_bloom = value != 0;
+    else if (!strcmp(key, "sparse")) { s->sparse_enabled = value != 0; s->touched_valid = false; }
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
     else return fail(HS_EINVAL, std::string("unknown option ") + key);
     return HS_OK;
@@ -899,7 +1028,7 @@ int feed_span_device(hs_screen *s, const char *text, size_t len, cudaEvent_t hos
     Ingest::Slot *sl = nullptr;
     {
         std::lock_guard<std::mutex> lk(s->mu);
-        int rc = in.ensure(len);
+        int rc = in.ensure(len, s->stream);
         if (rc) return rc;
     }
     int rc = in.slot_for(len, &sl);   // may wait for the GPU (outside the lock)
@@ -968,7 +1097,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     std::string err_all;
     std::mutex err_mu;
     auto worker = [&](int t) {
-        cudaSetDevice(g_device);
+        cudaSetDevice(s->db->device);
         int flip = 0;
         double my_ms = 4.0;  // how long this thread needs to pack one span
         for (;;) {
@@ -1021,7 +1150,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     // the device-ingest worker competes with the packer threads for spans: it costs no CPU
     // (one cudaMemcpyAsync + kernel launches per span) and is throttled by its raw-text slots
     auto device_worker = [&]() {
-        cudaSetDevice(g_device);
+        cudaSetDevice(s->db->device);
         // consecutive spans are contiguous text: take a few at a time so that the parser and
         // stream kernels run on >= 48 MB launches (fewer, fuller waves; fewer host wake-ups)
         const size_t batch = s->ingest_batch ? (size_t)s->ingest_batch : (threads > 0 ? 3 : 4);
@@ -1114,7 +1243,7 @@ int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
     std::string err_all;
     std::mutex err_mu;
     auto reader = [&](int t) {
-        cudaSetDevice(g_device);
+        cudaSetDevice(s->db->device);
         int flip = 0;
         auto bail = [&](int rc) {
             std::lock_guard<std::mutex> lk(err_mu);
@@ -1198,14 +1327,14 @@ int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
 HS_API int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads)
 {
     if (!s || (!text && n)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     return feed_text_impl(s, text, n, host_threads);
 }
 
 HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads)
 {
     if (!s || !path) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     // plain FASTA in a regular file: stream it through the pinned ring to the device parser
     if (s->ingest_mode != 0 && strcmp(path, "-") != 0) {
         const int fd = open(path, O_RDONLY);
@@ -1267,7 +1396,7 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
 HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases)
 {
     if (!s || ((!seq2 || !inv) && n_bases)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     std::lock_guard<std::mutex> lk(s->mu);
     s->st.n_bases += n_bases;
@@ -1277,7 +1406,7 @@ HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint3
 HS_API int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const void *d_inv, uint64_t n_bases)
 {
     if (!s || ((!d_seq2 || !d_inv) && n_bases)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     if (((uintptr_t)d_seq2 & 15) || ((uintptr_t)d_inv & 15)) return fail(HS_EINVAL, "packed device buffers must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(s->mu);
@@ -1290,7 +1419,7 @@ HS_API int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const 
 HS_API int hs_screen_flush(hs_screen *s)
 {
     if (!s) return fail(HS_EINVAL, "null handle");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     if (s->flushed) return HS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaEventRecord(s->red0, s->stream));
@@ -1325,6 +1454,11 @@ HS_API int hs_screen_flush(hs_screen *s)
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
     s->st.ms_reduce = ms;
+    if (s->rst_pending) {
+        CU(cudaEventElapsedTime(&ms, s->rst0, s->rst1));
+        s->st.ms_reset = ms;
+        s->rst_pending = false;
+    }
     s->flushed = true;
     return HS_OK;
 }
@@ -1334,41 +1468,58 @@ HS_API int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n)
     if (!s || !d_counts || !n) return fail(HS_EINVAL, "null argument");
     *d_counts = s->d_counts;
     *n = s->db->n_entries;
+    // whoever asks for the raw vector may add to it (the dense all-reduce): the record of which
+    // counts are non-zero no longer covers it, so reduction and reset take their dense forms
+    s->touched_valid = false;
     return HS_OK;
 }
 
 HS_API int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, uint32_t *n)
 {
     if (!s || !d_pairs || !n) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
     uint32_t *d_n = s->mix.field(offsetof(MixState, n_out));   // free scratch word once the mixture is settled
-    CU(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), s->stream));
-    CU(launch_counts_compact(s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, d_n, s->stream));
+    int rc = hs_screen_counts_compact_async(s, d_pairs, cap, d_n);
+    if (rc) return rc;
     CU(cudaMemcpyAsync(n, d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
-    s->st.n_launches++;
     return HS_OK;
 }
 
 HS_API int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t cap, void *d_n_out)
 {
     if (!s || !d_pairs || !d_n_out) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     // no flush needed: counts[] is final, in stream order, as soon as the last feed has been enqueued
     // (the mixture finaliser never touches it), so the exchange can start underneath hs_screen_flush
     CU(cudaMemsetAsync(d_n_out, 0, sizeof(uint32_t), s->stream));
-    CU(launch_counts_compact(s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, (uint32_t *)d_n_out, s->stream));
-    s->st.n_launches++;
+    SparseView sp = sparse_view(s);
+    if (!s->touched_valid) sp.touched = nullptr;
+    CU(launch_counts_compact(sp, s->d_counts, s->db->n_entries, (unsigned long long *)d_pairs, cap, (uint32_t *)d_n_out, s->stream));
+    s->st.n_launches += sp.touched ? 2 : 1;
     return HS_OK;
 }
 
 HS_API int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs)
 {
     if (!s || (!d_pairs && n_pairs)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
-    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
-    CU(launch_counts_scatter_add(s->d_counts, s->db->n_entries, (const unsigned long long *)d_pairs, n_pairs, s->stream));
+    ON_DEVICE(s->db->device);
+    SparseView sp = sparse_view(s);
+    if (!s->touched_valid) sp.touched = nullptr;
+    CU(launch_counts_scatter_add(sp, s->d_counts, s->db->n_entries, (const unsigned long long *)d_pairs, n_pairs, s->stream));
+    s->st.n_launches++;
+    return HS_OK;
+}
+
+HS_API int hs_screen_counts_absorb(hs_screen *s, const void *d_rows, uint32_t n_rows, uint32_t cap, uint32_t skip_row)
+{
+    if (!s || (!d_rows && n_rows)) return fail(HS_EINVAL, "null argument");
+    ON_DEVICE(s->db->device);
+    SparseView sp = sparse_view(s);
+    if (!s->touched_valid) sp.touched = nullptr;
+    CU(launch_counts_absorb(sp, s->d_counts, s->db->n_entries, (const unsigned long long *)d_rows, n_rows, cap, skip_row,
+                            s->db->sm, s->stream));
     s->st.n_launches++;
     return HS_OK;
 }
@@ -1379,6 +1530,45 @@ HS_API int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes, uint32_t *n)
     if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
     *n = (uint32_t)s->mixture.size();
     if (hashes) memcpy(hashes, s->mixture.data(), s->mixture.size() * 8);
+    return HS_OK;
+}
+
+HS_API int hs_screen_mixture_record(hs_screen *s, void *d_record)
+{
+    if (!s || !d_record) return fail(HS_EINVAL, "null argument");
+    ON_DEVICE(s->db->device);
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    // [length | s hashes, zero padded]: what every rank contributes to the mixture all-gather.  The
+    // settled local mixture is <= s values; it goes up from pinned memory on the screen's stream and
+    // the record stays on the device for the collective.
+    const size_t n = s->mixture.size(), words = (size_t)s->db->s + 1;
+    memset(s->h_mixture, 0, words * 8);
+    s->h_mixture[0] = n;
+    if (n) memcpy(s->h_mixture + 1, s->mixture.data(), n * 8);
+    CU(cudaMemcpyAsync(d_record, s->h_mixture, words * 8, cudaMemcpyHostToDevice, s->stream));
+    return HS_OK;
+}
+
+HS_API int hs_screen_mixture_merge_device(hs_screen *s, const void *d_rows, uint32_t n_rows)
+{
+    if (!s || !d_rows || !n_rows) return fail(HS_EINVAL, "null argument");
+    ON_DEVICE(s->db->device);
+    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    const uint32_t sc = s->db->s;
+    uint32_t need = 2;
+    while (need < (uint64_t)n_rows * sc) need <<= 1;
+    if (s->merge_cap < need) {
+        cudaFree(s->d_merge_work); cudaFree(s->d_merge_scratch); cudaFree(s->d_mixture);
+        s->d_merge_work = s->d_merge_scratch = s->d_mixture = nullptr;
+        CU(cudaMalloc((void **)&s->d_merge_work, (size_t)need * 8));
+        CU(cudaMalloc((void **)&s->d_merge_scratch, (size_t)need * 8));
+        CU(cudaMalloc((void **)&s->d_mixture, (size_t)std::max<uint32_t>(sc, 1) * 8));
+        s->merge_cap = need;
+    }
+    CU(launch_mixture_merge((const unsigned long long *)d_rows, n_rows, sc, sc, s->db->d_seg_s, (uint32_t)s->db->seg_s.size(),
+                            s->db->use64, s->d_merge_work, need, s->d_merge_scratch, s->d_mixture, s->d_sparse, s->stream));
+    s->st.n_launches += 3;
+    s->mixture_on_device = true;   // finish reads the set sizes from the device and brings the mixture back with the results
     return HS_OK;
 }
 
@@ -1413,34 +1603,32 @@ HS_API int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_
     return HS_OK;
 }
 
-HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *median, double *identity,
-                            double *pvalue, hs_stats_t *stats)
+namespace {
+
+// rows a11-a13 enqueued on the screen's stream: the O(present) kernels, or the dense ones
+int enqueue_reduce(hs_screen *s, bool wta, bool dense)
 {
-    if (!s) return fail(HS_EINVAL, "null handle");
-    NEED_DEVICE();
     hs_db *db = s->db;
     const uint64_t N = db->n_refs, E = db->n_entries;
-    // Single-GPU order: the per-sketch reduction needs only counts[], so it is enqueued BEFORE the
-    // mixture is settled and runs underneath the host round trips of that (flush); a caller that
-    // flushed first (multi-GPU: flush -> exchange -> finish) gets it here, after the exchange.
-    const bool early = !s->flushed;
-    if (early) {
-        CU(cudaEventRecord(s->red2, s->stream));
-        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
-        CU(cudaEventRecord(s->red3, s->stream));
-    }
-    int rc = hs_screen_flush(s);
-    if (rc) return rc;
-    if (early) {
-        float ems = 0;
-        CU(cudaEventElapsedTime(&ems, s->red2, s->red3));   // flush synchronised the stream
-        s->st.ms_reduce += ems;
-    }
-    CU(cudaEventRecord(s->red0, s->stream));
-    if (!early)
-        CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, g_sm, s->stream));
-    s->st.n_launches++;
     const size_t n_seg = db->seg_s.size();
+    if (!N) return HS_OK;
+    if (!dense) {
+        CU(cudaMemsetAsync(s->d_shared, 0, N * 8, s->stream));   // shared | median are adjacent
+        static_assert(offsetof(SparseState, overflow) == offsetof(SparseState, n_hit) + 8, "n_hit, n_pairs, overflow are cleared together");
+        CU(cudaMemsetAsync(&s->d_sparse->n_hit, 0, 3 * sizeof(uint32_t), s->stream));
+        SparseReduceArgs a;
+        memset(&a, 0, sizeof a);
+        a.sp = sparse_view(s);
+        a.counts = s->d_counts; a.next = db->d_next; a.offsets = db->d_offsets; a.n_refs = (uint32_t)N;
+        a.lengths = db->d_lengths; a.seg_begin = db->d_seg_begin; a.n_seg = (uint32_t)n_seg;
+        a.shared = s->d_shared; a.median = s->d_median; a.plain = s->d_plain; a.hit = s->d_hit;
+        a.seg_start = s->d_seg_start; a.seg_fill = s->d_seg_fill; a.depths = s->d_depths; a.pair_cap = s->pair_cap;
+        CU(launch_sparse_reduce(a, wta, db->sm, s->stream));
+        s->st.n_launches += wta ? 7 : 4;
+        return HS_OK;
+    }
+    CU(launch_sketch_reduce(db->d_offsets, N, db->d_canon, s->d_counts, nullptr, s->d_shared, s->d_median, db->sm, s->stream));
+    s->st.n_launches++;
     if (wta && E) {
         if (!s->d_winner) {
             CU(cudaMalloc((void **)&s->d_best_score, E * 8));
@@ -1451,33 +1639,103 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
             const uint64_t b = db->seg_begin[j], n = db->seg_begin[j + 1] - b;
             if (!n) continue;
             CU(launch_winner(db->d_offsets + b, n, db->d_canon, s->d_counts, s->d_shared + b, db->d_lengths + b,
-                             s->d_best_score, s->d_best_len, s->d_winner, E, g_sm, s->stream));
+                             s->d_best_score, s->d_best_len, s->d_winner, E, db->sm, s->stream));
             CU(launch_sketch_reduce(db->d_offsets + b, n, db->d_canon, s->d_counts, s->d_winner, s->d_shared + b,
-                                    s->d_median + b, g_sm, s->stream));
+                                    s->d_median + b, db->sm, s->stream));
             s->st.n_launches += 5;   // k_winner x4 (clear, score, length, index) + the reduction
         }
     }
-    for (size_t j = 0; j < n_seg; j++) {
+    return HS_OK;
+}
+
+// rows a14/a15 + the trip home: statistics per source file, the result columns, the sparse state
+int enqueue_stats_and_copy(hs_screen *s)
+{
+    hs_db *db = s->db;
+    const uint64_t N = db->n_refs;
+    for (size_t j = 0; j < db->seg_s.size(); j++) {
         const uint64_t b = db->seg_begin[j], n = db->seg_begin[j + 1] - b;
         if (!n) continue;
-        CU(launch_stats(db->k, set_size_of(s->mixture, db->use64, db->seg_s[j]), n, s->d_shared + b, nullptr,
+        CU(launch_stats(db->k, set_size_of(s->mixture, db->use64, db->seg_s[j]),
+                        s->mixture_on_device ? &s->d_sparse->set_size[j] : nullptr, n, s->d_shared + b, nullptr,
                         db->d_offsets + b, nullptr, s->d_identity + b, s->d_pvalue + b, s->stream));
         s->st.n_launches++;
     }
-    CU(cudaEventRecord(s->red1, s->stream));
     const uint64_t NA = std::max<uint64_t>(N, 1);   // layout of the allocation (hs_screen_new)
+    if (N) CU(cudaMemcpyAsync(s->h_result, s->d_identity, NA * 24, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(s->h_sparse, s->d_sparse, sizeof(SparseState), cudaMemcpyDeviceToHost, s->stream));
+    if (s->mixture_on_device && db->s)
+        CU(cudaMemcpyAsync(s->h_mixture, s->d_mixture, (size_t)db->s * 8, cudaMemcpyDeviceToHost, s->stream));
+    return HS_OK;
+}
+
+}  // namespace
+
+HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *median, double *identity,
+                            double *pvalue, hs_stats_t *stats)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    ON_DEVICE(s->db->device);
+    hs_db *db = s->db;
+    const uint64_t N = db->n_refs;
+    // Single-GPU order: the per-sketch reduction needs only counts[], so it is enqueued BEFORE the
+    // mixture is settled and runs underneath the host round trips of that (flush); a caller that
+    // flushed first (multi-GPU: flush -> exchange -> finish) gets it here, after the exchange.
+    const bool early = !s->flushed;
+    bool dense = !(s->sparse_enabled && s->touched_valid);
+    int rc;
+    if (early) {
+        CU(cudaEventRecord(s->red2, s->stream));
+        if ((rc = enqueue_reduce(s, wta != 0, dense)) != HS_OK) return rc;
+        CU(cudaEventRecord(s->red3, s->stream));
+    }
+    rc = hs_screen_flush(s);
+    if (rc) return rc;
+    if (early) {
+        float ems = 0;
+        CU(cudaEventElapsedTime(&ems, s->red2, s->red3));   // flush synchronised the stream
+        s->st.ms_reduce += ems;
+    }
+    CU(cudaEventRecord(s->red0, s->stream));
+    if (!early && (rc = enqueue_reduce(s, wta != 0, dense)) != HS_OK) return rc;
+    if ((rc = enqueue_stats_and_copy(s)) != HS_OK) return rc;
+    CU(cudaEventRecord(s->red1, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
+    s->st.ms_reduce += ms;
+    if (s->mixture_on_device) {   // the merged mixture and its set size arrive with the results
+        const uint32_t nm = std::min<uint32_t>(s->h_sparse->n_mix, db->s);
+        s->mixture.assign(s->h_mixture, s->h_mixture + nm);
+        s->st.n_mixture = nm;
+        s->st.set_size = s->h_sparse->set_size[0];
+    }
+    s->st.exchange_overflow = s->h_sparse->xchg_overflow;
+    s->st.exchange_max_pairs = s->h_sparse->xchg_max;
+    if (!dense && (s->h_sparse->n_touched > s->touched_cap || s->h_sparse->wrapped || s->h_sparse->overflow)) {
+        // the O(present) bookkeeping did not hold this query (more present hashes than its buffers, or a
+        // count that wrapped): the dense kernels give the answer, and the next reset clears every count
+        dense = true;
+        CU(cudaEventRecord(s->red0, s->stream));
+        if ((rc = enqueue_reduce(s, wta != 0, true)) != HS_OK) return rc;
+        if ((rc = enqueue_stats_and_copy(s)) != HS_OK) return rc;
+        CU(cudaEventRecord(s->red1, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
+        s->st.ms_reduce += ms;
+    }
+    s->st.reduce_path = dense ? 1u : 0u;
+    s->st.n_touched = s->h_sparse->n_touched;
+    s->st.n_hit_refs = dense ? 0u : s->h_sparse->n_hit;
+    s->st.n_pairs = dense ? 0u : s->h_sparse->n_pairs;
+    const uint64_t NA = std::max<uint64_t>(N, 1);
     double *h_id = reinterpret_cast<double *>(s->h_result), *h_pv = h_id + NA;
     uint32_t *h_sh = reinterpret_cast<uint32_t *>(h_pv + NA), *h_md = h_sh + NA;
-    if (N) CU(cudaMemcpyAsync(s->h_result, s->d_identity, NA * 24, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
     if (shared) for (uint64_t i = 0; i < N; i++) shared[i] = h_sh[i];
     if (median && N) memcpy(median, h_md, N * 4);
     if (identity && N) memcpy(identity, h_id, N * 8);
     if (pvalue && N) memcpy(pvalue, h_pv, N * 8);
     s->st.d2h_bytes += N * 24;
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
-    s->st.ms_reduce += ms;
     if (stats) *stats = s->st;
     return HS_OK;
 }
@@ -1485,7 +1743,7 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
 HS_API int hs_screen_reset(hs_screen *s)
 {
     if (!s) return fail(HS_EINVAL, "null handle");
-    NEED_DEVICE();
+    ON_DEVICE(s->db->device);
     CU(cudaStreamSynchronize(s->stream));
     return screen_zero(s);
 }
@@ -1500,9 +1758,15 @@ HS_API int hs_screen_stats(hs_screen *s, hs_stats_t *stats)
 HS_API void hs_screen_free(hs_screen *s)
 {
     if (!s) return;
-    if (g_device >= 0) cudaSetDevice(g_device);
+    if (s->db) cudaSetDevice(s->db->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_counts); cudaFree(s->d_stats);
+    cudaFree(s->d_sparse); cudaFree(s->d_touched); cudaFree(s->d_depths); cudaFree(s->d_hit);
+    cudaFree(s->d_mixture); cudaFree(s->d_merge_work); cudaFree(s->d_merge_scratch);
+    if (s->h_sparse) cudaFreeHost(s->h_sparse);
+    if (s->h_mixture) cudaFreeHost(s->h_mixture);
+    if (s->rst0) cudaEventDestroy(s->rst0);
+    if (s->rst1) cudaEventDestroy(s->rst1);
     cudaFree(s->d_identity);   // one block: identity | p-value | shared | median
     cudaFree(s->d_best_score); cudaFree(s->d_best_len); cudaFree(s->d_winner);
     s->mix.destroy();
@@ -1575,7 +1839,7 @@ HS_API int hs_pack_text_device(const char *text, size_t n, uint64_t *seq2, uint3
     if (!n) return HS_OK;
     const uint64_t alloc = hs_packed_words(n);
     Ingest in;
-    int rc = in.ensure(n);
+    int rc = in.ensure(n, 0);
     if (rc) return rc;
     uint8_t *raw = nullptr, *codes = nullptr;
     uint64_t *dseq = nullptr;
@@ -1606,7 +1870,7 @@ HS_API int hs_pack_text_device(const char *text, size_t n, uint64_t *seq2, uint3
 HS_API int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *out_entry)
 {
     if (!db || (!hashes && n) || (!out_entry && n)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(db->device);
     if (!n) return HS_OK;
     uint64_t *dh = nullptr;
     uint32_t *de = nullptr;
@@ -1616,7 +1880,7 @@ HS_API int hs_db_probe(hs_db *db, const uint64_t *hashes, uint64_t n, uint32_t *
     CU(cudaMalloc((void **)&dst, 2 * sizeof(unsigned long long)));
     CU(cudaMemset(dst, 0, 2 * sizeof(unsigned long long)));
     CU(cudaMemcpy(dh, hashes, n * 8, cudaMemcpyHostToDevice));
-    CU(launch_probe(db->view(), dh, n, de, dst, g_sm, 0));
+    CU(launch_probe(db->view(), dh, n, de, dst, db->sm, 0));
     CU(cudaMemcpy(out_entry, de, n * 4, cudaMemcpyDeviceToHost));
     cudaFree(dh); cudaFree(de); cudaFree(dst);
     return HS_OK;
@@ -1626,14 +1890,14 @@ HS_API int hs_db_probe_device(hs_db *db, const void *d_hashes, uint64_t n, uint6
                               float *ms)
 {
     if (!db || (!d_hashes && n)) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(db->device);
     unsigned long long *dst = nullptr, h[2] = {0, 0};
     cudaEvent_t e0, e1;
     CU(cudaMalloc((void **)&dst, 2 * sizeof(unsigned long long)));
     CU(cudaMemset(dst, 0, 2 * sizeof(unsigned long long)));
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, 0));
-    CU(launch_probe(db->view(), (const uint64_t *)d_hashes, n, nullptr, dst, g_sm, 0));
+    CU(launch_probe(db->view(), (const uint64_t *)d_hashes, n, nullptr, dst, db->sm, 0));
     CU(cudaEventRecord(e1, 0));
     CU(cudaEventSynchronize(e1));
     float t = 0;
@@ -1665,7 +1929,7 @@ HS_API int hs_gather_bench(const void *d_buf, uint64_t bytes, uint64_t n_reads, 
 HS_API int hs_db_entry_ids(hs_db *db, uint32_t *out)
 {
     if (!db || !out) return fail(HS_EINVAL, "null argument");
-    NEED_DEVICE();
+    ON_DEVICE(db->device);
     if (db->n_entries) CU(cudaMemcpy(out, db->d_canon, db->n_entries * 4, cudaMemcpyDeviceToHost));
     return HS_OK;
 }
@@ -1682,7 +1946,7 @@ HS_API int hs_stat_batch(uint32_t k, uint64_t set_size, uint64_t n, const uint64
     CU(cudaMalloc((void **)&di, n * 8)); CU(cudaMalloc((void **)&dp, n * 8));
     CU(cudaMemcpy(dx, shared, n * 8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(dn, size, n * 8, cudaMemcpyHostToDevice));
-    CU(launch_stats(k, set_size, n, nullptr, dx, nullptr, dn, di, dp, 0));
+    CU(launch_stats(k, set_size, nullptr, n, nullptr, dx, nullptr, dn, di, dp, 0));
     CU(cudaMemcpy(identity, di, n * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(pvalue, dp, n * 8, cudaMemcpyDeviceToHost));
     cudaFree(dx); cudaFree(dn); cudaFree(di); cudaFree(dp);
@@ -1698,10 +1962,10 @@ int sketch_device(uint32_t k, uint32_t s_, uint32_t seed, const uint64_t *dseq, 
     CU(cudaMalloc((void **)&dst, ST_COUNT * sizeof(unsigned long long)));
     CU(cudaMemset(dst, 0, ST_COUNT * sizeof(unsigned long long)));
     MixEngine mix;
-    int rc = mix.init(s_);
+    const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
+    int rc = mix.init(s_, use64);
     if (rc == HS_OK) rc = mix.reset(0);
     Chunk c{dseq, dinv, n_bases};
-    const bool use64 = pow(4.0, (double)k) > pow(2.0, 32.0);
     auto offer = [&]() -> int {
         StreamArgs a = base_args(c, k, seed, use64);
         a.do_mix = 1; a.mix = mix.view(mix.launch_cap(c.n_bases)); a.stats = dst;

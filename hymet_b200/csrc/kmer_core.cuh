@@ -375,11 +375,22 @@ HS_HD void for_each_kmer_in_word(uint64_t prev, uint64_t cur, uint32_t inv_prev,
 }
 
 // ---- sketch hash table ------------------------------------------------------
-// Buckets of four 8-byte keys (one 32-byte DRAM sector); kEmpty marks a free
-// slot.  Reference hashes are bottom-s values (numerically small) so the bucket
-// index re-mixes both halves before the multiply-high range reduction.
+// One bucket = one 128-byte line, the unit B200 moves between HBM and L2 whatever the
+// request size (round 1, ncu: 3.8 DRAM sectors per 32-byte bucket read):
+//   u64 word  0..9   keys (kEmptyKey = free)
+//   u32 word 20..29  canonical entry id of the key in the same slot
+//   u32 word 30      overflow flag: a key whose probe sequence passed this bucket lives further on
+//   u32 word 31      unused
+// so a probe is ONE line whether it hits or misses (round 1 kept the ids in a second array: a
+// second DRAM fetch per hit), a miss ends at the first bucket whose flag is clear, and ten slots
+// per bucket let the load factor be 0.6 (21 B per key; round 1: four slots at 1/3 = 36 B).
+// Reference hashes are bottom-s values (numerically small) so the bucket index re-mixes both
+// halves before the multiply-high range reduction.
 constexpr uint64_t kEmptyKey = ~0ull;
-constexpr int kBucketSlots = 4;
+constexpr int kBucketSlots = 10;
+constexpr int kBucketWords = 16;          // 64-bit words per bucket
+constexpr int kBucketValWord32 = 20;      // first id, as a 32-bit word index inside the bucket
+constexpr int kBucketOverWord32 = 30;
 
 HS_HD uint32_t bucket_of(uint64_t h, uint32_t n_buckets)
 {
@@ -394,12 +405,16 @@ HS_HD uint32_t bucket_of(uint64_t h, uint32_t n_buckets)
 #endif
 }
 
-// Blocked Bloom filter: which 64-bit word, and which 3 bits inside it, belong to hash h.
-HS_HD void bloom_slot(uint64_t h, uint32_t word_mask, uint32_t &word, unsigned long long &bits)
+// Blocked Bloom filter over the keys ABOVE the dense range (see TableView): which 32-bit word, and
+// which 3 bits inside it, belong to hash h.  A 64-bit MurmurHash3 value is already mixed, so its
+// bits are used as they are (18 position bits, then the word index); 32-bit hashes (k <= 16) are
+// re-mixed first.
+HS_HD void bloom_slot(uint64_t h, uint32_t word_mask, bool use64, uint32_t &word, uint32_t &bits)
 {
-    const uint64_t g = h * 0x9E3779B97F4A7C15ull;
-    word = (uint32_t)(g >> 34) & word_mask;
-    bits = (1ull << (g & 63)) | (1ull << ((g >> 6) & 63)) | (1ull << ((g >> 12) & 63));
+    const uint64_t g = use64 ? h : h * 0x9E3779B97F4A7C15ull;
+    const uint32_t lo = use64 ? (uint32_t)g : (uint32_t)(g >> 32);
+    word = (uint32_t)(g >> (use64 ? 15 : 8)) & word_mask;
+    bits = (1u << (lo & 31u)) | (1u << ((lo >> 5) & 31u)) | (1u << ((lo >> 10) & 31u));
 }
 
 HS_HD uint32_t mixset_slot(uint64_t h, uint32_t mask)

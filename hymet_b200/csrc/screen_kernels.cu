@@ -19,12 +19,15 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "kmer_core.cuh"
 #include "screen_kernels.h"
 
 namespace hs {
+
+constexpr int kMaxDevices = 64;
 
 // ---------------------------------------------------------------------------
 // PTX: mbarrier + bulk async copy global -> shared (TMA engine; SASS UBLKCP)
@@ -75,24 +78,62 @@ __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
 }
 
 // ---------------------------------------------------------------------------
-// table lookup (shared by k_stream, k_table_canon, k_probe)
+// table lookup, one thread per probe (k_stream's rare path, k_table_canon)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t table_find(const TableView &t, uint64_t h, uint32_t &n_reads)
+// LEAN: one 16-byte load at a time (two live registers instead of twenty) -- k_stream probes for
+// ~0.07 % of its k-mers and must not pay for the probe's registers in its hot loop; the later
+// loads of a bucket hit the line the first one brought in.  !LEAN: all six loads of a bucket in flight.
+template <bool LEAN>
+__device__ __forceinline__ uint32_t table_find_from(const TableView &t, uint64_t h, uint32_t b, uint32_t &n_reads)
 {
-    if (h == kEmptyKey) return t.special;
-    uint32_t b = bucket_of(h, t.n_buckets);
     for (uint32_t tries = 0; tries < t.n_buckets; tries++) {
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)b * kBucketSlots);
-        const ulonglong2 k01 = __ldg(p), k23 = __ldg(p + 1);  // one 32-byte sector
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)b * kBucketWords);
+        const uint32_t *p32 = reinterpret_cast<const uint32_t *>(p);
         n_reads++;
-        if (k01.x == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 0);
-        if (k01.y == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 1);
-        if (k23.x == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 2);
-        if (k23.y == h) return __ldg(t.vals + (size_t)b * kBucketSlots + 3);
-        if (k01.x == kEmptyKey || k01.y == kEmptyKey || k23.x == kEmptyKey || k23.y == kEmptyKey) return kNoEntry;
+        int slot = -1;
+        if (LEAN) {
+#pragma unroll 1
+            for (int i = 0; i < kBucketSlots / 2; i++) {
+                const ulonglong2 k = __ldg(p + i);
+                if (k.x == h) { slot = 2 * i; break; }
+                if (k.y == h) { slot = 2 * i + 1; break; }
+            }
+        } else {
+            ulonglong2 k[kBucketSlots / 2];
+#pragma unroll
+            for (int i = 0; i < kBucketSlots / 2; i++) k[i] = __ldg(p + i);
+#pragma unroll
+            for (int i = 0; i < kBucketSlots / 2; i++) {
+                if (k[i].x == h) slot = 2 * i;
+                if (k[i].y == h) slot = 2 * i + 1;
+            }
+        }
+        if (slot >= 0) return __ldg(p32 + kBucketValWord32 + slot);
+        if (!__ldg(p32 + kBucketOverWord32)) return kNoEntry;   // nothing that hashed here went further
         b = (b + 1 == t.n_buckets) ? 0u : b + 1;
     }
     return kNoEntry;
+}
+
+template <bool LEAN>
+__device__ __forceinline__ uint32_t table_find(const TableView &t, uint64_t h, uint32_t &n_reads)
+{
+    if (h == kEmptyKey) return t.special;
+    return table_find_from<LEAN>(t, h, bucket_of(h, t.n_buckets), n_reads);
+}
+
+// a count left zero: remember which one (SparseState), or note that it wrapped (S8)
+__device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts, uint32_t id, uint32_t add)
+{
+    const uint32_t old = atomicAdd(counts + id, add);
+    if (sp.touched) {
+        if (old == 0u) {
+            const uint32_t p = atomicAdd(&sp.st->n_touched, 1u);
+            if (p < sp.cap) sp.touched[p] = id;
+        } else if (old + add < old) {
+            atomicExch(&sp.st->wrapped, 1u);
+        }
+    }
 }
 
 __device__ __forceinline__ void mix_insert(const MixView &m, uint64_t *set, uint64_t h)
@@ -161,9 +202,12 @@ struct SmemPremul {
 #endif
 constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
 
-template <int KT, bool EMIT>
+// MODE: 0 = screen, 1 = K1 parity (emit every hash), 2 = screen with the Bloom reads of a group of
+// kIlp k-mers issued together (databases with keys above the dense range)
+template <int KT, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
+    constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2;
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
@@ -262,7 +306,7 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
         }
         if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
 
-        auto sink = [&](int j, uint64_t h) {
+        auto sink = [&](int j, uint64_t h, uint32_t bloom_word) {
             if (EMIT) {
                 a.emit_hash[pos0 + j] = h;
                 a.emit_valid[pos0 + j] = 1;
@@ -272,18 +316,18 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
                 mix_insert(a.mix, mix_set, h);
             }
             if (a.do_count && (!a.do_filter || h <= a.tab.max_key)) {
-                if (a.do_filter && a.tab.bloom) {  // L2-resident second-level filter (exact: no false negatives)
-                    uint32_t bw;
-                    unsigned long long bb;
-                    bloom_slot(h, a.tab.bloom_mask, bw, bb);
-                    if ((__ldg(a.tab.bloom + bw) & bb) != bb) return;
+                if (a.do_filter && a.tab.bloom && h > a.tab.dense_max) {  // second tier (exact: no false negatives)
+                    uint32_t bw, bb;
+                    bloom_slot(h, a.tab.bloom_mask, use64, bw, bb);
+                    if (!BLOOMB) bloom_word = __ldg(a.tab.bloom + bw);
+                    if ((bloom_word & bb) != bb) return;
                 }
                 n_probe++;
-                const uint32_t id = table_find(a.tab, h, n_reads);
+                const uint32_t id = table_find<true>(a.tab, h, n_reads);
                 if (id != kNoEntry) {
                     // warp-aggregated count: lanes that hit the same key add once
                     const uint32_t peers = __match_any_sync(__activemask(), id);
-                    if ((uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(a.counts + id, (uint32_t)__popc(peers));
+                    if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id, (uint32_t)__popc(peers));
                     n_hits++;
                 }
             }
@@ -310,10 +354,20 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
 #pragma unroll
                     for (int u = 0; u < kIlp; u++)
                         h[u] = hash_canonical_premul_top(canonical_top_half(fa, fb, fc, ra, rb, rc, q + u), k, a.seed, use64, L);
+                    uint32_t pre[kIlp];
+#pragma unroll
+                    for (int u = 0; u < kIlp; u++) {
+                        pre[u] = ~0u;
+                        if (BLOOMB) {   // all kIlp reads are issued before the first one is looked at
+                            uint32_t bw, bb;
+                            bloom_slot(h[u], a.tab.bloom_mask, use64, bw, bb);
+                            if (h[u] > a.tab.dense_max && h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
+                        }
+                    }
 #pragma unroll
                     for (int u = 0; u < kIlp; u++) {
                         const int j = half * 16 + q + u;
-                        if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u]);
+                        if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
                     }
                 }
             }
@@ -332,49 +386,76 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
     }
 }
 
-template <int KT, bool EMIT>
+template <int KT, int MODE>
 static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream_t st)
 {
-    static int occ = 0;
-    static uint32_t dyn = 2 * kLutBytes;
-    if (!occ) {
-        cudaError_t e;
-        // the tables need a 16 KB-aligned 32 KB window.  Dynamic shared memory starts right after the
-        // 1 KB the system reserves per CTA and the kernel's static buffers, so ask for exactly the
-        // distance to the next 16 KB boundary plus the tables (the kernel traps if that ever stops
-        // being true): 4 CTAs of 48 KB per SM instead of 3 with a full 16 KB of slack.
-        cudaFuncAttributes fa;
-        if ((e = cudaFuncGetAttributes(&fa, k_stream<KT, EMIT>)) != cudaSuccess) return e;
-        const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
-        dyn = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes;
-        if ((e = cudaFuncSetAttribute(k_stream<KT, EMIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_stream<KT, EMIT>, kCtaThreads, dyn);
-        if (e != cudaSuccess) return e;
-        if (occ < 1) occ = 1;
+    // per device: function attributes belong to the context, and one process may drive several GPUs
+    static std::mutex mu;
+    static int occ_dev[kMaxDevices] = {0};
+    static uint32_t dyn_dev[kMaxDevices] = {0};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    int occ;
+    uint32_t dyn;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!occ_dev[dev]) {
+            // the tables need a 16 KB-aligned 32 KB window.  Dynamic shared memory starts right after the
+            // 1 KB the system reserves per CTA and the kernel's static buffers, so ask for exactly the
+            // distance to the next 16 KB boundary plus the tables (the kernel traps if that ever stops
+            // being true): 4 CTAs of 48 KB per SM instead of 3 with a full 16 KB of slack.
+            cudaFuncAttributes fa;
+            if ((e = cudaFuncGetAttributes(&fa, k_stream<KT, MODE>)) != cudaSuccess) return e;
+            const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
+            const uint32_t d = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes;
+            if ((e = cudaFuncSetAttribute(k_stream<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d)) != cudaSuccess) return e;
+            int o = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_stream<KT, MODE>, kCtaThreads, d);
+            if (e != cudaSuccess) return e;
+            dyn_dev[dev] = d;
+            occ_dev[dev] = o < 1 ? 1 : o;
+        }
+        occ = occ_dev[dev];
+        dyn = dyn_dev[dev];
     }
     uint32_t grid = (uint32_t)sm_count * (uint32_t)occ;
     if (grid > a.n_tiles - a.tile_begin) grid = a.n_tiles - a.tile_begin;
     if (!grid) return cudaSuccess;
-    k_stream<KT, EMIT><<<grid, kCtaThreads, dyn, st>>>(a);
+    k_stream<KT, MODE><<<grid, kCtaThreads, dyn, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st)
 {
-    if (a.emit_hash) return launch_stream_t<0, true>(a, sm_count, st);   // parity runs: generic-k instantiation
+    if (a.emit_hash) return launch_stream_t<0, 1>(a, sm_count, st);   // parity runs: generic-k instantiation
+    if (a.batch_bloom && a.do_count && a.do_filter && a.tab.bloom) {
+        switch (a.k) {
+        case 21: return launch_stream_t<21, 2>(a, sm_count, st);
+        case 31: return launch_stream_t<31, 2>(a, sm_count, st);
+        default: return launch_stream_t<0, 2>(a, sm_count, st);
+        }
+    }
     switch (a.k) {
-    case 21: return launch_stream_t<21, false>(a, sm_count, st);
-    case 31: return launch_stream_t<31, false>(a, sm_count, st);
-    case 16: return launch_stream_t<16, false>(a, sm_count, st);
-    default: return launch_stream_t<0, false>(a, sm_count, st);
+    case 21: return launch_stream_t<21, 0>(a, sm_count, st);
+    case 31: return launch_stream_t<31, 0>(a, sm_count, st);
+    case 16: return launch_stream_t<16, 0>(a, sm_count, st);
+    default: return launch_stream_t<0, 0>(a, sm_count, st);
     }
 }
 
 // ---------------------------------------------------------------------------
 // Table build (row a5) and standalone probe (K2)
 // ---------------------------------------------------------------------------
-__global__ void k_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
-                               uint64_t n, uint32_t *special, uint32_t *fail)
+__global__ void k_table_init(uint64_t *buckets, uint64_t n_words)
+{   // keys and ids all-ones (free slot / identity of atomicMin), overflow flag + pad zero
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x)
+        buckets[w] = (w & (kBucketWords - 1)) == kBucketWords - 1 ? 0ull : ~0ull;
+}
+
+__global__ void k_table_insert(uint64_t *buckets, uint32_t n_buckets, const uint64_t *hashes, uint64_t n,
+                               uint32_t *special, uint32_t *fail)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t h = hashes[e];
@@ -382,109 +463,123 @@ __global__ void k_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_bucket
         uint32_t b = bucket_of(h, n_buckets);
         bool done = false;
         for (uint32_t tries = 0; tries < n_buckets && !done; tries++) {
-#pragma unroll
+            uint64_t *kb = buckets + (size_t)b * kBucketWords;
+            uint32_t *b32 = reinterpret_cast<uint32_t *>(kb);
+#pragma unroll 1
             for (int s = 0; s < kBucketSlots && !done; s++) {
-                const size_t slot = (size_t)b * kBucketSlots + s;
-                unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(keys + slot));
+                unsigned long long cur = __ldcg(reinterpret_cast<const unsigned long long *>(kb + s));
                 if (cur == kEmptyKey) {
-                    cur = atomicCAS(reinterpret_cast<unsigned long long *>(keys + slot), (unsigned long long)kEmptyKey,
+                    cur = atomicCAS(reinterpret_cast<unsigned long long *>(kb + s), (unsigned long long)kEmptyKey,
                                     (unsigned long long)h);
                     if (cur == kEmptyKey) cur = h;
                 }
                 if (cur == h) {
                     // canonical id of a key = smallest entry index holding it: identical on
                     // every GPU whatever the insertion order, so counts[] all-reduce cleanly
-                    atomicMin(vals + slot, (uint32_t)e);
+                    atomicMin(b32 + kBucketValWord32 + s, (uint32_t)e);
                     done = true;
                 }
             }
-            b = (b + 1 == n_buckets) ? 0u : b + 1;
+            if (!done) {   // full of other keys: this key moves on, and lookups must follow
+                atomicExch(b32 + kBucketOverWord32, 1u);
+                b = (b + 1 == n_buckets) ? 0u : b + 1;
+            }
         }
         if (!done) atomicExch(fail, 1u);
     }
 }
 
-__global__ void k_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n)
+__global__ void k_bloom_build(uint32_t *bloom, uint32_t bloom_mask, uint64_t dense_max, bool use64,
+                              const uint64_t *hashes, uint64_t n)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t w;
-        unsigned long long b;
-        bloom_slot(hashes[e], bloom_mask, w, b);
+        const uint64_t h = hashes[e];
+        if (h <= dense_max) continue;   // probed directly
+        uint32_t w, b;
+        bloom_slot(h, bloom_mask, use64, w, b);
         atomicOr(bloom + w, b);
     }
 }
 
-__global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_t n, uint32_t *canon,
+__global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_t n, uint32_t *canon, uint32_t *next,
                               unsigned long long *n_distinct)
 {
     uint32_t local = 0, dummy = 0;
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t id = table_find(t, hashes[e], dummy);
+        const uint32_t id = table_find<false>(t, hashes[e], dummy);
         canon[e] = id;
+        // the inverted index (hash -> references that hold it) as a chain through the
+        // entries: the canonical entry is the head, every other holder pushes itself behind it
+        if (id != (uint32_t)e) next[e] = atomicExch(next + id, (uint32_t)e);
         local += id == (uint32_t)e;
     }
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_distinct, (unsigned long long)local);
 }
 
-// K2 alone.  Four independent probes per thread: their eight 128-bit bucket loads are all
-// issued before the first compare, so a warp keeps 128 sectors in flight.
-constexpr int kProbeUnroll = 4;
+// K2 alone, warp-cooperative: eight lanes read one 128-byte bucket with one 16-byte load each (a
+// single coalesced line per probe), so a warp works on four probes at a time; four rounds of loads
+// are issued before the first compare (16 lines in flight per warp).  Lanes 0-4 of a group hold the
+// ten keys, lanes 5-7 the ids and the overflow flag.
 __global__ void __launch_bounds__(256) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
                                                uint32_t *out_entry, unsigned long long *stats)
 {
+    const uint32_t lane = threadIdx.x & 31u, g = lane & 7u, G = lane >> 3;
+    const uint32_t full = 0xffffffffu;
     uint32_t hits = 0, reads = 0;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x * kProbeUnroll;
-    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * kProbeUnroll; base < n; base += stride) {
-        uint64_t h[kProbeUnroll];
-        uint32_t b[kProbeUnroll];
-        ulonglong2 k01[kProbeUnroll], k23[kProbeUnroll];
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
+        const uint64_t mine = base + lane < n ? __ldg(hashes + base + lane) : kEmptyKey;
+#pragma unroll 1
+        for (int r0 = 0; r0 < 8; r0 += 4) {
+            uint64_t h[4];
+            uint32_t b[4];
+            ulonglong2 v[4];
 #pragma unroll
-        for (int u = 0; u < kProbeUnroll; u++) h[u] = base + u < n ? __ldg(hashes + base + u) : kEmptyKey;
+            for (int u = 0; u < 4; u++) {
+                h[u] = __shfl_sync(full, mine, (r0 + u) * 4 + (int)G);
+                b[u] = bucket_of(h[u], t.n_buckets);
+                v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)b[u] * kBucketWords) + g);
+            }
 #pragma unroll
-        for (int u = 0; u < kProbeUnroll; u++) {
-            b[u] = bucket_of(h[u], t.n_buckets);
-            const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)b[u] * kBucketSlots);
-            k01[u] = __ldg(p); k23[u] = __ldg(p + 1);
-        }
-#pragma unroll
-        for (int u = 0; u < kProbeUnroll; u++) {
-            if (base + u >= n) continue;
-            uint32_t id;
-            if (h[u] == kEmptyKey) {
-                id = t.special;
-            } else {
-                reads++;
-                const size_t v = (size_t)b[u] * kBucketSlots;
-                if (k01[u].x == h[u]) id = __ldg(t.vals + v);
-                else if (k01[u].y == h[u]) id = __ldg(t.vals + v + 1);
-                else if (k23[u].x == h[u]) id = __ldg(t.vals + v + 2);
-                else if (k23[u].y == h[u]) id = __ldg(t.vals + v + 3);
-                else if (k01[u].x == kEmptyKey || k01[u].y == kEmptyKey || k23[u].x == kEmptyKey || k23[u].y == kEmptyKey)
-                    id = kNoEntry;
-                else {  // bucket full of other keys: continue along the chain (rare at load 1/3)
-                    id = kNoEntry;
-                    uint32_t bb = (b[u] + 1 == t.n_buckets) ? 0u : b[u] + 1;
-                    for (uint32_t tries = 1; tries < t.n_buckets; tries++) {
-                        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(t.keys + (size_t)bb * kBucketSlots);
-                        const ulonglong2 a = __ldg(p), c = __ldg(p + 1);
+            for (int u = 0; u < 4; u++) {
+                const uint32_t src = (uint32_t)(r0 + u) * 4u + G;
+                const bool live = base + src < n;
+                int slot = -1;
+                if (g < 5u) {
+                    if (v[u].x == h[u]) slot = 2 * (int)g;
+                    else if (v[u].y == h[u]) slot = 2 * (int)g + 1;
+                }
+                const uint32_t m = (__ballot_sync(full, slot >= 0) >> (G * 8u)) & 0xFFu;
+                const int kl = m ? __ffs(m) - 1 : 0;
+                const uint32_t w32 = (uint32_t)kBucketValWord32 + (uint32_t)__shfl_sync(full, slot, (int)(G * 8u) + kl);
+                const uint32_t comp = w32 & 3u;
+                const uint32_t pick = comp == 0 ? (uint32_t)v[u].x : comp == 1 ? (uint32_t)(v[u].x >> 32)
+                                    : comp == 2 ? (uint32_t)v[u].y : (uint32_t)(v[u].y >> 32);
+                uint32_t id = __shfl_sync(full, pick, (int)(G * 8u + ((w32 >> 2) & 7u)));
+                const uint32_t over = __shfl_sync(full, (uint32_t)v[u].y, (int)(G * 8u) + 7);   // 32-bit word 30
+                if (g == 0u && live) {
+                    if (h[u] == kEmptyKey) {
+                        id = t.special;
+                    } else {
                         reads++;
-                        const size_t vv = (size_t)bb * kBucketSlots;
-                        if (a.x == h[u]) { id = __ldg(t.vals + vv); break; }
-                        if (a.y == h[u]) { id = __ldg(t.vals + vv + 1); break; }
-                        if (c.x == h[u]) { id = __ldg(t.vals + vv + 2); break; }
-                        if (c.y == h[u]) { id = __ldg(t.vals + vv + 3); break; }
-                        if (a.x == kEmptyKey || a.y == kEmptyKey || c.x == kEmptyKey || c.y == kEmptyKey) break;
-                        bb = (bb + 1 == t.n_buckets) ? 0u : bb + 1;
+                        if (!m) {
+                            id = kNoEntry;
+                            if (over) {   // rare (a few % of buckets at load 0.6): follow the chain alone
+                                const uint32_t nb = (b[u] + 1 == t.n_buckets) ? 0u : b[u] + 1;
+                                id = table_find_from<false>(t, h[u], nb, reads);
+                            }
+                        }
                     }
+                    if (out_entry) out_entry[base + src] = id;
+                    hits += id != kNoEntry;
                 }
             }
-            if (out_entry) out_entry[base + u] = id;
-            hits += id != kNoEntry;
         }
     }
     hits = warp_sum(hits); reads = warp_sum(reads);
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (hits) atomicAdd(stats + 0, (unsigned long long)hits);
         if (reads) atomicAdd(stats + 1, (unsigned long long)reads);
     }
@@ -530,29 +625,29 @@ static inline uint32_t grid_for(uint64_t n, int threads, uint32_t cap)
     return (uint32_t)g;
 }
 
-cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
-                                uint64_t n_entries, uint32_t *special, unsigned long long *, uint32_t *fail,
-                                cudaStream_t st)
+cudaError_t launch_table_insert(uint64_t *buckets, uint32_t n_buckets, const uint64_t *hashes, uint64_t n_entries,
+                                uint32_t *special, uint32_t *fail, cudaStream_t st)
 {
-    if (!n_entries) return cudaSuccess;
-    k_table_insert<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(keys, vals, n_buckets, hashes, n_entries,
-                                                                      special, fail);
+    const uint64_t words = (uint64_t)n_buckets * kBucketWords;
+    k_table_init<<<grid_for(words, 256, 148 * 32), 256, 0, st>>>(buckets, words);
+    if (!n_entries) return cudaGetLastError();
+    k_table_insert<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(buckets, n_buckets, hashes, n_entries, special, fail);
     return cudaGetLastError();
 }
 
-cudaError_t launch_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n,
-                               cudaStream_t st)
+cudaError_t launch_bloom_build(uint32_t *bloom, uint32_t bloom_mask, uint64_t dense_max, bool use64,
+                               const uint64_t *hashes, uint64_t n, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_bloom_build<<<grid_for(n, 256, 148 * 32), 256, 0, st>>>(bloom, bloom_mask, hashes, n);
+    k_bloom_build<<<grid_for(n, 256, 148 * 32), 256, 0, st>>>(bloom, bloom_mask, dense_max, use64, hashes, n);
     return cudaGetLastError();
 }
 
 cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint64_t n_entries, uint32_t *canon,
-                               unsigned long long *n_distinct, cudaStream_t st)
+                               uint32_t *next, unsigned long long *n_distinct, cudaStream_t st)
 {
     if (!n_entries) return cudaSuccess;
-    k_table_canon<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(t, hashes, n_entries, canon, n_distinct);
+    k_table_canon<<<grid_for(n_entries, 256, 148 * 32), 256, 0, st>>>(t, hashes, n_entries, canon, next, n_distinct);
     return cudaGetLastError();
 }
 
@@ -560,7 +655,7 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
                          unsigned long long *stats, int sm_count, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_probe<<<grid_for((n + kProbeUnroll - 1) / kProbeUnroll, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
+    k_probe<<<grid_for(n, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
     return cudaGetLastError();
 }
 
@@ -629,6 +724,19 @@ __global__ void k_mix_apply(const MixView v)
         st->tau = t;
     }
     st->new_count = 0;
+}
+
+__global__ void k_mix_state_init(MixState *st, unsigned long long tau)
+{
+    MixState z;
+    memset(&z, 0, sizeof z);
+    z.tau = tau;
+    *st = z;
+}
+cudaError_t launch_mix_state_init(MixState *st, uint64_t tau, cudaStream_t stm)
+{
+    k_mix_state_init<<<1, 1, 0, stm>>>(st, (unsigned long long)tau);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
@@ -942,11 +1050,13 @@ __device__ double binom_upper_tail_warp(uint64_t x, uint64_t n, double r, uint32
     return upper ? side : 1.0 - side;
 }
 
-__global__ void __launch_bounds__(256) k_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
-                                               const uint64_t *shared64, const uint64_t *offsets,
-                                               const uint64_t *sizes, double *identity, double *pvalue)
+__global__ void __launch_bounds__(256) k_stats(uint32_t k, uint64_t set_size, const unsigned long long *set_size_dev,
+                                               uint64_t n, const uint32_t *shared32, const uint64_t *shared64,
+                                               const uint64_t *offsets, const uint64_t *sizes, double *identity,
+                                               double *pvalue)
 {
     const uint32_t lane = threadIdx.x & 31u;
+    if (set_size_dev) set_size = __ldcg(set_size_dev);
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const double kmer_space = ldexp(1.0, 2 * (int)k);  // 4^k
     const double r = 1.0 / (1.0 + kmer_space / (double)set_size);
@@ -965,14 +1075,14 @@ __global__ void __launch_bounds__(256) k_stats(uint32_t k, uint64_t set_size, ui
     }
 }
 
-cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
-                         const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes,
-                         double *identity, double *pvalue, cudaStream_t st)
+cudaError_t launch_stats(uint32_t k, uint64_t set_size, const unsigned long long *set_size_dev, uint64_t n,
+                         const uint32_t *shared32, const uint64_t *shared64, const uint64_t *offsets,
+                         const uint64_t *sizes, double *identity, double *pvalue, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
     const uint64_t want = (n + 7) / 8;   // 8 warps per CTA, one sketch per warp and trip
-    k_stats<<<(uint32_t)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(k, set_size, n, shared32, shared64, offsets,
-                                                                          sizes, identity, pvalue);
+    k_stats<<<(uint32_t)(want < 148 * 32 ? want : 148 * 32), 256, 0, st>>>(k, set_size, set_size_dev, n, shared32, shared64,
+                                                                          offsets, sizes, identity, pvalue);
     return cudaGetLastError();
 }
 
@@ -1336,13 +1446,213 @@ cudaError_t launch_fasta_to_codes(const uint8_t *text, uint32_t n, uint8_t *code
 }
 
 // ---------------------------------------------------------------------------
-// Sparse form of the multi-GPU count exchange: counts[] is almost all zeros (only hashes
-// that occurred in this rank's shard), so ranks trade (entry id, count) pairs instead of
-// the dense vector when that is smaller.  Integer adds: order independent, exact.
+// O(present hashes) reduction: rows a11 ("Summing shared"), a12 (-w), a13 (medians)
+//
+// k_stream left the ids of the non-zero counts in touched[].  Per present key the chain
+// next[] lists the entries (hence references) that hold it.  Four small passes:
+//   count    shared[ref]++ per (key, holder)            (-w: only for the key's winner, S17)
+//   alloc    hand every reference with hits a segment of depths[]
+//   scatter  the same walk again, writing each key's count into its reference's segment
+//   median   one warp per reference with hits: radix selection of element shared/2 (S12)
+// Every kernel returns at once when the list is incomplete (overflow) or a count wrapped; the
+// host then reruns the dense O(stored hashes) kernels above.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs,
-                                                        uint32_t cap, uint32_t *n_out)
+__device__ __forceinline__ bool sparse_list(const SparseView &sp, uint32_t &n)
 {
+    n = __ldcg(&sp.st->n_touched);
+    return n <= sp.cap;
+}
+__device__ __forceinline__ bool sparse_ok(const SparseView &sp, uint32_t &n)
+{
+    return sparse_list(sp, n) && !__ldcg(&sp.st->wrapped);
+}
+
+// reference that owns entry e: the largest i with offsets[i] <= e (offsets[0] = 0 <= e < offsets[n_refs])
+__device__ __forceinline__ uint32_t ref_of_entry(const uint64_t *offsets, uint32_t n_refs, uint64_t e)
+{
+    uint32_t lo = 0, hi = n_refs;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= e) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// S17: among the holders of key t inside source file j, the one with the best (score, length, index);
+// score order == identity order (S13): identity is monotone in shared/size, and equal rationals give
+// equal doubles.  kNoEntry when file j does not hold the key.
+__device__ __forceinline__ uint32_t chain_winner(const SparseReduceArgs &a, uint32_t t, uint32_t j)
+{
+    const uint64_t lo = a.seg_begin[j], hi = a.seg_begin[j + 1];
+    unsigned long long best_s = 0, best_l = 0;
+    uint32_t best_i = kNoEntry;
+    for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) {
+        const uint32_t i = ref_of_entry(a.offsets, a.n_refs, e);
+        if (i < lo || i >= hi) continue;
+        const uint32_t sh = a.plain[i];
+        const uint64_t size = a.offsets[i + 1] - a.offsets[i];
+        const double jac = sh == size ? 1.0 : (double)sh / (double)size;
+        const unsigned long long sb = (unsigned long long)__double_as_longlong(jac), len = a.lengths[i];
+        if (best_i == kNoEntry || sb > best_s || (sb == best_s && (len > best_l || (len == best_l && i > best_i)))) {
+            best_s = sb; best_l = len; best_i = i;
+        }
+    }
+    return best_i;
+}
+
+template <bool WTA, bool SCATTER>
+__global__ void __launch_bounds__(256) k_sparse_walk(const SparseReduceArgs a)
+{
+    uint32_t n;
+    if (!sparse_ok(a.sp, n)) return;
+    auto visit = [&](uint32_t i, uint32_t c) {
+        if (SCATTER) {
+            const uint32_t pos = a.seg_start[i] + atomicAdd(a.seg_fill + i, 1u);
+            if (pos < a.pair_cap) a.depths[pos] = c;
+        } else {
+            const uint32_t old = atomicAdd(a.shared + i, 1u);
+            if (!WTA && old == 0u) a.hit[atomicAdd(&a.sp.st->n_hit, 1u)] = i;   // at most n_refs appends
+        }
+    };
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const uint32_t t = a.sp.touched[p];
+        const uint32_t c = __ldcg(a.counts + t);
+        if (!c) continue;
+        if (!WTA) {
+            for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) visit(ref_of_entry(a.offsets, a.n_refs, e), c);
+        } else {
+            for (uint32_t j = 0; j < a.n_seg; j++) {
+                const uint32_t w = chain_winner(a, t, j);
+                if (w != kNoEntry) visit(w, c);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sparse_zero_hit(const SparseReduceArgs a)
+{
+    uint32_t n;
+    if (!sparse_ok(a.sp, n)) return;
+    const uint32_t nh = __ldcg(&a.sp.st->n_hit);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nh; q += gridDim.x * blockDim.x) a.shared[a.hit[q]] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_sparse_alloc(const SparseReduceArgs a)
+{
+    uint32_t n;
+    if (!sparse_ok(a.sp, n)) return;
+    const uint32_t nh = __ldcg(&a.sp.st->n_hit);
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nh; q += gridDim.x * blockDim.x) {
+        const uint32_t i = a.hit[q], sh = a.shared[i];
+        const uint32_t start = atomicAdd(&a.sp.st->n_pairs, sh);   // sum of shared <= stored hashes < 2^32
+        a.seg_start[i] = start;
+        a.seg_fill[i] = 0;
+        if (start + sh > a.pair_cap) atomicExch(&a.sp.st->overflow, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sparse_median(const SparseReduceArgs a)
+{
+    uint32_t n;
+    if (!sparse_ok(a.sp, n) || __ldcg(&a.sp.st->overflow)) return;
+    const uint32_t nh = __ldcg(&a.sp.st->n_hit), lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = warp; q < nh; q += n_warps) {
+        const uint32_t i = a.hit[q], S = a.shared[i];
+        if (!S) continue;   // lost every key to a better reference (-w): median stays 0
+        const uint32_t *d = a.depths + a.seg_start[i];
+        uint32_t mx = 0;
+        for (uint32_t x = lane; x < S; x += 32) mx = max(mx, __ldcg(d + x));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        // S12: sorted_depths[S/2] by MSB-first radix selection (depths are the non-zero counts)
+        uint32_t kk = S / 2, prefix = 0;
+        for (int bit = 31 - __clz(mx); bit >= 0; bit--) {
+            const uint32_t himask = ~((2u << bit) - 1u);
+            uint32_t z = 0;
+            for (uint32_t x = lane; x < S; x += 32) {
+                const uint32_t c = __ldcg(d + x);
+                z += ((c & himask) == prefix) && !((c >> bit) & 1u);
+            }
+            z = warp_sum(z);
+            if (kk >= z) { kk -= z; prefix |= 1u << bit; }
+        }
+        if (lane == 0) a.median[i] = prefix;
+    }
+}
+
+cudaError_t launch_sparse_reduce(const SparseReduceArgs &a, bool wta, int sm_count, cudaStream_t st)
+{
+    if (!a.n_refs || !a.sp.touched) return cudaSuccess;
+    const uint32_t grid = (uint32_t)sm_count * 4u;
+    k_sparse_walk<false, false><<<grid, 256, 0, st>>>(a);
+    if (wta) {
+        cudaError_t e = cudaMemcpyAsync(a.plain, a.shared, (size_t)a.n_refs * 4, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+        k_sparse_zero_hit<<<grid, 256, 0, st>>>(a);
+        k_sparse_walk<true, false><<<grid, 256, 0, st>>>(a);
+    }
+    k_sparse_alloc<<<grid, 256, 0, st>>>(a);
+    if (wta) k_sparse_walk<true, true><<<grid, 256, 0, st>>>(a);
+    else k_sparse_walk<false, true><<<grid, 256, 0, st>>>(a);
+    k_sparse_median<<<grid, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+// counts[] back to zero in O(touched): only the recorded ids were ever non-zero
+__global__ void __launch_bounds__(256) k_sparse_reset(const SparseView sp, uint32_t *counts)
+{
+    uint32_t n;
+    if (!sparse_list(sp, n)) return;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) counts[sp.touched[p]] = 0;
+}
+
+// ... unless the list is incomplete: then every count is cleared
+__global__ void __launch_bounds__(256) k_counts_clear_if_overflow(const SparseView sp, uint4 *counts16, uint64_t n16)
+{
+    uint32_t n;
+    if (sparse_list(sp, n)) return;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x)
+        counts16[i] = make_uint4(0, 0, 0, 0);
+}
+
+cudaError_t launch_counts_clear_if_overflow(const SparseView &sp, uint32_t *counts, uint64_t n, cudaStream_t st)
+{
+    if (!n) return cudaSuccess;
+    // counts[] is a cudaMalloc allocation (256-byte aligned) padded to a multiple of four entries
+    const uint64_t n16 = (n + 3) / 4;
+    k_counts_clear_if_overflow<<<grid_for(n16, 256, 148 * 8), 256, 0, st>>>(sp, reinterpret_cast<uint4 *>(counts), n16);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sparse_reset(const SparseView &sp, uint32_t *counts, int sm_count, cudaStream_t st)
+{
+    k_sparse_reset<<<(uint32_t)sm_count * 4u, 256, 0, st>>>(sp, counts);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU count exchange: ranks trade (entry id, count) pairs of the hashes that occurred in
+// their shard instead of the dense vector.  Integer adds: order independent, exact.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_touched_pairs(const SparseView sp, const uint32_t *counts,
+                                                       unsigned long long *pairs, uint32_t cap, uint32_t *n_out)
+{
+    uint32_t n;
+    if (!sparse_list(sp, n)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = n;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n && p < cap; p += gridDim.x * blockDim.x) {
+        const uint32_t t = sp.touched[p];
+        pairs[p] = ((unsigned long long)t << 32) | __ldcg(counts + t);
+    }
+}
+
+// the touched list is missing or incomplete: scan every count
+__global__ void __launch_bounds__(256) k_counts_compact(const SparseView sp, const uint32_t *counts, uint64_t n,
+                                                        unsigned long long *pairs, uint32_t cap, uint32_t *n_out)
+{
+    uint32_t nt;
+    if (sp.touched && sparse_list(sp, nt)) return;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t c = counts[i];
         if (c) {
@@ -1352,29 +1662,122 @@ __global__ void __launch_bounds__(256) k_counts_compact(const uint32_t *counts, 
     }
 }
 
-__global__ void __launch_bounds__(256) k_counts_scatter_add(uint32_t *counts, uint64_t n_counts,
+__device__ __forceinline__ void add_pair(const SparseView &sp, uint32_t *counts, uint64_t n_counts, unsigned long long p)
+{
+    const uint64_t id = p >> 32;
+    const uint32_t c = (uint32_t)p;
+    if (id < n_counts && c) count_add(sp, counts, (uint32_t)id, c);   // padding carries id 0xFFFFFFFF
+}
+
+__global__ void __launch_bounds__(256) k_counts_scatter_add(const SparseView sp, uint32_t *counts, uint64_t n_counts,
                                                             const unsigned long long *pairs, uint64_t n_pairs)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned long long p = pairs[i];
-        const uint64_t id = p >> 32;
-        if (id < n_counts) atomicAdd(counts + id, (uint32_t)p);  // padding carries id 0xFFFFFFFF
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x)
+        add_pair(sp, counts, n_counts, pairs[i]);
+}
+
+__global__ void __launch_bounds__(256) k_counts_absorb(const SparseView sp, uint32_t *counts, uint64_t n_counts,
+                                                       const unsigned long long *rows, uint32_t n_rows, uint32_t cap,
+                                                       uint32_t skip)
+{
+    const size_t stride = (size_t)cap + 1;
+    uint32_t most = 0;
+    for (uint32_t r = 0; r < n_rows; r++) most = max(most, (uint32_t)__ldcg(rows + r * stride));
+    if (blockIdx.x == 0 && threadIdx.x == 0) sp.st->xchg_max = most;
+    if (most > cap) {   // some rank's record is incomplete: add nothing
+        if (blockIdx.x == 0 && threadIdx.x == 0) sp.st->xchg_overflow = 1u;
+        return;
+    }
+    const uint64_t total = (uint64_t)n_rows * cap;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(x / cap), i = (uint32_t)(x % cap);
+        if (r == skip || i >= (uint32_t)__ldcg(rows + r * stride)) continue;
+        add_pair(sp, counts, n_counts, __ldcg(rows + r * stride + 1 + i));
     }
 }
 
-cudaError_t launch_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs, uint32_t cap,
-                                  uint32_t *n_out, cudaStream_t st)
+cudaError_t launch_counts_compact(const SparseView &sp, const uint32_t *counts, uint64_t n, unsigned long long *pairs,
+                                  uint32_t cap, uint32_t *n_out, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_counts_compact<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(counts, n, pairs, cap, n_out);
+    if (sp.touched) k_touched_pairs<<<148 * 4, 256, 0, st>>>(sp, counts, pairs, cap, n_out);
+    k_counts_compact<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(sp, counts, n, pairs, cap, n_out);
     return cudaGetLastError();
 }
 
-cudaError_t launch_counts_scatter_add(uint32_t *counts, uint64_t n_counts, const unsigned long long *pairs,
-                                      uint64_t n_pairs, cudaStream_t st)
+cudaError_t launch_counts_scatter_add(const SparseView &sp, uint32_t *counts, uint64_t n_counts,
+                                      const unsigned long long *pairs, uint64_t n_pairs, cudaStream_t st)
 {
     if (!n_pairs) return cudaSuccess;
-    k_counts_scatter_add<<<grid_for(n_pairs, 256, 148 * 8), 256, 0, st>>>(counts, n_counts, pairs, n_pairs);
+    k_counts_scatter_add<<<grid_for(n_pairs, 256, 148 * 8), 256, 0, st>>>(sp, counts, n_counts, pairs, n_pairs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_counts_absorb(const SparseView &sp, uint32_t *counts, uint64_t n_counts,
+                                 const unsigned long long *rows, uint32_t n_rows, uint32_t cap, uint32_t skip,
+                                 int sm_count, cudaStream_t st)
+{
+    if (!n_rows || !cap) return cudaSuccess;
+    k_counts_absorb<<<(uint32_t)sm_count * 8u, 256, 0, st>>>(sp, counts, n_counts, rows, n_rows, cap, skip);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU mixture: union of the ranks' bottom-s lists, its s smallest, and S10 -- on the device,
+// so that the exchange needs no host round trip between the collectives and the reduction.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mixture_gather(const unsigned long long *rows, uint32_t n_rows, uint32_t s_cap,
+                                                        uint64_t *work, uint32_t work_cap, SparseState *st)
+{
+    // row r = [length | s_cap hashes]; the value 2^64-1 is a legal hash but also the sort's padding:
+    // it is set aside here (st->mix_has_max = seen) and appended again after the unique pass
+    const size_t stride = (size_t)s_cap + 1;
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < work_cap; x += gridDim.x * blockDim.x) {
+        uint64_t v = kEmptyKey;
+        if (x < n_rows * s_cap) {
+            const uint32_t r = x / s_cap, i = x % s_cap;
+            const uint32_t len = (uint32_t)min((unsigned long long)s_cap, rows[r * stride]);
+            if (i < len) {
+                v = rows[r * stride + 1 + i];
+                if (v == kEmptyKey) atomicExch(&st->mix_has_max, 1u);
+            }
+        }
+        work[x] = v;
+    }
+}
+
+__global__ void k_mixture_finish(const uint64_t *sorted, const uint32_t *n_unique, uint32_t s, const uint32_t *seg_s,
+                                 uint32_t n_seg, int use64, uint64_t *out, SparseState *st)
+{
+    uint32_t n = min(*n_unique, s);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = sorted[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (st->mix_has_max && n < s) out[n++] = kEmptyKey;
+        st->n_mix = n;
+        for (uint32_t j = 0; j < n_seg && j < 8u; j++) {
+            // S10: (uint64) (2^W * |M| / max(M)) in double, M = the seg_s[j] smallest
+            const uint32_t m = min(n, seg_s[j]);
+            unsigned long long v = 0;
+            if (m) {
+                const double est = ldexp(1.0, use64 ? 64 : 32) * (double)m / (double)out[m - 1];
+                v = est < 18446744073709551615.0 ? (unsigned long long)est : ~0ull;
+            }
+            st->set_size[j] = v;
+        }
+    }
+}
+
+cudaError_t launch_mixture_merge(const unsigned long long *rows, uint32_t n_rows, uint32_t s_cap, uint32_t s,
+                                 const uint32_t *seg_s, uint32_t n_seg, bool use64, uint64_t *work, uint32_t work_cap,
+                                 uint64_t *scratch, uint64_t *out, SparseState *st, cudaStream_t stm)
+{
+    if ((uint64_t)n_rows * s_cap > work_cap) return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(&st->mix_has_max, 0, sizeof(uint32_t), stm);
+    if (e != cudaSuccess) return e;
+    k_mixture_gather<<<grid_for(work_cap, 256, 148 * 4), 256, 0, stm>>>(rows, n_rows, s_cap, work, work_cap, st);
+    if ((e = launch_sort_unique(work, work_cap, scratch, &st->n_mix, stm)) != cudaSuccess) return e;
+    k_mixture_finish<<<1, 256, 0, stm>>>(work, &st->n_mix, s, seg_s, n_seg, use64 ? 1 : 0, out, st);
     return cudaGetLastError();
 }
 

@@ -16,17 +16,41 @@ constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
 enum StatSlot { ST_VALID = 0, ST_PROBES, ST_BUCKETS, ST_HITS, ST_MIXINS, ST_COUNT };
 
 struct TableView {
-    const uint64_t *keys;   // n_buckets * 4, kEmptyKey = free
-    const uint32_t *vals;   // n_buckets * 4, canonical entry id of the key
+    const uint64_t *buckets; // n_buckets * kBucketWords: keys | canonical entry ids | overflow flag (kmer_core.cuh)
     uint32_t n_buckets;
-    uint64_t max_key;       // largest stored key (range pre-filter)
+    uint64_t max_key;       // largest stored key (exact range pre-filter)
     uint32_t special;       // canonical entry id of key == kEmptyKey, or kNoEntry
-    // Second-level pre-filter for databases whose keys are spread over the whole hash range
-    // (sketches of tiny genomes keep ALL their k-mer hashes, so max_key ~ 2^64 and the range
-    // test stops helping): a blocked Bloom filter, one 64-bit word and 3 bits per key, sized to
-    // stay L2 resident.  No false negatives => results unchanged.  NULL when not built.
-    const unsigned long long *bloom;
+    // Two-tier pre-filter for databases whose keys are spread over the whole hash range (sketches
+    // of viral/plasmid-sized genomes keep ALL their k-mer hashes, so max_key ~ 2^64 and the range
+    // test alone stops helping).  Keys <= dense_max -- where the sketches of ordinary genomes
+    // live, a sliver of the hash range -- are probed directly; the keys above it are few and go
+    // through a blocked Bloom filter (32-bit blocks, 3 bits per key, L2 resident) first.  No false
+    // negatives => results unchanged.  bloom == NULL: every hash <= max_key is probed.
+    const uint32_t *bloom;
     uint32_t bloom_mask;    // words - 1 (power of two)
+    uint64_t dense_max;
+};
+
+// Per-screen record of WHICH counts are non-zero, so that everything after the streaming pass
+// (count exchange, "Summing shared", -w, medians, reset) is O(present hashes), as it is in mash
+// itself, not O(stored hashes).
+struct SparseState {
+    uint32_t n_touched;     // entry ids appended to touched[] (> cap: the list is incomplete)
+    uint32_t wrapped;       // a count passed 2^32 (S8 wraps): a zero may be a present key
+    uint32_t n_hit;         // references with shared > 0
+    uint32_t n_pairs;       // depth slots handed out
+    uint32_t overflow;      // a sparse buffer was too small -> the caller reruns the dense reduction
+    uint32_t xchg_overflow; // multi-GPU: some rank's record held more pairs than its capacity
+    uint32_t xchg_max;      // multi-GPU: the largest pair count among the ranks' records
+    uint32_t n_mix;         // merged mixture length (device-side merge)
+    uint32_t mix_has_max;   // the value 2^64-1 is in the merged mixture (it doubles as the sort padding)
+    uint32_t pad;
+    unsigned long long set_size[8];   // S10 per source file, when the mixture was merged on the device
+};
+struct SparseView {
+    uint32_t *touched;      // canonical entry ids whose count left zero, in arrival order
+    uint32_t cap;
+    SparseState *st;
 };
 
 // Mixture bottom-s state lives on the device so that streaming never waits for the host:
@@ -64,24 +88,28 @@ struct StreamArgs {
     int do_mix;             // offer hashes <= tau to the mixture set
     TableView tab;
     uint32_t *counts;       // per canonical entry id
+    SparseView sparse;      // touched == NULL: do not record
     MixView mix;
     unsigned long long *stats;  // ST_COUNT slots
     uint64_t *emit_hash;    // optional: per position hash (K1 parity), n_bases entries
     uint8_t *emit_valid;
+    int batch_bloom;        // use the instantiation that issues the Bloom reads of a group of k-mers together
 };
 
 // ---- streaming (K1+K2+K3 insert) -------------------------------------------
 cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st);
 
 // ---- database build (row a5) -------------------------------------------------
-cudaError_t launch_table_insert(uint64_t *keys, uint32_t *vals, uint32_t n_buckets, const uint64_t *hashes,
-                                uint64_t n_entries, uint32_t *special, unsigned long long *max_key,
-                                uint32_t *fail, cudaStream_t st);
+cudaError_t launch_table_insert(uint64_t *buckets, uint32_t n_buckets, const uint64_t *hashes,
+                                uint64_t n_entries, uint32_t *special, uint32_t *fail, cudaStream_t st);
+// canon[e] = canonical id of entry e's key; next[] links the entries that hold the same key into a
+// chain that starts at the canonical one (next[] must be filled with kNoEntry beforehand)
 cudaError_t launch_table_canon(const TableView &t, const uint64_t *hashes, uint64_t n_entries, uint32_t *canon,
-                               unsigned long long *n_distinct, cudaStream_t st);
-cudaError_t launch_bloom_build(unsigned long long *bloom, uint32_t bloom_mask, const uint64_t *hashes, uint64_t n,
-                               cudaStream_t st);
-// standalone probe (K2): out_entry may be NULL; stats[0]=hits, stats[1]=bucket reads
+                               uint32_t *next, unsigned long long *n_distinct, cudaStream_t st);
+cudaError_t launch_bloom_build(uint32_t *bloom, uint32_t bloom_mask, uint64_t dense_max, bool use64,
+                               const uint64_t *hashes, uint64_t n, cudaStream_t st);
+// standalone probe (K2), warp-cooperative: eight lanes read one 128-byte bucket.  out_entry may be
+// NULL; stats[0]=hits, stats[1]=bucket reads
 cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n, uint32_t *out_entry,
                          unsigned long long *stats, int sm_count, cudaStream_t st);
 
@@ -89,6 +117,8 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
 cudaError_t launch_gather_bench(const void *buf, uint64_t bytes, uint64_t total_reads, int sm_count, cudaStream_t st);
 
 // ---- mixture bottom-s (K3) ---------------------------------------------------
+// MixState := {tau, everything else 0} without a host buffer (no synchronisation to reuse one)
+cudaError_t launch_mix_state_init(MixState *st, uint64_t tau, cudaStream_t stm);
 // copy keys <= thr from the set into out (append with atomic cursor); counts all <= thr
 cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, uint64_t *out, uint32_t out_cap,
                                uint32_t *n_out, cudaStream_t st);
@@ -99,6 +129,7 @@ cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st);
 cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st);
 
 // ---- per-sketch reduction (K4), winner-take-all (K5), statistics (K6) ---------
+// DENSE forms (O(stored hashes)): the fallback when the touched list overflowed or counts wrapped
 cudaError_t launch_sketch_reduce(const uint64_t *offsets, uint64_t n_refs, const uint32_t *canon,
                                  const uint32_t *counts, const uint32_t *winner /*nullable*/, uint32_t *shared,
                                  uint32_t *median, int sm_count, cudaStream_t st);
@@ -106,15 +137,53 @@ cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32
                           const uint32_t *shared, const uint64_t *lengths, unsigned long long *best_score,
                           unsigned long long *best_len, uint32_t *winner, uint64_t n_entries, int sm_count,
                           cudaStream_t st);
-cudaError_t launch_stats(uint32_t k, uint64_t set_size, uint64_t n, const uint32_t *shared32,
-                         const uint64_t *shared64, const uint64_t *offsets, const uint64_t *sizes,
-                         double *identity, double *pvalue, cudaStream_t st);
+// set_size_dev != NULL: read S10's set size from device memory instead of the argument
+cudaError_t launch_stats(uint32_t k, uint64_t set_size, const unsigned long long *set_size_dev, uint64_t n,
+                         const uint32_t *shared32, const uint64_t *shared64, const uint64_t *offsets,
+                         const uint64_t *sizes, double *identity, double *pvalue, cudaStream_t st);
 
-// ---- sparse count exchange (multi-GPU) -------------------------------------------
-cudaError_t launch_counts_compact(const uint32_t *counts, uint64_t n, unsigned long long *pairs, uint32_t cap,
-                                  uint32_t *n_out, cudaStream_t st);
-cudaError_t launch_counts_scatter_add(uint32_t *counts, uint64_t n_counts, const unsigned long long *pairs,
-                                      uint64_t n_pairs, cudaStream_t st);
+// SPARSE forms (O(present hashes)), rows a11-a13: walk the touched list and, per present key, the
+// chain of references that hold it.
+struct SparseReduceArgs {
+    SparseView sp;
+    const uint32_t *counts, *next;
+    const uint64_t *offsets;       // n_refs + 1
+    uint32_t n_refs;
+    const uint64_t *lengths;       // S18, for -w ties
+    const uint64_t *seg_begin;     // n_seg + 1 reference indices: -w competes inside one source file
+    uint32_t n_seg;
+    uint32_t *shared, *median;     // n_refs each, zeroed by the caller
+    uint32_t *plain;               // n_refs: shared counts before -w (its scores)
+    uint32_t *hit;                 // n_refs: references with hits, arrival order
+    uint32_t *seg_start, *seg_fill;// n_refs each
+    uint32_t *depths;              // pair_cap
+    uint32_t pair_cap;
+};
+cudaError_t launch_sparse_reduce(const SparseReduceArgs &a, bool wta, int sm_count, cudaStream_t st);
+// counts[touched[i]] = 0 for the recorded ids; the second launch clears every count instead when the
+// list is incomplete (decided on the device: one of the two returns at once).  counts[] must be
+// allocated in multiples of four entries.
+cudaError_t launch_sparse_reset(const SparseView &sp, uint32_t *counts, int sm_count, cudaStream_t st);
+cudaError_t launch_counts_clear_if_overflow(const SparseView &sp, uint32_t *counts, uint64_t n, cudaStream_t st);
+
+// ---- count exchange (multi-GPU) -----------------------------------------------------
+// (entry id << 32 | count) pairs of the touched ids; *n_out = how many there are (may exceed cap:
+// then the pairs are incomplete).  Falls back, on the device, to scanning all counts when the
+// touched list itself overflowed.
+cudaError_t launch_counts_compact(const SparseView &sp, const uint32_t *counts, uint64_t n, unsigned long long *pairs,
+                                  uint32_t cap, uint32_t *n_out, cudaStream_t st);
+cudaError_t launch_counts_scatter_add(const SparseView &sp, uint32_t *counts, uint64_t n_counts,
+                                      const unsigned long long *pairs, uint64_t n_pairs, cudaStream_t st);
+// All ranks' records at once: rows of (1 + cap) words, word 0 = pair count; row `skip` is this
+// rank's own.  Nothing is added (and xchg_overflow is raised) if any row holds more than cap pairs.
+cudaError_t launch_counts_absorb(const SparseView &sp, uint32_t *counts, uint64_t n_counts,
+                                 const unsigned long long *rows, uint32_t n_rows, uint32_t cap, uint32_t skip,
+                                 int sm_count, cudaStream_t st);
+// Union of n_rows ascending hash lists (row = [length | s_cap hashes]) -> out[<= s] ascending distinct,
+// length in st->n_mix, and S10's set size for each of n_seg sketch sizes in st->set_size[]
+cudaError_t launch_mixture_merge(const unsigned long long *rows, uint32_t n_rows, uint32_t s_cap, uint32_t s,
+                                 const uint32_t *seg_s, uint32_t n_seg, bool use64, uint64_t *work, uint32_t work_cap,
+                                 uint64_t *scratch, uint64_t *out, SparseState *st, cudaStream_t stm);
 
 // ---- device-side packer (codes -> 2-bit words + invalid mask) -------------------
 cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t n_words_alloc,

@@ -97,28 +97,28 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
-# ---- the exchange record: [n_pairs | mixture length | <= s mixture hashes | up to cap (id << 32 | count) pairs] ----
-def record_header(mixture: np.ndarray, s: int) -> np.ndarray:
-    """First 2 + s int64 words of a rank's record (slot 0, the pair count, is filled in later)."""
-    h = np.zeros(2 + s, np.int64)
+# ---- the exchange records (layout shared with hs_screen_counts_absorb / hs_screen_mixture_merge_device) ----
+#   pair record     [n_pairs | up to cap (entry id << 32 | count) pairs]         1 + cap int64 words
+#   mixture record  [length  | s hashes, zero padded]                            1 + s int64 words
+def mixture_record(mixture: np.ndarray, s: int) -> np.ndarray:
+    """What hs_screen_mixture_record writes for a settled local mixture."""
+    h = np.zeros(1 + s, np.int64)
     n = len(mixture)
-    h[1] = n
+    h[0] = n
     if n:
-        h[2:2 + n] = np.asarray(mixture, np.uint64).view(np.int64)
+        h[1:1 + n] = np.asarray(mixture, np.uint64).view(np.int64)
     return h
 
 
-def parse_heads(heads: np.ndarray):
-    """heads[world, 2 + s] (int64) -> (pair count per rank, list of mixture arrays)."""
-    n_pairs = (heads[:, 0] & 0xFFFFFFFF).astype(np.int64)
-    mixtures = [heads[r, 2:2 + int(heads[r, 1])].view(np.uint64) for r in range(heads.shape[0])]
-    return n_pairs, mixtures
+def parse_mixture_rows(rows: np.ndarray):
+    """rows[world, 1 + s] (int64) -> list of per-rank mixture arrays."""
+    return [rows[r, 1:1 + int(rows[r, 0])].view(np.uint64) for r in range(rows.shape[0])]
 
 
 def next_cap(most: int, cap: int, n_entries: int) -> int:
     """Capacity (pairs) of the next record given the largest pair count just seen: the next power of
     two above 1.5 x that, never more than one pair per entry; unchanged unless this record
-    overflowed or the next one could be half the size.  Every rank computes it from the same heads."""
+    overflowed or the next one could be half the size.  Every rank computes it from the same numbers."""
     want = 4096
     while want < most + most // 2:
         want <<= 1
@@ -127,7 +127,7 @@ def next_cap(most: int, cap: int, n_entries: int) -> int:
 
 
 def pack_pairs(ids: np.ndarray, counts: np.ndarray) -> np.ndarray:
-    """What k_counts_compact writes: (entry id << 32) | count, as int64 words."""
+    """What the compaction kernel writes: (entry id << 32) | count, as int64 words."""
     return ((np.asarray(ids, np.uint64) << np.uint64(32)) | np.asarray(counts, np.uint64)).view(np.int64)
 
 
@@ -139,17 +139,22 @@ def unpack_pairs(pairs: np.ndarray):
 class DistributedScreen:
     """hs.Screen whose finish() first exchanges counts and mixture with the other ranks.
 
-    Default ("auto"): every rank compacts its non-zero (entry id, count) pairs on the device
-    (k_counts_compact) into a fixed-size record [pair count | up to `cap` pairs] -- sized from the
-    previous screen's pair counts, at most 2^20 pairs -- and an asynchronous all-gather of the records
-    starts BEFORE the mixture is settled (counts[] is final once the feeds are enqueued), so the
-    big collective runs underneath hs_screen_flush.  A second, tiny all-gather carries every rank's
-    <= s mixture hashes.  The host synchronises once, after both; each rank then merges the other
-    mixtures and scatter-adds the other ranks' pairs into its counts[].  A metagenome touches a
-    tiny part of a 50 000-genome table, so the pairs are a few MB where the dense vector is
-    hundreds.  If any rank has more than `cap` non-zero counts the exchange falls back to the north
-    star's single dense NCCL all-reduce of counts[E] (`exchange="dense"` forces it).  Both are
-    exact integer sums.
+    Default ("auto").  Once the last feed is enqueued counts[] is final in stream order, so each rank
+    turns its record of touched entries into (entry id, count) pairs -- O(present hashes), no scan of
+    the table-sized vector -- inside a fixed-size record [pair count | up to `cap` pairs] and starts an
+    ASYNCHRONOUS all-gather of the records; the mixture finaliser (hs_screen_flush) runs underneath
+    it.  Each rank then writes its <= s mixture hashes into a second, small record on the device,
+    all-gathers those, and enqueues two library calls that consume the gathered buffers where they
+    lie: hs_screen_mixture_merge_device (sort + unique + set size on the device) and
+    hs_screen_counts_absorb (ONE launch over all ranks' pairs).  The host never looks at the gathered
+    data: between the last feed and the result copy the only synchronisations are the mixture
+    finaliser's own and the final one of hs_screen_finish.
+
+    `cap` follows the previous screen (next_cap).  If any rank's record is too small the absorb
+    kernel adds nothing and says so in the stats that come back with the results; every rank sees the
+    same records, takes the same decision, and redoes the count exchange as the north star's single
+    dense NCCL all-reduce of counts[E] (`exchange="dense"` forces that path).  Both are exact
+    integer sums.
     """
 
     def __init__(self, db: hs.Database, device: int, exchange: str = "auto", **kw):
@@ -162,12 +167,13 @@ class DistributedScreen:
             kw["stream_ptr"] = self._tstream.cuda_stream
         self.scr = hs.Screen(db, **kw)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.exchange_mode = os.environ.get("HYMET_SCREEN_EXCHANGE", exchange)
         self.last_exchange = None
         self.cap = int(min(1 << 20, max(4096, int(db.n_entries) // 8)))
         if self.exchange_mode == "sparse":      # forced: room for every entry, never falls back
             self.cap = int(max(4096, db.n_entries))
-        self._rec = self._all = self._pin = self._hdr = self._hdr_all = None
+        self._rec = self._all = self._mix = self._mix_all = None
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
         return getattr(self.scr, name)
@@ -188,50 +194,43 @@ class DistributedScreen:
 
     def _exchange(self):
         dev = torch.device("cuda", self.device)
-        s, cap, me = self.db.s, self.cap, dist.get_rank()
+        s, cap = self.db.s, self.cap
         sparse = self.exchange_mode != "dense"
-        hdr = 2 + s
-        if self._hdr is None:
-            self._hdr = torch.zeros(hdr, dtype=torch.int64, device=dev)
-            self._hdr_all = torch.empty(self.world * hdr, dtype=torch.int64, device=dev)
-            self._pin = torch.zeros(hdr, dtype=torch.int64, pin_memory=True)
+        if self._mix is None:
+            self._mix = torch.zeros(1 + s, dtype=torch.int64, device=dev)
+            self._mix_all = torch.empty(self.world * (1 + s), dtype=torch.int64, device=dev)
         work = None
         if sparse:
             n_rec = 1 + cap                               # [pair count | pairs]
             if self._rec is None or self._rec.numel() != n_rec:
                 self._rec = torch.zeros(n_rec, dtype=torch.int64, device=dev)
                 self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
-            # counts[] is final once the feeds are enqueued: compact and start the big collective now,
-            # asynchronously, so that it runs underneath the mixture finaliser's host round trips
             self.scr.counts_compact_async(self._rec[1:].data_ptr(), cap, self._rec.data_ptr())
             work = dist.all_gather_into_tensor(self._all, self._rec, async_op=True)
-        self.scr.flush()
-        self._pin.copy_(torch.from_numpy(record_header(self.scr.mixture(), s)))
-        self._hdr.copy_(self._pin, non_blocking=True)
-        dist.all_gather_into_tensor(self._hdr_all, self._hdr)             # 8 x (2 + s) words
-        if work is not None:
-            work.wait()                                                   # stream-level wait, the host does not block
-        heads = self._hdr_all.view(self.world, hdr).cpu().numpy()         # the one host sync after the collectives
-        _, mixtures = parse_heads(heads)
-        for r in range(self.world):
-            if r != me and len(mixtures[r]):
-                self.scr.merge_mixture(mixtures[r])
+        self.scr.flush()                                  # host round trips of the mixture finaliser: the collective runs underneath
+        self.scr.mixture_record(self._mix.data_ptr())
+        dist.all_gather_into_tensor(self._mix_all, self._mix)             # world x (1 + s) words
+        self.scr.mixture_merge_device(self._mix_all.data_ptr(), self.world)
         if not sparse:
             return self._dense()
-        rows = self._all.view(self.world, 1 + cap)
-        n_pairs = (rows[:, 0].cpu().numpy() & 0xFFFFFFFF).astype(np.int64)
-        most = int(n_pairs.max())
-        if self.exchange_mode != "sparse":
-            # size the next record from what this one carried: the collective moves world x cap x 8
-            # bytes whatever is in them (every rank sees the same counts, so takes the same decision)
-            self.cap = next_cap(most, cap, self.db.n_entries)
-        if most > cap:                        # too many distinct hits for this record: dense all-reduce instead
-            return self._dense()
-        for r in range(self.world):
-            if r != me and int(n_pairs[r]):
-                self.scr.counts_scatter_add(rows[r, 1:].data_ptr(), int(n_pairs[r]))
+        work.wait()                                       # stream-level wait, the host does not block
+        self.scr.counts_absorb(self._all.data_ptr(), self.world, cap, self.rank)
+        self._cap_used = cap
         self.last_exchange = "sparse"
 
     def finish(self, wta: bool = False) -> hs.ScreenResult:
         self.exchange()
-        return self.scr.finish(wta)
+        res = self.scr.finish(wta)
+        if self.world > 1 and self.last_exchange == "sparse":
+            most = int(res.stats["exchange_max_pairs"])
+            if self.exchange_mode != "sparse":
+                # size the next record from what this one carried: the collective moves world x cap x 8
+                # bytes whatever is in them (every rank sees the same records, so takes the same decision)
+                self.cap = next_cap(most, self._cap_used, self.db.n_entries)
+            if res.stats["exchange_overflow"]:
+                # some rank had more distinct hits than its record holds: nothing was added; redo the
+                # count exchange densely and reduce again (the mixture is already merged)
+                with torch.cuda.stream(self._tstream):
+                    self._dense()
+                res = self.scr.finish(wta)
+        return res

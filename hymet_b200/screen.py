@@ -253,6 +253,17 @@ class Screen:
     def counts_scatter_add(self, d_pairs_ptr: int, n_pairs: int):
         check(_abi.load().hs_screen_counts_scatter_add(self._h, C.c_void_p(d_pairs_ptr), n_pairs))
 
+    def counts_absorb(self, d_rows_ptr: int, n_rows: int, cap: int, skip_row: int):
+        """All ranks' pair records (device memory, after the all-gather) added in one launch."""
+        check(_abi.load().hs_screen_counts_absorb(self._h, C.c_void_p(d_rows_ptr), n_rows, cap, skip_row))
+
+    def mixture_record(self, d_record_ptr: int):
+        """[length | s hashes] of the settled local mixture -> device memory ((s + 1) int64 words)."""
+        check(_abi.load().hs_screen_mixture_record(self._h, C.c_void_p(d_record_ptr)))
+
+    def mixture_merge_device(self, d_rows_ptr: int, n_rows: int):
+        check(_abi.load().hs_screen_mixture_merge_device(self._h, C.c_void_p(d_rows_ptr), n_rows))
+
     def mixture(self) -> np.ndarray:
         out = np.zeros(max(self.db.s, 1), np.uint64)
         n = C.c_uint32()

@@ -48,11 +48,14 @@ typedef struct {
     uint32_t k, s, seed, use64;   /* from the sketch file, never from the CLI (Appendix A) */
     uint64_t n_refs, n_entries;   /* N sketches, E stored hashes */
     uint64_t n_distinct;          /* D distinct hashes (device dbs only, else 0) */
-    uint64_t n_buckets;           /* hash-table buckets of 4 keys (device dbs only) */
+    uint64_t n_buckets;           /* hash-table buckets: 128-byte lines of 10 keys + their ids (device dbs only) */
     uint64_t max_key;             /* largest stored hash: exact range pre-filter */
     uint64_t device_bytes;        /* HBM held by the db */
-    uint64_t bloom_bytes;         /* size of the L2-resident Bloom second-level filter (0 = not built) */
+    uint64_t bloom_bytes;         /* size of the L2-resident Bloom second-tier filter (0 = not built) */
     double t_parse_s, t_build_s;  /* .msh parse / GPU table build, seconds */
+    uint64_t dense_max;           /* hashes <= dense_max are probed directly, (dense_max, max_key] go through the
+                                     Bloom tier first (== max_key when that tier was not built) */
+    uint64_t bloom_keys;          /* estimate of the stored hashes above dense_max */
 } hs_db_info_t;
 
 typedef struct {
@@ -71,13 +74,23 @@ typedef struct {
     uint32_t n_mix_passes;   /* hashing passes needed for the mixture set (1 unless re-thresholded) */
     float ms_stream;         /* device time of the k-mer/probe kernels (CUDA events) */
     float ms_reduce;         /* device time of mixture finalise + per-sketch reduction */
+    float ms_reset;          /* device time of the reset that preceded this screen (counts, mixture set) */
+    uint32_t reduce_path;    /* 0 = O(present hashes) kernels, 1 = dense O(stored hashes) kernels */
+    uint32_t n_touched;      /* distinct stored hashes present in the query (non-zero counts) */
+    uint32_t n_hit_refs;     /* references with shared > 0 (sparse path) */
+    uint32_t n_pairs;        /* (present hash, reference holding it) pairs walked (sparse path) */
+    uint32_t exchange_overflow; /* multi-GPU: a rank's pair record was too small, nothing was added
+                                   (hs_screen_counts_absorb): redo the exchange densely */
+    uint32_t exchange_max_pairs; /* multi-GPU: largest pair count among the ranks' records (sizes the next one) */
 } hs_stats_t;
 
 /* ---- library ------------------------------------------------------------ */
 const char *hs_version(void);
 const char *hs_last_error(void);
-/* Bind this thread/process to CUDA device `device` (ordinal).  Fails with HS_ENODEV
- * unless the device is compute capability 10.x. */
+/* Select CUDA device `device` (ordinal) for the handles created from now on and for the
+ * handle-less entry points.  Fails with HS_ENODEV unless the device is compute capability 10.x.
+ * A db and its screens stay on the device they were created on, so one process can drive
+ * several GPUs: hs_init(0), build db 0, hs_init(1), build db 1, ... */
 int hs_init(int device);
 /* Number of SMs of the bound device (148 on B200); 0 before hs_init. */
 int hs_sm_count(void);
@@ -118,7 +131,8 @@ int hs_screen_new(hs_db *db, hs_screen **out);
 /* Run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = library's own). */
 int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
 /* Options: "filter" 1/0 = skip probes for hashes above the db's largest key (exact;
- * default 1); "keep_query" 1/0 = keep packed chunks in HBM until finish (default 1,
+ * default 1); "batch_bloom" 1/0 = issue the Bloom-tier reads of four k-mers together (default 1);
+ * "sparse" 1/0 = O(present hashes) reduction and reset (default 1; 0 = always the dense kernels); "keep_query" 1/0 = keep packed chunks in HBM until finish (default 1,
  * needed if the mixture threshold must be revisited); "chunk_bases" = host packer
  * chunk size; "piece_bases" = positions per upload+launch piece of packed host feeds;
  * "ingest" 0/1/2 = host packer only / device parser only / both compete (default; packer
@@ -169,19 +183,36 @@ int hs_screen_counts_devptr(hs_screen *s, void **d_counts, uint64_t *n);
  * found, may exceed cap: then nothing useful was written), and add another rank's pairs into
  * counts[] (pairs whose id is >= n_entries are padding and ignored). */
 int hs_screen_counts_compact(hs_screen *s, void *d_pairs, uint32_t cap, uint32_t *n);
-/* Same compaction, enqueued on the screen's stream without waiting: the pair count goes to the
+/* (The pairs come from the screen's record of which counts left zero -- O(present hashes) -- or, when
+ * that record overflowed, from a scan of all counts.)
+ * Same compaction, enqueued on the screen's stream without waiting: the pair count goes to the
  * uint32 at d_n_out (device memory), so a whole exchange needs a single host synchronisation.
  * May be called before hs_screen_flush (after the last feed): counts[] no longer changes, and the
  * collective that carries the pairs can then run underneath the flush. */
 int hs_screen_counts_compact_async(hs_screen *s, void *d_pairs, uint32_t cap, void *d_n_out);
 int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_pairs);
+/* The whole exchange in one launch: d_rows = what an all-gather of every rank's record leaves in
+ * DEVICE memory, n_rows records of (1 + cap) 64-bit words each, word 0 = that rank's pair count, then
+ * its pairs; row `skip_row` (this rank's own) is not added.  If any record holds more than cap pairs
+ * nothing is added and hs_stats_t.exchange_overflow is set by the next hs_screen_finish -- every rank
+ * sees the same records, so every rank takes the same decision.  No host synchronisation. */
+int hs_screen_counts_absorb(hs_screen *s, const void *d_rows, uint32_t n_rows, uint32_t cap, uint32_t skip_row);
 int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);
+/* Mixture exchange without the host: write this rank's record [length | s hashes, zero padded]
+ * ((s + 1) 64-bit words, DEVICE memory) after flush; after the all-gather, merge n_rows such records
+ * on the device (sort + unique, keep the s smallest, S10's set size per source file).  hs_screen_finish
+ * then takes the set size from device memory and returns the merged mixture with the results. */
+int hs_screen_mixture_record(hs_screen *s, void *d_record);
+int hs_screen_mixture_merge_device(hs_screen *s, const void *d_rows, uint32_t n_rows);
 int hs_screen_mixture_merge(hs_screen *s, const uint64_t *hashes, uint32_t n);
 /* Set size (S10) used for the p-values of one file of a multi-file db (after flush). */
 int hs_screen_segment_set_size(hs_screen *s, uint32_t segment, uint64_t *set_size);
 
 /* rows a11-a15: shared, median multiplicity, identity, p-value for every sketch, in
- * sketch order.  winner_take_all = mash's -w (S17).  Arrays have n_refs elements. */
+ * sketch order.  winner_take_all = mash's -w (S17).  Arrays have n_refs elements.
+ * The work is O(hashes present in the query) -- the streaming kernel records which counts left
+ * zero, and every stored hash is chained to the references that hold it -- with the dense
+ * O(stored hashes) kernels as the fallback when that record overflows (hs_stats_t.reduce_path). */
 int hs_screen_finish(hs_screen *s, int winner_take_all, uint64_t *shared, uint32_t *median,
                      double *identity, double *pvalue, hs_stats_t *stats);
 /* Forget the query (counts, mixture, stats) so the handle can screen another one. */

@@ -47,9 +47,24 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _absorb_cpu(counts, rows, cap, skip):
+    """CPU stand-in for hs_screen_counts_absorb (k_counts_absorb): add every other rank's pairs, or
+    nothing at all when any record is incomplete.  Returns (overflow, largest pair count)."""
+    n_pairs = (rows[:, 0] & 0xFFFFFFFF).astype(np.int64)
+    most = int(n_pairs.max())
+    if most > cap:
+        return True, most
+    for rr in range(rows.shape[0]):
+        if rr != skip:
+            i2, c2 = hd.unpack_pairs(rows[rr, 1:1 + int(n_pairs[rr])])
+            np.add.at(counts, i2, c2)
+    return False, most
+
+
 def _record_worker(rank, world, port, q):
-    """The sparse exchange of hymet_b200.dist.DistributedScreen with CPU stand-ins for the two device
-    kernels (compaction, scatter-add): same record layout, same helpers, same capacity policy."""
+    """The exchange of hymet_b200.dist.DistributedScreen with CPU stand-ins for the device kernels
+    (pair compaction, absorb, mixture merge): same record layouts, same helpers, same capacity policy,
+    same fallback decision taken from the gathered records alone."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     r, w, _ = hd.init_from_env("gloo")
@@ -62,27 +77,23 @@ def _record_worker(rank, world, port, q):
     for step in range(3):
         counts = local.counts_per_entry.astype(np.uint32).copy()
         ids = np.nonzero(counts)[0]
-        rec = np.zeros(2 + s + cap, np.int64)
-        rec[:2 + s] = hd.record_header(local.mixture, s)
-        rec[0] = len(ids)                                               # k_counts_compact: count, then <= cap pairs
-        rec[2 + s:2 + s + min(cap, len(ids))] = hd.pack_pairs(ids[:cap], counts[ids[:cap]])
+        rec = np.zeros(1 + cap, np.int64)
+        rec[0] = len(ids)                                               # pair count, then <= cap pairs
+        rec[1:1 + min(cap, len(ids))] = hd.pack_pairs(ids[:cap], counts[ids[:cap]])
         out = torch.empty(w * len(rec), dtype=torch.int64)
-        dist.all_gather_into_tensor(out, torch.from_numpy(rec))
-        rows = out.numpy().reshape(w, len(rec))
-        n_pairs, mixtures = hd.parse_heads(rows[:, :2 + s])
-        merged = hd.merge_bottom_s(mixtures, s)
-        most = int(n_pairs.max())
+        work = dist.all_gather_into_tensor(out, torch.from_numpy(rec), async_op=True)
+        mrec = hd.mixture_record(local.mixture, s)
+        mout = torch.empty(w * len(mrec), dtype=torch.int64)
+        dist.all_gather_into_tensor(mout, torch.from_numpy(mrec))
+        merged = hd.merge_bottom_s(hd.parse_mixture_rows(mout.numpy().reshape(w, 1 + s)), s)
+        work.wait()
+        overflow, most = _absorb_cpu(counts, out.numpy().reshape(w, 1 + cap), cap, r)
         new_cap = hd.next_cap(most, cap, E)
-        if most > cap:
+        mode = "sparse"
+        if overflow:
             t = torch.from_numpy(counts.view(np.int32))
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             mode = "dense"
-        else:
-            for rr in range(w):
-                if rr != r:
-                    i2, c2 = hd.unpack_pairs(rows[rr, 2 + s:2 + s + int(n_pairs[rr])])
-                    np.add.at(counts, i2, c2)                                   # k_counts_scatter_add
-            mode = "sparse"
         log.append((mode, cap, counts.copy(), merged))
         cap = new_cap
     q.put((r, log))
@@ -125,8 +136,8 @@ def test_record_helpers():
     i2, c2 = hd.unpack_pairs(hd.pack_pairs(ids, cnt))
     assert i2.tolist() == ids.tolist() and c2.tolist() == cnt.tolist()
     mix = np.array([3, 2 ** 63 + 1], np.uint64)
-    n, m = hd.parse_heads(np.stack([hd.record_header(mix, 4), hd.record_header(np.zeros(0, np.uint64), 4)]))
-    assert m[0].tolist() == mix.tolist() and len(m[1]) == 0 and n.tolist() == [0, 0]
+    m = hd.parse_mixture_rows(np.stack([hd.mixture_record(mix, 4), hd.mixture_record(np.zeros(0, np.uint64), 4)]))
+    assert m[0].tolist() == mix.tolist() and len(m[1]) == 0
 
 
 @pytest.mark.timeout(120)

@@ -96,6 +96,8 @@ SIGNATURES = {
     "hs_screen_mixture_merge": (C.c_int, [C.c_void_p, u64p, C.c_uint32]),
     "hs_screen_segment_set_size": (C.c_int, [C.c_void_p, C.c_uint32, u64p]),
     "hs_screen_finish": (C.c_int, [C.c_void_p, C.c_int, u64p, u32p, f64p, f64p, C.POINTER(Stats)]),
+    "hs_screen_finish_hits": (C.c_int, [C.c_void_p, C.c_int, u32p, C.POINTER(Stats)]),
+    "hs_screen_hits_copy": (C.c_int, [C.c_void_p, C.c_uint32, u32p, u64p, u32p, f64p, f64p]),
     "hs_screen_reset": (C.c_int, [C.c_void_p]),
     "hs_screen_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "hs_screen_free": (None, [C.c_void_p]),

@@ -77,6 +77,7 @@ class LiteScreen:
     def __init__(self, db: LiteDb, probe_filter: bool = True):
         self.db = db
         self._cols = None
+        self._hits = None
         self._h = C.c_void_p()
         check(_abi.load().hs_screen_new(db._h, C.byref(self._h)))
         if not probe_filter:
@@ -95,23 +96,37 @@ class LiteScreen:
 
     def finish_lines(self, wta: bool, min_identity: float, max_pvalue: float, begin: int = 0, end: int = None) -> Iterator[str]:
         """Rows a11-a16: reduce (once), then the TSV lines of references [begin, end) in sketch order
-        (S15: keep iff (shared > 0 or -i < 0) and identity >= -i and p <= -v; numbers as C `%g`)."""
-        if self._cols is None:
-            n = max(self.db.n_refs, 1)
-            cols = ((C.c_uint64 * n)(), (C.c_uint32 * n)(), (C.c_double * n)(), (C.c_double * n)())
-            check(_abi.load().hs_screen_finish(self._h, int(wta), cols[0], cols[1], cols[2], cols[3], None))
-            self._cols = cols
-        shared, median, identity, pvalue = self._cols
-        all_rows = min_identity < 0.0
-        for i in range(begin, self.db.n_refs if end is None else end):
-            sh = shared[i]
-            if not sh and not all_rows:
+        (S15: keep iff (shared > 0 or -i < 0) and identity >= -i and p <= -v; numbers as C `%g`).
+        Unless -i < 0 asks for every reference, only the rows with shared > 0 ever leave the GPU."""
+        L = _abi.load()
+        end = self.db.n_refs if end is None else end
+        if min_identity < 0.0:
+            if self._cols is None:
+                n = max(self.db.n_refs, 1)
+                cols = ((C.c_uint64 * n)(), (C.c_uint32 * n)(), (C.c_double * n)(), (C.c_double * n)())
+                check(L.hs_screen_finish(self._h, int(wta), cols[0], cols[1], cols[2], cols[3], None))
+                self._cols = cols
+            shared, median, identity, pvalue = self._cols
+            rows = ((i, i) for i in range(begin, end))
+        else:
+            if self._hits is None:
+                n = C.c_uint32()
+                check(L.hs_screen_finish_hits(self._h, int(wta), C.byref(n), None))
+                h = max(n.value, 1)
+                hits = ((C.c_uint32 * h)(), (C.c_uint64 * h)(), (C.c_uint32 * h)(), (C.c_double * h)(), (C.c_double * h)(), n.value)
+                check(L.hs_screen_hits_copy(self._h, n.value, hits[0], hits[1], hits[2], hits[3], hits[4]))
+                self._hits = hits
+            ref, shared, median, identity, pvalue, n = self._hits
+            rows = ((q, ref[q]) for q in range(n) if begin <= ref[q] < end)
+        for q, i in rows:
+            sh = shared[q]
+            if not sh and min_identity >= 0.0:
                 continue
-            ident, p = identity[i], pvalue[i]
+            ident, p = identity[q], pvalue[q]
             if ident < min_identity or p > max_pvalue:
                 continue
             name, comment, _, size = self.db.ref(i)
-            yield "%s\t%d/%d\t%d\t%s\t%s\t%s\n" % ("%g" % ident, sh, size, median[i], "%g" % p, name, comment)
+            yield "%s\t%d/%d\t%d\t%s\t%s\t%s\n" % ("%g" % ident, sh, size, median[q], "%g" % p, name, comment)
 
 
 def screen_lines(db_path: str, inputs: List[str], threads: int, wta: bool, min_identity: float, max_pvalue: float,

@@ -213,6 +213,9 @@ struct MixEngine {
     MixState *d_state = nullptr;
     MixState *h_state = nullptr;  // pinned mirror, valid after sync_state()
     uint64_t *d_cand = nullptr, *d_scratch = nullptr;
+    uint32_t *d_hist = nullptr;   // device-side selection: 2048 bins
+    uint32_t sel_pad = 0;         // its sort capacity (power of two >= s + slack, <= cand_cap)
+    bool fast_select = true;
     uint64_t *h_cand = nullptr;   // pinned: the settled mixture travels with the state, one sync for both
     bool auto_tau = true;  // first pass: cap tau per launch so expected offers stay <= cap/8
     uint32_t passes = 1;
@@ -230,13 +233,18 @@ struct MixEngine {
         CU(cudaHostAlloc((void **)&h_state, sizeof(MixState), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
         CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
+        CU(cudaMalloc((void **)&d_hist, 2048 * sizeof(uint32_t)));
+        sel_pad = 2048;
+        while (sel_pad < s + 1024) sel_pad <<= 1;
+        if (sel_pad > cand_cap) sel_pad = cand_cap;
+        if (const char *e = getenv("HYMET_SCREEN_FAST_SELECT")) fast_select = atoi(e) != 0;
         CU(cudaHostAlloc((void **)&h_cand, (size_t)s * 8, cudaHostAllocDefault));
         return HS_OK;
     }
     void destroy()
     {
         for (int i = 0; i < 2; i++) cudaFree(d_set[i]);
-        cudaFree(d_state); cudaFree(d_cand); cudaFree(d_scratch);
+        cudaFree(d_state); cudaFree(d_cand); cudaFree(d_scratch); cudaFree(d_hist);
         if (h_state) cudaFreeHost(h_state);
         if (h_cand) cudaFreeHost(h_cand);
     }
@@ -362,6 +370,10 @@ struct hs_screen {
     bool mixture_on_device = false;
     cudaEvent_t rst0 = nullptr, rst1 = nullptr;
     bool rst_pending = false;
+    // result rows of the references with hits (hs_screen_finish_hits): pinned, host-mapped, written by the GPU
+    char *h_rows = nullptr;
+    HitRows rows_host{}, rows_dev{};
+    std::vector<uint32_t> hit_order;   // indices into the rows, ascending by reference, shared > 0 only
     MixEngine mix;
     std::vector<uint64_t> mixture;  // settled s smallest distinct hashes, ascending
     bool flushed = false;
@@ -374,7 +386,7 @@ struct hs_screen {
     std::vector<Staging> staging;
     std::mutex mu;  // serialises arena + launches when packer threads feed concurrently
     bool filter = true;
-    int batch_bloom = 1;
+    int batch_bloom = 1, coop_probe = 1;
     uint64_t chunk_text = (uint64_t)16 << 20;
     hs_stats_t st;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -434,7 +446,7 @@ int db_build(hs_db *db, const uint64_t *hashes)
     if (E > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "more than 2^32 stored hashes");
     if (N > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "more than 2^32 references");
     if (db->k == 0 || db->k > 32) return fail(HS_EUNSUPPORTED, "k-mer size must be 1..32");
-    uint64_t nb = (E + 5) / 6 + 1;  // 10 slots per bucket -> load factor <= 0.6
+    uint64_t nb = (E + 4) / 5 + 1;  // 10 slots per bucket -> load factor <= 0.5: 1.4 % of the buckets overflow (0.6: 4.3 %)
     if (nb < 16) nb = 16;
     if (nb > 0xFFFFFFF0ull) return fail(HS_EUNSUPPORTED, "hash table too large");
     db->n_buckets = (uint32_t)nb;
@@ -544,6 +556,10 @@ int launch_chunk(hs_screen *s, const Chunk &c, bool count, bool mix, uint64_t ti
     a.do_count = count; a.do_filter = s->filter; a.do_mix = mix;
     a.tab = s->db->view(); a.counts = s->d_counts;
     a.batch_bloom = s->batch_bloom;
+    // the range test removes probes only when the keys are confined to a sliver of the hash range; a db
+    // whose keys cover a quarter of it or more and has no Bloom tier probes for most k-mers: that is
+    // the warp-cooperative kernel's job, as is "filter" = 0
+    a.probe_all = s->coop_probe && (!s->filter || (!s->db->d_bloom && s->db->max_key >= ((uint64_t)1 << 62)));
     if (count && s->sparse_enabled) a.sparse = SparseView{s->d_touched, s->touched_cap, s->d_sparse};
     const uint64_t launch_positions = (tile_end - tile_begin) * kTileWords * 32;
     a.mix = s->mix.view(mix ? s->mix.launch_cap(launch_positions) : ~0ull);
@@ -608,6 +624,24 @@ int screen_zero(hs_screen *s)
 template <class Rehash>
 int mix_finalize(MixEngine &m, cudaStream_t st, std::vector<uint64_t> &out, uint32_t &n_launches, Rehash &&rehash)
 {
+    if (m.fast_select) {
+        // Common case in ONE synchronisation: the device picks the threshold (histogram of the live set),
+        // collects, sorts and dedups; state and the s smallest come back together.  Anything unusual --
+        // the set overflowed, fewer than s values below tau, a crowded histogram bin -- is left to the
+        // iterative path below, which starts from the same device state.
+        CU(launch_mix_select(m.view(~0ull), m.s, m.use64, m.d_hist, m.d_cand, m.sel_pad, m.d_scratch, st));
+        n_launches += 4;
+        CU(cudaMemcpyAsync(m.h_cand, m.d_cand, (size_t)m.s * 8, cudaMemcpyDeviceToHost, st));
+        int rc = m.sync_state(st);
+        if (rc) return rc;
+        const MixState &hs_ = *m.h_state;
+        if (!hs_.overflow && !hs_.sel_too_many && hs_.n_out <= m.sel_pad && (hs_.n_unique >= m.s || hs_.tau == ~0ull)) {
+            const uint32_t nu = std::min(hs_.n_unique, m.s);
+            out.assign(m.h_cand, m.h_cand + nu);
+            if (hs_.has_max && out.size() < m.s) out.push_back(~0ull);  // hash == 2^64-1 present
+            return HS_OK;
+        }
+    }
     for (int round = 0; round < 40; round++) {
         int rc = m.sync_state(st);
         if (rc) return rc;
@@ -956,6 +990,7 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
     else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "batch_bloom")) s->batch_bloom = value != 0;
+    else if (!strcmp(key, "coop_probe")) s->coop_probe = value != 0;
     else if (!strcmp(key, "sparse")) { s->sparse_enabled = value != 0; s->touched_valid = false; }
     else if (!strcmp(key, "keep_query")) { if (!value) return fail(HS_EUNSUPPORTED, "keep_query=0 is not implemented: chunks stay resident until reset"); }
     else return fail(HS_EINVAL, std::string("unknown option ") + key);
@@ -1671,13 +1706,50 @@ int enqueue_stats_and_copy(hs_screen *s)
 
 }  // namespace
 
-HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *median, double *identity,
-                            double *pvalue, hs_stats_t *stats)
+namespace {
+
+// rows a14-a16 for the references with hits only, written by the GPU into host-mapped rows
+int enqueue_hits(hs_screen *s, bool dense)
 {
-    if (!s) return fail(HS_EINVAL, "null handle");
-    ON_DEVICE(s->db->device);
     hs_db *db = s->db;
     const uint64_t N = db->n_refs;
+    if (N && !s->h_rows) {
+        const size_t n3 = (N * 12 + 7) & ~(size_t)7;
+        CU(cudaHostAlloc((void **)&s->h_rows, n3 + N * 16, cudaHostAllocMapped));
+        char *d = nullptr;
+        CU(cudaHostGetDevicePointer((void **)&d, s->h_rows, 0));
+        auto lay = [&](char *base) {
+            HitRows r;
+            r.ref = reinterpret_cast<uint32_t *>(base); r.shared = r.ref + N; r.median = r.shared + N;
+            r.identity = reinterpret_cast<double *>(base + n3); r.pvalue = r.identity + N;
+            r.cap = (uint32_t)N;
+            return r;
+        };
+        s->rows_host = lay(s->h_rows);
+        s->rows_dev = lay(d);
+    }
+    if (N) {
+        StatsHitArgs a;
+        memset(&a, 0, sizeof a);
+        a.k = db->k; a.n_seg = (uint32_t)db->seg_s.size();
+        for (size_t j = 0; j < db->seg_s.size(); j++) a.set_size[j] = set_size_of(s->mixture, db->use64, db->seg_s[j]);
+        a.set_size_dev = s->mixture_on_device ? s->d_sparse->set_size : nullptr;
+        a.seg_begin = db->d_seg_begin; a.hit = s->d_hit; a.n_hit = &s->d_sparse->n_hit;
+        a.shared = s->d_shared; a.median = s->d_median; a.offsets = db->d_offsets; a.rows = s->rows_dev;
+        CU(launch_stats_hits(a, dense, (uint32_t)N, s->d_hit, &s->d_sparse->n_hit, db->sm, s->stream));
+        s->st.n_launches += dense ? 2 : 1;
+    }
+    CU(cudaMemcpyAsync(s->h_sparse, s->d_sparse, sizeof(SparseState), cudaMemcpyDeviceToHost, s->stream));
+    if (s->mixture_on_device && db->s)
+        CU(cudaMemcpyAsync(s->h_mixture, s->d_mixture, (size_t)db->s * 8, cudaMemcpyDeviceToHost, s->stream));
+    return HS_OK;
+}
+
+// the common part of hs_screen_finish / hs_screen_finish_hits: settle the mixture, reduce, statistics,
+// results on the host (all N references as columns, or only the references with hits as rows)
+int finish_core(hs_screen *s, bool wta, bool hits)
+{
+    hs_db *db = s->db;
     // Single-GPU order: the per-sketch reduction needs only counts[], so it is enqueued BEFORE the
     // mixture is settled and runs underneath the host round trips of that (flush); a caller that
     // flushed first (multi-GPU: flush -> exchange -> finish) gets it here, after the exchange.
@@ -1686,7 +1758,7 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
     int rc;
     if (early) {
         CU(cudaEventRecord(s->red2, s->stream));
-        if ((rc = enqueue_reduce(s, wta != 0, dense)) != HS_OK) return rc;
+        if ((rc = enqueue_reduce(s, wta, dense)) != HS_OK) return rc;
         CU(cudaEventRecord(s->red3, s->stream));
     }
     rc = hs_screen_flush(s);
@@ -1697,8 +1769,8 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
         s->st.ms_reduce += ems;
     }
     CU(cudaEventRecord(s->red0, s->stream));
-    if (!early && (rc = enqueue_reduce(s, wta != 0, dense)) != HS_OK) return rc;
-    if ((rc = enqueue_stats_and_copy(s)) != HS_OK) return rc;
+    if (!early && (rc = enqueue_reduce(s, wta, dense)) != HS_OK) return rc;
+    if ((rc = hits ? enqueue_hits(s, dense) : enqueue_stats_and_copy(s)) != HS_OK) return rc;
     CU(cudaEventRecord(s->red1, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0;
@@ -1716,19 +1788,33 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
         // the O(present) bookkeeping did not hold this query (more present hashes than its buffers, or a
         // count that wrapped): the dense kernels give the answer, and the next reset clears every count
         dense = true;
+        const uint32_t n_touched = s->h_sparse->n_touched;
         CU(cudaEventRecord(s->red0, s->stream));
-        if ((rc = enqueue_reduce(s, wta != 0, true)) != HS_OK) return rc;
-        if ((rc = enqueue_stats_and_copy(s)) != HS_OK) return rc;
+        if ((rc = enqueue_reduce(s, wta, true)) != HS_OK) return rc;
+        if ((rc = hits ? enqueue_hits(s, true) : enqueue_stats_and_copy(s)) != HS_OK) return rc;
         CU(cudaEventRecord(s->red1, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
         s->st.ms_reduce += ms;
+        s->h_sparse->n_touched = n_touched;
     }
     s->st.reduce_path = dense ? 1u : 0u;
     s->st.n_touched = s->h_sparse->n_touched;
-    s->st.n_hit_refs = dense ? 0u : s->h_sparse->n_hit;
+    s->st.n_hit_refs = (dense && !hits) ? 0u : s->h_sparse->n_hit;
     s->st.n_pairs = dense ? 0u : s->h_sparse->n_pairs;
-    const uint64_t NA = std::max<uint64_t>(N, 1);
+    return HS_OK;
+}
+
+}  // namespace
+
+HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *median, double *identity,
+                            double *pvalue, hs_stats_t *stats)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    ON_DEVICE(s->db->device);
+    int rc = finish_core(s, wta != 0, false);
+    if (rc) return rc;
+    const uint64_t N = s->db->n_refs, NA = std::max<uint64_t>(N, 1);   // layout of the allocation (hs_screen_new)
     double *h_id = reinterpret_cast<double *>(s->h_result), *h_pv = h_id + NA;
     uint32_t *h_sh = reinterpret_cast<uint32_t *>(h_pv + NA), *h_md = h_sh + NA;
     if (shared) for (uint64_t i = 0; i < N; i++) shared[i] = h_sh[i];
@@ -1737,6 +1823,40 @@ HS_API int hs_screen_finish(hs_screen *s, int wta, uint64_t *shared, uint32_t *m
     if (pvalue && N) memcpy(pvalue, h_pv, N * 8);
     s->st.d2h_bytes += N * 24;
     if (stats) *stats = s->st;
+    return HS_OK;
+}
+
+HS_API int hs_screen_finish_hits(hs_screen *s, int wta, uint32_t *n_hits, hs_stats_t *stats)
+{
+    if (!s || !n_hits) return fail(HS_EINVAL, "null argument");
+    ON_DEVICE(s->db->device);
+    int rc = finish_core(s, wta != 0, true);
+    if (rc) return rc;
+    const uint32_t n = (uint32_t)std::min<uint64_t>(s->h_sparse->n_hit, s->db->n_refs);
+    s->hit_order.clear();
+    for (uint32_t q = 0; q < n; q++)
+        if (s->rows_host.shared[q]) s->hit_order.push_back(q);   // -w leaves references that lost every hash: not reported
+    const uint32_t *ref = s->rows_host.ref;
+    std::sort(s->hit_order.begin(), s->hit_order.end(), [ref](uint32_t a, uint32_t b) { return ref[a] < ref[b]; });
+    *n_hits = (uint32_t)s->hit_order.size();
+    s->st.d2h_bytes += (uint64_t)n * 28;
+    if (stats) *stats = s->st;
+    return HS_OK;
+}
+
+HS_API int hs_screen_hits_copy(hs_screen *s, uint32_t cap, uint32_t *ref, uint64_t *shared, uint32_t *median,
+                               double *identity, double *pvalue)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    const uint32_t n = (uint32_t)std::min<size_t>(cap, s->hit_order.size());
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t q = s->hit_order[i];
+        if (ref) ref[i] = s->rows_host.ref[q];
+        if (shared) shared[i] = s->rows_host.shared[q];
+        if (median) median[i] = s->rows_host.median[q];
+        if (identity) identity[i] = s->rows_host.identity[q];
+        if (pvalue) pvalue[i] = s->rows_host.pvalue[q];
+    }
     return HS_OK;
 }
 
@@ -1765,6 +1885,7 @@ HS_API void hs_screen_free(hs_screen *s)
     cudaFree(s->d_mixture); cudaFree(s->d_merge_work); cudaFree(s->d_merge_scratch);
     if (s->h_sparse) cudaFreeHost(s->h_sparse);
     if (s->h_mixture) cudaFreeHost(s->h_mixture);
+    if (s->h_rows) cudaFreeHost(s->h_rows);
     if (s->rst0) cudaEventDestroy(s->rst0);
     if (s->rst1) cudaEventDestroy(s->rst1);
     cudaFree(s->d_identity);   // one block: identity | p-value | shared | median

@@ -383,7 +383,7 @@ HS_HD void for_each_kmer_in_word(uint64_t prev, uint64_t cur, uint32_t inv_prev,
 //   u32 word 31      unused
 // so a probe is ONE line whether it hits or misses (round 1 kept the ids in a second array: a
 // second DRAM fetch per hit), a miss ends at the first bucket whose flag is clear, and ten slots
-// per bucket let the load factor be 0.6 (21 B per key; round 1: four slots at 1/3 = 36 B).
+// per bucket let the load factor be 0.5 (26 B per key; round 1: four slots at 1/3 = 36 B).
 // Reference hashes are bottom-s values (numerically small) so the bucket index re-mixes both
 // halves before the multiply-high range reduction.
 constexpr uint64_t kEmptyKey = ~0ull;

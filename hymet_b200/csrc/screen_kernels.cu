@@ -136,6 +136,116 @@ __device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts
     }
 }
 
+// Warp-cooperative table lookup of ONE HASH PER LANE (K2's "warp-cooperative bucket probe").
+// Eight lanes read one 128-byte bucket with one 16-byte load each -- a single coalesced line per
+// probe -- so a warp works on four probes per round and needs eight rounds for its 32 hashes; the
+// loads of INFLIGHT rounds are issued before the first compare.  Lanes 0-4 of a group hold the ten
+// keys, lanes 5-7 the ids and the overflow flag.  A probe whose home bucket overflowed (a few % at
+// load 0.5) is not chased on the spot by one lane while 31 wait for a DRAM round trip: it is set
+// aside and the warp follows all such chains together, four at a time, after the main rounds.
+// Must be called by all 32 lanes (convergent).  Returns the canonical entry id of this lane's hash
+// (kNoEntry: absent, or want == false); `reads` counts bucket lines on the group-leader lanes.
+template <int INFLIGHT>
+__device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine, bool want, uint32_t &reads)
+{
+    static_assert(INFLIGHT == 4 || INFLIGHT == 8, "rounds in flight");
+    const uint32_t lane = threadIdx.x & 31u, g = lane & 7u, G = lane >> 3, full = 0xffffffffu;
+    const uint32_t wants = __ballot_sync(full, want);
+    if (!wants) return kNoEntry;                       // warp-uniform
+    uint32_t res[8];                                   // per round, meaningful on every lane of the group
+    uint32_t pend = 0;                                 // rounds whose chain goes on (group-uniform)
+#pragma unroll
+    for (int r = 0; r < 8; r++) res[r] = kNoEntry;
+
+    // one bucket line for the group's probe: match, id, overflow flag -- all lanes of the group get the same answer
+    auto look = [&](const ulonglong2 &v, uint64_t h, bool &found, bool &over) -> uint32_t {
+        int slot = -1;
+        if (g < 5u) {
+            if (v.x == h) slot = 2 * (int)g;
+            else if (v.y == h) slot = 2 * (int)g + 1;
+        }
+        const uint32_t m = (__ballot_sync(full, slot >= 0) >> (G * 8u)) & 0xFFu;
+        const int kl = m ? __ffs(m) - 1 : 0;
+        const uint32_t w32 = (uint32_t)kBucketValWord32 + (uint32_t)__shfl_sync(full, slot, (int)(G * 8u) + kl);
+        const uint32_t comp = w32 & 3u;
+        const uint32_t pick = comp == 0 ? (uint32_t)v.x : comp == 1 ? (uint32_t)(v.x >> 32)
+                            : comp == 2 ? (uint32_t)v.y : (uint32_t)(v.y >> 32);
+        const uint32_t id = __shfl_sync(full, pick, (int)(G * 8u + ((w32 >> 2) & 7u)));
+        over = __shfl_sync(full, (uint32_t)v.y, (int)(G * 8u) + 7) != 0u;   // 32-bit word 30 of the bucket
+        found = m != 0u;
+        return id;
+    };
+
+#pragma unroll 1
+    for (int r0 = 0; r0 < 8; r0 += INFLIGHT) {
+        if (!((wants >> (4 * r0)) & ((INFLIGHT == 8) ? 0xFFFFFFFFu : 0xFFFFu))) continue;   // warp-uniform
+        uint64_t h[INFLIGHT];
+        uint32_t live = 0;
+        ulonglong2 v[INFLIGHT];
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; u++) {
+            const int src = (r0 + u) * 4 + (int)G;
+            h[u] = __shfl_sync(full, mine, src);
+            const bool lv = ((wants >> src) & 1u) && h[u] != kEmptyKey;
+            live |= lv ? (1u << u) : 0u;
+            v[u] = make_ulonglong2(0, 0);
+            if (lv) v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)bucket_of(h[u], t.n_buckets) * kBucketWords) + g);
+        }
+#pragma unroll
+        for (int u = 0; u < INFLIGHT; u++) {
+            bool found, over;
+            const uint32_t id = look(v[u], h[u], found, over);
+            const int src = (r0 + u) * 4 + (int)G;
+            if ((live >> u) & 1u) {
+                if (g == 0u) reads++;
+                if (found) res[r0 + u] = id;
+                else if (over) pend |= 1u << (r0 + u);
+            } else if (((wants >> src) & 1u) && h[u] == kEmptyKey) {
+                res[r0 + u] = t.special;
+            }
+        }
+    }
+    // chains: every group follows its own pending probes, one bucket per trip, all groups in step
+    int cr = -1;                                       // round being followed by this group (group-uniform)
+    uint32_t cstep = 0;                                // buckets past the home bucket
+    for (;;) {
+        if (cr < 0 && pend) {
+            cr = __ffs(pend) - 1;
+            pend &= pend - 1;
+            cstep = 1;
+        }
+        if (!__any_sync(full, cr >= 0)) break;
+        const int rr = cr < 0 ? 0 : cr;
+        const uint64_t hh = __shfl_sync(full, mine, rr * 4 + (int)G);
+        uint64_t cb = (uint64_t)bucket_of(hh, t.n_buckets) + cstep;
+        if (cb >= t.n_buckets) cb -= t.n_buckets;
+        ulonglong2 v = make_ulonglong2(0, 0);
+        if (cr >= 0) v = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)cb * kBucketWords) + g);
+        bool found, over;
+        const uint32_t id = look(v, hh, found, over);
+        if (cr >= 0) {
+            if (g == 0u) reads++;
+            if (found) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (q == cr) res[q] = id;
+                cr = -1;
+            } else if (!over || cstep + 1 >= t.n_buckets) {
+                cr = -1;
+            } else {
+                cstep++;
+            }
+        }
+    }
+    // hand every lane the answer for its own hash: lane (r * 4 + G) <- group G's res[r]
+    uint32_t out = kNoEntry;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        const uint32_t x = __shfl_sync(full, res[q], (int)((lane & 3u) * 8u));
+        if ((int)(lane >> 2) == q) out = x;
+    }
+    return want ? out : kNoEntry;
+}
+
 __device__ __forceinline__ void mix_insert(const MixView &m, uint64_t *set, uint64_t h)
 {
     if (h == kEmptyKey) { atomicExch(&m.st->has_max, 1u); return; }
@@ -203,11 +313,13 @@ struct SmemPremul {
 constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
 
 // MODE: 0 = screen, 1 = K1 parity (emit every hash), 2 = screen with the Bloom reads of a group of
-// kIlp k-mers issued together (databases with keys above the dense range)
+// kIlp k-mers issued together (databases with keys above the dense range), 3 = screen that probes for
+// (nearly) every k-mer: the warp looks its hashes up cooperatively (coop_probe), control flow stays
+// warp-uniform and the CTA may use twice the registers (the kernel waits on HBM, not on issue slots)
 template <int KT, int MODE>
-__global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const StreamArgs a)
+__global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
-    constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2;
+    constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2, COOP = MODE == 3;
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
@@ -304,7 +416,7 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
             const uint32_t nv = pos0 >= n_bases ? 0u : (uint32_t)(n_bases - pos0);
             icur |= nv ? ((1u << (32 - nv)) - 1u) : ~0u;
         }
-        if (icur == ~0u) continue;  // padding / all-N word: no k-mer ends here
+        if (!COOP && icur == ~0u) continue;  // padding / all-N word: no k-mer ends here (COOP: every lane stays for the warp's lookups)
 
         auto sink = [&](int j, uint64_t h, uint32_t bloom_word) {
             if (EMIT) {
@@ -364,6 +476,26 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
                             if (h[u] > a.tab.dense_max && h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
                         }
                     }
+                    if (COOP) {
+#pragma unroll
+                        for (int u = 0; u < kIlp; u++) {
+                            const int j = half * 16 + q + u;
+                            const bool valid = (ok >> (31 - j)) & 1u;
+                            if (valid && a.do_mix && h[u] <= mix_tau) {
+                                n_mix++;
+                                mix_insert(a.mix, mix_set, h[u]);
+                            }
+                            const bool want = valid && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key);
+                            n_probe += want;
+                            const uint32_t id = coop_probe<4>(a.tab, h[u], want, n_reads);   // all 32 lanes, every trip
+                            if (id != kNoEntry) {
+                                const uint32_t peers = __match_any_sync(__activemask(), id);
+                                if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id, (uint32_t)__popc(peers));
+                                n_hits++;
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int u = 0; u < kIlp; u++) {
                         const int j = half * 16 + q + u;
@@ -372,7 +504,7 @@ __global__ void __launch_bounds__(kCtaThreads, HS_MIN_CTAS) k_stream(const Strea
                 }
             }
         };
-        if (ok == ~0u) word(std::false_type{}); else word(std::true_type{});
+        if (!COOP && ok == ~0u) word(std::false_type{}); else word(std::true_type{});
     }
 
     n_valid = warp_sum(n_valid); n_probe = warp_sum(n_probe); n_reads = warp_sum(n_reads);
@@ -430,6 +562,13 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
 cudaError_t launch_stream(const StreamArgs &a, int sm_count, cudaStream_t st)
 {
     if (a.emit_hash) return launch_stream_t<0, 1>(a, sm_count, st);   // parity runs: generic-k instantiation
+    if (a.probe_all && a.do_count) {
+        switch (a.k) {
+        case 21: return launch_stream_t<21, 3>(a, sm_count, st);
+        case 31: return launch_stream_t<31, 3>(a, sm_count, st);
+        default: return launch_stream_t<0, 3>(a, sm_count, st);
+        }
+    }
     if (a.batch_bloom && a.do_count && a.do_filter && a.tab.bloom) {
         switch (a.k) {
         case 21: return launch_stream_t<21, 2>(a, sm_count, st);
@@ -517,65 +656,21 @@ __global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_distinct, (unsigned long long)local);
 }
 
-// K2 alone, warp-cooperative: eight lanes read one 128-byte bucket with one 16-byte load each (a
-// single coalesced line per probe), so a warp works on four probes at a time; four rounds of loads
-// are issued before the first compare (16 lines in flight per warp).  Lanes 0-4 of a group hold the
-// ten keys, lanes 5-7 the ids and the overflow flag.
+// K2 alone: one hash per lane, the cooperative lookup above with all eight rounds of loads in flight.
 __global__ void __launch_bounds__(256) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
                                                uint32_t *out_entry, unsigned long long *stats)
 {
-    const uint32_t lane = threadIdx.x & 31u, g = lane & 7u, G = lane >> 3;
-    const uint32_t full = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t hits = 0, reads = 0;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
-        const uint64_t mine = base + lane < n ? __ldg(hashes + base + lane) : kEmptyKey;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 8; r0 += 4) {
-            uint64_t h[4];
-            uint32_t b[4];
-            ulonglong2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                h[u] = __shfl_sync(full, mine, (r0 + u) * 4 + (int)G);
-                b[u] = bucket_of(h[u], t.n_buckets);
-                v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)b[u] * kBucketWords) + g);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const uint32_t src = (uint32_t)(r0 + u) * 4u + G;
-                const bool live = base + src < n;
-                int slot = -1;
-                if (g < 5u) {
-                    if (v[u].x == h[u]) slot = 2 * (int)g;
-                    else if (v[u].y == h[u]) slot = 2 * (int)g + 1;
-                }
-                const uint32_t m = (__ballot_sync(full, slot >= 0) >> (G * 8u)) & 0xFFu;
-                const int kl = m ? __ffs(m) - 1 : 0;
-                const uint32_t w32 = (uint32_t)kBucketValWord32 + (uint32_t)__shfl_sync(full, slot, (int)(G * 8u) + kl);
-                const uint32_t comp = w32 & 3u;
-                const uint32_t pick = comp == 0 ? (uint32_t)v[u].x : comp == 1 ? (uint32_t)(v[u].x >> 32)
-                                    : comp == 2 ? (uint32_t)v[u].y : (uint32_t)(v[u].y >> 32);
-                uint32_t id = __shfl_sync(full, pick, (int)(G * 8u + ((w32 >> 2) & 7u)));
-                const uint32_t over = __shfl_sync(full, (uint32_t)v[u].y, (int)(G * 8u) + 7);   // 32-bit word 30
-                if (g == 0u && live) {
-                    if (h[u] == kEmptyKey) {
-                        id = t.special;
-                    } else {
-                        reads++;
-                        if (!m) {
-                            id = kNoEntry;
-                            if (over) {   // rare (a few % of buckets at load 0.6): follow the chain alone
-                                const uint32_t nb = (b[u] + 1 == t.n_buckets) ? 0u : b[u] + 1;
-                                id = table_find_from<false>(t, h[u], nb, reads);
-                            }
-                        }
-                    }
-                    if (out_entry) out_entry[base + src] = id;
-                    hits += id != kNoEntry;
-                }
-            }
+        const bool have = base + lane < n;
+        const uint64_t mine = have ? __ldg(hashes + base + lane) : 0ull;
+        const uint32_t id = coop_probe<8>(t, mine, have, reads);
+        if (have) {
+            if (out_entry) out_entry[base + lane] = id;
+            hits += id != kNoEntry;
         }
     }
     hits = warp_sum(hits); reads = warp_sum(reads);
@@ -775,12 +870,13 @@ __device__ void bitonic_sort_block(uint64_t *w, uint32_t n_pad)
     }
 }
 
-__global__ void __launch_bounds__(1024) k_sort_unique(uint64_t *data, uint32_t n, uint32_t n_pad, uint64_t *scratch,
-                                                      uint32_t *n_unique)
+__global__ void __launch_bounds__(1024) k_sort_unique(uint64_t *data, uint32_t n, const uint32_t *n_dev, uint32_t n_pad,
+                                                      uint64_t *scratch, uint32_t *n_unique)
 {
     extern __shared__ uint64_t sm[];
     __shared__ uint32_t warp_tot[32];
     uint64_t *w = scratch ? scratch : sm;
+    if (n_dev) n = min(__ldcg(n_dev), n_pad);
     for (uint32_t i = threadIdx.x; i < n_pad; i += blockDim.x) w[i] = i < n ? data[i] : kEmptyKey;
     __syncthreads();
     bitonic_sort_block(w, n_pad);
@@ -827,8 +923,104 @@ cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, ui
         attr = true;
     }
     const bool in_smem = n_pad <= kSortSmemMax;
-    k_sort_unique<<<1, 1024, in_smem ? n_pad * sizeof(uint64_t) : 0, st>>>(data, n, n_pad, in_smem ? nullptr : scratch,
+    k_sort_unique<<<1, 1024, in_smem ? n_pad * sizeof(uint64_t) : 0, st>>>(data, n, nullptr, n_pad, in_smem ? nullptr : scratch,
                                                                           n_unique);
+    return cudaGetLastError();
+}
+
+// ---- device-side selection of the s smallest (no host round trip) -----------------
+constexpr uint32_t kSelBins = 2048;
+__device__ __forceinline__ unsigned long long sel_width(const MixState *st, bool use64)
+{
+    const unsigned long long tau = use64 ? st->tau : min(st->tau, 0xFFFFFFFFull);
+    return tau / kSelBins + 1ull;
+}
+
+__global__ void __launch_bounds__(256) k_mix_hist(const MixView v, int use64, uint32_t *hist)
+{
+    __shared__ uint32_t sh[kSelBins];
+    for (uint32_t i = threadIdx.x; i < kSelBins; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned long long tau = v.st->tau, width = sel_width(v.st, use64 != 0);
+    const uint64_t *set = v.sets[v.st->cur & 1u];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= v.mask; i += gridDim.x * blockDim.x) {
+        const uint64_t x = set[i];
+        if (x == kEmptyKey || x > tau) continue;   // older, larger values may linger from before tau dropped
+        const unsigned long long b = x / width;
+        atomicAdd(&sh[b < kSelBins ? (uint32_t)b : kSelBins - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kSelBins; i += blockDim.x)
+        if (sh[i]) atomicAdd(hist + i, sh[i]);
+}
+
+__global__ void __launch_bounds__(1024) k_mix_pick(const MixView v, int use64, uint32_t s, const uint32_t *hist)
+{
+    __shared__ uint32_t tot[32];
+    __shared__ uint32_t first;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // inclusive prefix sums of the 2048 bins, two per thread
+    const uint32_t a = hist[2 * threadIdx.x], b = hist[2 * threadIdx.x + 1];
+    uint32_t inc = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) tot[wid] = inc;
+    if (threadIdx.x == 0) first = kSelBins;
+    __syncthreads();
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < wid; w++) before += tot[w];
+    const uint32_t cum1 = before + inc, cum0 = cum1 - b;        // through bins 2t+1 and 2t
+    if (cum0 >= s) atomicMin(&first, 2 * threadIdx.x);
+    else if (cum1 >= s) atomicMin(&first, 2 * threadIdx.x + 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        MixState *st = v.st;
+        const unsigned long long width = sel_width(st, use64 != 0);
+        unsigned long long thr = st->tau;                        // fewer than s values in all: take everything
+        if (first + 1 < kSelBins) {
+            const unsigned long long t = (unsigned long long)(first + 1) * width - 1ull;
+            if (t < thr) thr = t;
+        }
+        st->sel_thr = thr;
+        st->n_out = 0;
+        st->sel_too_many = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mix_collect_sel(const MixView v, uint64_t *out, uint32_t out_cap)
+{
+    const unsigned long long thr = v.st->sel_thr;
+    const uint64_t *set = v.sets[v.st->cur & 1u];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= v.mask; i += gridDim.x * blockDim.x) {
+        const uint64_t x = set[i];
+        if (x != kEmptyKey && x <= thr) {
+            const uint32_t p = atomicAdd(&v.st->n_out, 1u);
+            if (p < out_cap) out[p] = x; else v.st->sel_too_many = 1u;
+        }
+    }
+}
+
+cudaError_t launch_mix_select(const MixView &v, uint32_t s, bool use64, uint32_t *hist, uint64_t *out, uint32_t n_pad,
+                              uint64_t *scratch, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(hist, 0, kSelBins * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    const uint32_t cap = v.mask + 1u;
+    k_mix_hist<<<grid_for(cap, 256, 148 * 2), 256, 0, st>>>(v, use64 ? 1 : 0, hist);
+    k_mix_pick<<<1, 1024, 0, st>>>(v, use64 ? 1 : 0, s, hist);
+    k_mix_collect_sel<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(v, out, n_pad);
+    static bool attr = false;
+    if (!attr) {
+        e = cudaFuncSetAttribute(k_sort_unique, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortSmemMax * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const bool in_smem = n_pad <= kSortSmemMax;
+    k_sort_unique<<<1, 1024, in_smem ? n_pad * sizeof(uint64_t) : 0, st>>>(out, 0, &v.st->n_out, n_pad, in_smem ? nullptr : scratch,
+                                                                          &v.st->n_unique);
     return cudaGetLastError();
 }
 
@@ -1073,6 +1265,54 @@ __global__ void __launch_bounds__(256) k_stats(uint32_t k, uint64_t set_size, co
             pvalue[i] = p;
         }
     }
+}
+
+// Rows a14-a16 in O(references with hits): identity + p-value only where shared > 0 -- everything
+// else is "not reported" (S15) -- written straight into host-mapped rows, so that the trip home is the
+// hits, not N x 24 bytes of mostly zeros (300 000 sketches: 7 MB per screen).
+__global__ void __launch_bounds__(256) k_stats_hits(const StatsHitArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nh = min(__ldcg(a.n_hit), a.rows.cap);
+    const double kmer_space = ldexp(1.0, 2 * (int)a.k);  // 4^k
+    for (uint32_t q = warp; q < nh; q += n_warps) {
+        const uint32_t i = a.hit[q];
+        uint32_t j = 0;
+        while (j + 1 < a.n_seg && (uint64_t)i >= a.seg_begin[j + 1]) j++;
+        const unsigned long long set_size = a.set_size_dev ? __ldcg(a.set_size_dev + j) : a.set_size[j];
+        const double r = 1.0 / (1.0 + kmer_space / (double)set_size);
+        const uint64_t x = a.shared[i], size = a.offsets[i + 1] - a.offsets[i];
+        const double p = binom_upper_tail_warp(x, size, r, lane);
+        if (lane == 0) {
+            double id;
+            if (x == size) id = 1.0;
+            else if (x == 0) id = 0.0;
+            else id = pow((double)x / (double)size, 1.0 / (double)a.k);
+            a.rows.ref[q] = i; a.rows.shared[q] = (uint32_t)x; a.rows.median[q] = a.median[i];
+            a.rows.identity[q] = id; a.rows.pvalue[q] = p;
+        }
+    }
+}
+
+// dense reduction ran: the references with hits are found by looking at all of them
+__global__ void __launch_bounds__(256) k_hits_from_dense(const uint32_t *shared, uint32_t n_refs, uint32_t *hit, uint32_t *n_hit)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_refs; i += gridDim.x * blockDim.x)
+        if (shared[i]) hit[atomicAdd(n_hit, 1u)] = i;
+}
+
+cudaError_t launch_stats_hits(const StatsHitArgs &a, bool from_dense, uint32_t n_refs, uint32_t *hit, uint32_t *n_hit,
+                              int sm_count, cudaStream_t st)
+{
+    if (!n_refs) return cudaSuccess;
+    if (from_dense) {
+        cudaError_t e = cudaMemsetAsync(n_hit, 0, sizeof(uint32_t), st);
+        if (e != cudaSuccess) return e;
+        k_hits_from_dense<<<grid_for(n_refs, 256, 148 * 4), 256, 0, st>>>(a.shared, n_refs, hit, n_hit);
+    }
+    k_stats_hits<<<(uint32_t)sm_count * 4u, 256, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_stats(uint32_t k, uint64_t set_size, const unsigned long long *set_size_dev, uint64_t n,

@@ -64,6 +64,8 @@ struct MixState {
     uint32_t cur;            // live set
     uint32_t n_out, n_unique;  // finalisation scratch
     uint32_t rebuilds;
+    uint32_t sel_too_many;   // device-side selection: more candidates than the sort holds (host falls back)
+    unsigned long long sel_thr;  // device-side selection: values <= sel_thr were collected
 };
 struct MixView {
     uint64_t *sets[2];      // open addressing, capacity mask+1, kEmptyKey = free
@@ -94,6 +96,7 @@ struct StreamArgs {
     uint64_t *emit_hash;    // optional: per position hash (K1 parity), n_bases entries
     uint8_t *emit_valid;
     int batch_bloom;        // use the instantiation that issues the Bloom reads of a group of k-mers together
+    int probe_all;          // (nearly) every k-mer probes: use the warp-cooperative instantiation
 };
 
 // ---- streaming (K1+K2+K3 insert) -------------------------------------------
@@ -125,6 +128,12 @@ cudaError_t launch_mix_collect(const uint64_t *set, uint32_t cap, uint64_t thr, 
 // after a streaming launch: fold its cap into tau and, if the live set is more than a
 // quarter full, rebuild it at tau/4 into the other buffer (exact: >= s smaller values stay)
 cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st);
+// The whole selection on the device, no host decision in between: histogram of the live set below
+// tau (2048 bins) -> smallest threshold with >= s values under it -> collect -> sort + unique.
+// out[] (capacity n_pad, a power of two >= s + slack) ends up ascending and distinct, st->n_unique
+// long; st->sel_too_many is raised when more than n_pad values lay under the threshold.
+cudaError_t launch_mix_select(const MixView &v, uint32_t s, bool use64, uint32_t *hist /*2048*/, uint64_t *out,
+                              uint32_t n_pad, uint64_t *scratch, cudaStream_t st);
 // sort ascending + unique in place (n <= cap_pow2 handled by padding); *n_unique out
 cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st);
 
@@ -141,6 +150,22 @@ cudaError_t launch_winner(const uint64_t *offsets, uint64_t n_refs, const uint32
 cudaError_t launch_stats(uint32_t k, uint64_t set_size, const unsigned long long *set_size_dev, uint64_t n,
                          const uint32_t *shared32, const uint64_t *shared64, const uint64_t *offsets,
                          const uint64_t *sizes, double *identity, double *pvalue, cudaStream_t st);
+
+// rows a14-a16 for the references with hits only; the rows live in host-mapped pinned memory
+struct HitRows { uint32_t *ref, *shared, *median; double *identity, *pvalue; uint32_t cap; };
+struct StatsHitArgs {
+    uint32_t k, n_seg;
+    unsigned long long set_size[8];           // S10 per source file (host value) ...
+    const unsigned long long *set_size_dev;   // ... or, when not NULL, read from device memory
+    const uint64_t *seg_begin;                // n_seg + 1 (device)
+    const uint32_t *hit, *n_hit;              // references with hits, how many (device)
+    const uint32_t *shared, *median;          // per reference
+    const uint64_t *offsets;
+    HitRows rows;
+};
+// from_dense: build hit[] / n_hit from shared[] first (the dense reduction leaves no hit list)
+cudaError_t launch_stats_hits(const StatsHitArgs &a, bool from_dense, uint32_t n_refs, uint32_t *hit, uint32_t *n_hit,
+                              int sm_count, cudaStream_t st);
 
 // SPARSE forms (O(present hashes)), rows a11-a13: walk the touched list and, per present key, the
 // chain of references that hold it.

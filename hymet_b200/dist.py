@@ -219,8 +219,15 @@ class DistributedScreen:
         self.last_exchange = "sparse"
 
     def finish(self, wta: bool = False) -> hs.ScreenResult:
+        return self._finish(wta, self.scr.finish)
+
+    def finish_hits(self, wta: bool = False) -> hs.ScreenHits:
+        """Same, returning only the references with hits (O(hits) on the way back to the host)."""
+        return self._finish(wta, self.scr.finish_hits)
+
+    def _finish(self, wta, fin):
         self.exchange()
-        res = self.scr.finish(wta)
+        res = fin(wta)
         if self.world > 1 and self.last_exchange == "sparse":
             most = int(res.stats["exchange_max_pairs"])
             if self.exchange_mode != "sparse":
@@ -232,5 +239,5 @@ class DistributedScreen:
                 # count exchange densely and reduce again (the mixture is already merged)
                 with torch.cuda.stream(self._tstream):
                     self._dense()
-                res = self.scr.finish(wta)
+                res = fin(wta)
         return res

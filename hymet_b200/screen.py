@@ -32,6 +32,26 @@ class ScreenResult:
     stats: dict
 
 
+@dataclass
+class ScreenHits:
+    """Only the references mash would print (shared > 0), ascending by reference index."""
+    ref: np.ndarray        # uint32 [H]
+    shared: np.ndarray     # uint64 [H]
+    median: np.ndarray     # uint32 [H]
+    identity: np.ndarray   # float64 [H]
+    pvalue: np.ndarray     # float64 [H]
+    set_size: int
+    stats: dict
+
+    def to_dense(self, n_refs: int) -> ScreenResult:
+        """The columns hs_screen_finish would have returned (shared = 0 => identity 0, p-value 1)."""
+        shared = np.zeros(n_refs, np.uint64); median = np.zeros(n_refs, np.uint32)
+        ident = np.zeros(n_refs, np.float64); pv = np.ones(n_refs, np.float64)
+        shared[self.ref] = self.shared; median[self.ref] = self.median
+        ident[self.ref] = self.identity; pv[self.ref] = self.pvalue
+        return ScreenResult(shared, median, ident, pv, self.set_size, self.stats)
+
+
 class Database:
     """A sketch database resident in the HBM of one B200 (rows a4/a5)."""
 
@@ -289,6 +309,19 @@ class Screen:
                                            _ptr(ident, C.c_double), _ptr(pv, C.c_double), C.byref(st)))
         N = self.db.n_refs
         return ScreenResult(shared[:N], median[:N], ident[:N], pv[:N], int(st.set_size), st.asdict())
+
+    def finish_hits(self, wta: bool = False) -> ScreenHits:
+        """Rows a11-a16 for the references with shared > 0 only (what the TSV holds): O(hits) on the way home."""
+        L = _abi.load()
+        n, st = C.c_uint32(), _abi.Stats()
+        check(L.hs_screen_finish_hits(self._h, int(wta), C.byref(n), C.byref(st)))
+        h = max(n.value, 1)
+        ref = np.zeros(h, np.uint32); shared = np.zeros(h, np.uint64); median = np.zeros(h, np.uint32)
+        ident = np.zeros(h, np.float64); pv = np.zeros(h, np.float64)
+        check(L.hs_screen_hits_copy(self._h, n.value, _ptr(ref, C.c_uint32), _ptr(shared, C.c_uint64), _ptr(median, C.c_uint32),
+                                    _ptr(ident, C.c_double), _ptr(pv, C.c_double)))
+        k = n.value
+        return ScreenHits(ref[:k], shared[:k], median[:k], ident[:k], pv[:k], int(st.set_size), st.asdict())
 
     def stats(self) -> dict:
         st = _abi.Stats()

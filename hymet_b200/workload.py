@@ -37,6 +37,7 @@ class Workload:
     fasta: Optional[torch.Tensor] = None   # pinned uint8 host tensor with the same contigs as FASTA text
     h_seq: Optional[torch.Tensor] = None   # pinned packed copies (e2e from packed host buffers)
     h_inv: Optional[torch.Tensor] = None
+    fasta_sample: Optional[bytes] = None   # FASTA text of the first contigs (bounded CPU-oracle sample)
 
 
 def _contig_table(rng: np.random.Generator, n_genomes: int, genome_len: int, total: int):
@@ -132,9 +133,24 @@ def pack_codes(codes: torch.Tensor):
     return seq, inv, n
 
 
-def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int = 500, genome_len: int = 2_000_000,
-            k: int = 21, s: int = 1000, rate: float = 0.01, seed: int = 2, shard: int = 0, with_fasta: bool = True,
-            with_host_packed: bool = True, fasta_width: int = 80, cluster_copies: int = 0, tiny: int = 0) -> Workload:
+@dataclass
+class SketchSet:
+    """A synthetic sketch database + the genomes its "real" sketches came from (device codes)."""
+    k: int
+    s: int
+    offsets: np.ndarray
+    hashes: np.ndarray
+    lengths: np.ndarray
+    n_real: int
+    genome_len: int
+    genomes: torch.Tensor        # uint8 codes [n_real * genome_len] on the device
+    seed: int
+
+
+def make_db(device: int, n_sketches: int = 50_000, n_real: int = 500, genome_len: int = 2_000_000, k: int = 21,
+            s: int = 1000, seed: int = 2, cluster_copies: int = 0, tiny: int = 0) -> SketchSet:
+    """`n_real` genomes sketched from their sequence with the GPU sketcher + decoy sketches (bottom-s of
+    uniform hashes: statistically what sketches of unrelated genomes look like)."""
     torch.cuda.set_device(device)
     dev = torch.device("cuda", device)
     hs._abi.init(device)
@@ -169,20 +185,46 @@ def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int 
         real_len[n_real - cluster_copies:] -= (np.arange(cluster_copies, dtype=np.uint64) % np.uint64(7))
     lengths = np.concatenate([real_len, dlen])
     offsets = np.arange(n_sketches + 1, dtype=np.uint64) * np.uint64(s)
+    return SketchSet(k=k, s=s, offsets=offsets, hashes=hashes, lengths=lengths, n_real=n_real, genome_len=genome_len,
+                     genomes=genomes, seed=seed)
 
-    qrng = np.random.default_rng(seed * 1000 + shard)      # each rank cuts its own shard of contigs
-    gen.manual_seed(seed * 1000 + shard)
-    lens, g, st, rc = _contig_table(qrng, n_real, genome_len, mbp * 1_000_000)
-    codes = _fill_query_codes(genomes, genome_len, lens, g, st, rc, rate, gen)
+
+def make_query(sk: SketchSet, mbp: int, rate: float = 0.01, shard: int = 0, with_fasta: bool = False,
+               with_host_packed: bool = False, fasta_width: int = 80, fasta_sample_mbp: int = 0, name: str = "c2") -> Workload:
+    """`mbp` Mbp of contigs cut from the real genomes (Zymo-fitted lengths, `rate` substitutions, half
+    reverse-complemented), packed on the device.  Shard `shard` is an independent draw: N ranks with
+    shards 0..N-1 hold N disjoint parts of one contig set.  fasta_sample_mbp > 0: also the FASTA text
+    of the first contigs up to that many Mbp (host bytes; the CPU oracle's bounded sample)."""
+    dev = sk.genomes.device
+    qrng = np.random.default_rng(sk.seed * 1000 + shard)      # each rank cuts its own shard of contigs
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(sk.seed * 1000 + shard)
+    lens, g, st, rc = _contig_table(qrng, sk.n_real, sk.genome_len, mbp * 1_000_000)
+    codes = _fill_query_codes(sk.genomes, sk.genome_len, lens, g, st, rc, rate, gen)
     d_seq, d_inv, n_pos = pack_codes(codes)
-    wl = Workload(name="c2", k=k, s=s, offsets=offsets, hashes=hashes, lengths=lengths, n_real=n_real, d_seq=d_seq,
-                  d_inv=d_inv, n_positions=n_pos, n_bases=int(lens.sum()), n_contigs=len(lens))
+    wl = Workload(name=name, k=sk.k, s=sk.s, offsets=sk.offsets, hashes=sk.hashes, lengths=sk.lengths, n_real=sk.n_real,
+                  d_seq=d_seq, d_inv=d_inv, n_positions=n_pos, n_bases=int(lens.sum()), n_contigs=len(lens))
     if with_fasta:
         wl.fasta = _fasta_from_codes(codes, lens, fasta_width)
+    if fasta_sample_mbp:
+        c = int(np.searchsorted(np.cumsum(lens), fasta_sample_mbp * 1_000_000, side="left")) + 1
+        c = min(c, len(lens))
+        n_codes = int((lens[:c] + 1).sum())
+        wl.fasta_sample = _fasta_from_codes(codes[:n_codes], lens[:c], fasta_width).numpy().tobytes()
     if with_host_packed:
         words = (n_pos + 31) // 32
         wl.h_seq = torch.empty(words, dtype=torch.int64, pin_memory=True).copy_(d_seq[:words])
         wl.h_inv = torch.empty(words, dtype=torch.int32, pin_memory=True).copy_(d_inv[:words])
-    del genomes, codes
+    del codes
+    torch.cuda.empty_cache()
+    return wl
+
+
+def make_c2(device: int, mbp: int = 1000, n_sketches: int = 50_000, n_real: int = 500, genome_len: int = 2_000_000,
+            k: int = 21, s: int = 1000, rate: float = 0.01, seed: int = 2, shard: int = 0, with_fasta: bool = True,
+            with_host_packed: bool = True, fasta_width: int = 80, cluster_copies: int = 0, tiny: int = 0) -> Workload:
+    sk = make_db(device, n_sketches, n_real, genome_len, k, s, seed, cluster_copies, tiny)
+    wl = make_query(sk, mbp, rate, shard, with_fasta, with_host_packed, fasta_width)
+    del sk
     torch.cuda.empty_cache()
     return wl

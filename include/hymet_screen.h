@@ -215,6 +215,14 @@ int hs_screen_segment_set_size(hs_screen *s, uint32_t segment, uint64_t *set_siz
  * O(stored hashes) kernels as the fallback when that record overflows (hs_stats_t.reduce_path). */
 int hs_screen_finish(hs_screen *s, int winner_take_all, uint64_t *shared, uint32_t *median,
                      double *identity, double *pvalue, hs_stats_t *stats);
+/* The same reduction, but only the references mash would print (shared > 0; S15) come back: rows a14-a16
+ * are computed for those alone and the GPU writes them into pinned host rows, so the trip home is
+ * O(references with hits) instead of 24 bytes for each of N.  *n_hits = how many there are;
+ * hs_screen_hits_copy then fills the caller's arrays (`cap` elements each, NULL to skip a column) in
+ * ascending reference order -- the line order of the TSV. */
+int hs_screen_finish_hits(hs_screen *s, int winner_take_all, uint32_t *n_hits, hs_stats_t *stats);
+int hs_screen_hits_copy(hs_screen *s, uint32_t cap, uint32_t *ref, uint64_t *shared, uint32_t *median,
+                        double *identity, double *pvalue);
 /* Forget the query (counts, mixture, stats) so the handle can screen another one. */
 int hs_screen_reset(hs_screen *s);
 int hs_screen_stats(hs_screen *s, hs_stats_t *stats);

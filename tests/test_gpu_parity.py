@@ -388,38 +388,78 @@ def test_cli_tsv_byte_identical_to_oracle_cli(tmp_path):
     assert r.returncode == 1 and b"ERROR" in r.stderr and r.stdout == b""
 
 
-def test_unmodified_mash_sh_pipeline(tmp_path):
-    """The reference's own scripts/mash.sh (restated inline, the GPU box has no
-    /root/reference) with our `mash` first on PATH: all five outputs equal the ones
-    produced with the oracle CLI as `mash`."""
-    mash_sh = """#!/bin/bash
-INPUT_DIR="$1"; MASH_SCREEN="$2"; SCREEN_TAB="$3"; FILTERED_SCREEN="$4"; SORTED_SCREEN="$5"
-TOP_HITS="$6"; SELECTED_GENOMES="$7"; INITIAL_THRESHOLD="$8"
-mash screen -p 8 -v 0.9 "$MASH_SCREEN" "$INPUT_DIR"/*.fna > "$SCREEN_TAB"
-sort -u -k5,5 "$SCREEN_TAB" > "$FILTERED_SCREEN"
-sort -gr "$FILTERED_SCREEN" > "$SORTED_SCREEN"
-best=$INITIAL_THRESHOLD
-awk -v threshold="$best" '$1 > threshold' "$SORTED_SCREEN" > "$TOP_HITS"
-cut -f5 "$TOP_HITS" > "$SELECTED_GENOMES"
-"""
-    rng = np.random.default_rng(9)
-    genomes = [synth.random_genome(rng, 30_000) for _ in range(30)]
-    dbp = write_db(tmp_path, genomes, 21, 1000)
-    indir = tmp_path / "input"; indir.mkdir()
-    (indir / "sample_0.fna").write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[:6], 150_000, 0.01, median=4000.0), "s"))
-    sh = tmp_path / "mash.sh"; sh.write_text(mash_sh)
+def reference_mash_sh(tmp_path, golden_dir):
+    """The reference's scripts/mash.sh, byte for byte, from the compressed fixture."""
+    import base64
+    import gzip
+    import hashlib
+    fx = json.load(open(os.path.join(golden_dir, "mash_sh_fixture.json")))
+    raw = gzip.decompress(base64.b64decode(fx["gzip_base64"]))
+    assert hashlib.sha256(raw).hexdigest() == fx["sha256"]
+    sh = tmp_path / "mash.sh"
+    sh.write_bytes(raw)
+    return str(sh)
+
+
+def run_mash_sh(tmp_path, script, mash_exe, tag, indir, dbp, thr):
+    import stat
+
+    from tests.test_stage_cpu import FAKE_BC
+    bindir = tmp_path / ("bin_" + tag); bindir.mkdir()
+    os.symlink(mash_exe, bindir / "mash")
+    bc = bindir / "bc"                       # no bc in the image: exact-decimal stand-in (tests/test_stage_cpu.py)
+    bc.write_text(FAKE_BC)
+    bc.chmod(bc.stat().st_mode | stat.S_IXUSR)
+    od = tmp_path / ("out_" + tag); od.mkdir()
+    files = [str(od / f) for f in ("screen.tab", "filtered.tab", "sorted.tab", "top_hits.tab", "selected.txt")]
+    env = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ["PATH"], LC_ALL="C")
+    p = subprocess.run(["bash", script, str(indir), dbp] + files + [thr], capture_output=True, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return [open(f, "rb").read() for f in files], p.stdout.decode()
+
+
+@pytest.mark.parametrize("seed,n_genomes,n_files,thr,rates,per_file", [
+    (1, 24, 1, "0.9", (0.0,), 5),                        # first threshold is enough
+    (5, 10, 3, "0.9", (0.0, 0.12, 0.2), 2),              # the bc/awk loop steps down to .78
+    (7, 3, 1, "0.9", (0.1,), 2),                         # never enough candidates: the 0.71 fallback
+])
+def test_full_reference_mash_sh_with_gpu_mash(tmp_path, golden_dir, seed, n_genomes, n_files, thr, rates, per_file):
+    """/root/reference/scripts/mash.sh:1-59, UNMODIFIED (fixture), with bin/mash first on PATH: the
+    screen (line 14), both sorts, the min-candidates arithmetic, the threshold loop and the fallback
+    (lines 19-51) leave the same five files and the same log as with the oracle CLI as `mash`, and as
+    hymet_b200.stage.select computes."""
+    from hymet_b200 import stage
+    from tests.test_stage_cpu import make_case
+    script = reference_mash_sh(tmp_path, golden_dir)
+    dbp, indir = make_case(tmp_path, seed, n_genomes, n_files, rates=rates, per_file=per_file)
     orc.build()
-    outs = {}
-    for tag, mash_exe in (("gpu", os.path.join(ROOT, "bin", "mash")), ("oracle", orc.BIN)):
-        bindir = tmp_path / ("bin_" + tag); bindir.mkdir()
-        os.symlink(mash_exe, bindir / "mash")
-        od = tmp_path / ("out_" + tag); od.mkdir()
-        files = [str(od / f) for f in ("screen.tab", "filtered.tab", "sorted.tab", "top_hits.tab", "selected.txt")]
-        env = dict(os.environ, PATH=str(bindir) + os.pathsep + os.environ["PATH"], LC_ALL="C")
-        subprocess.run(["bash", str(sh), str(indir), dbp] + files + ["0.9"], check=True, env=env)
-        outs[tag] = [open(f, "rb").read() for f in files]
-    assert outs["gpu"] == outs["oracle"]
-    assert len(outs["gpu"][4].splitlines()) >= 3
+    gpu, gpu_log = run_mash_sh(tmp_path, script, os.path.join(ROOT, "bin", "mash"), "gpu", indir, dbp, thr)
+    ora, ora_log = run_mash_sh(tmp_path, script, orc.BIN, "oracle", indir, dbp, thr)
+    assert gpu == ora and gpu_log == ora_log
+    assert gpu[0].count(b"\n") >= 3
+    _, n_find = stage.input_files(indir)
+    r = stage.select(gpu[0], n_find, thr)
+    assert [r["filtered"], r["sorted"], r["top_hits"], r["selected"]] == gpu[1:] and r["log"] == gpu_log
+    if seed == 5:
+        assert gpu_log.count("Testing threshold") > 3
+    if seed == 7:
+        assert "No suitable threshold found" in gpu_log
+
+
+@pytest.mark.parametrize("thr", ["0.9", "0.82"])
+def test_full_reference_mash_sh_on_real_genomes(tmp_path, golden_dir, thr):
+    """Same, on the Zymo fixture: the files the unmodified script left behind in the build container
+    (tests/golden/zymo_mash_sh.json, oracle CLI as `mash`) are reproduced with the GPU `mash`."""
+    import gzip
+    script = reference_mash_sh(tmp_path, golden_dir)
+    indir = tmp_path / "input"; indir.mkdir()
+    (indir / "sample_0.fna").write_bytes(gzip.open(os.path.join(golden_dir, "zymo_query.fna.gz"), "rb").read())
+    got, log = run_mash_sh(tmp_path, script, os.path.join(ROOT, "bin", "mash"), "gpu", indir,
+                           os.path.join(golden_dir, "zymo25.msh"), thr)
+    want = json.load(open(os.path.join(golden_dir, "zymo_mash_sh.json")))[thr]
+    assert got[0] == open(os.path.join(golden_dir, "zymo_screen.tsv"), "rb").read()
+    assert [g.decode() for g in got[1:]] == [want["filtered"], want["sorted"], want["top_hits"], want["selected"]]
+    assert log == want["log"]
 
 
 # ------------------------------------------------- BASELINE-size properties -------

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Run bench.py over the BASELINE.json configs (3, 4, 5) and collect the JSON lines.
+"""Run bench.py over the BASELINE.json configs (3, 4, 5) and collect the JSON lines, each with a CPU-oracle
+parity check on a bounded sample of its own contigs (SWEEP_NO_CPU=1 skips that).
 Usage: python tools/sweep.py out.jsonl  (on a GPU box)"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +24,7 @@ with open(out, "a") as fh:
     for name, extra in runs:
         if only and name not in only:
             continue
-        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-e2e", "--no-cpu"] + extra
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "3", "--warmup", "3", "--no-e2e", "--no-extras", "--workload", "c2"] + extra + (["--no-cpu"] if os.environ.get("SWEEP_NO_CPU") else [])
         env = dict(os.environ, HYMET_SCREEN_BLOOM="0") if name.endswith("nobloom") else dict(os.environ)
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, env=env)
         line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
@@ -31,8 +32,9 @@ with open(out, "a") as fh:
             d = json.loads(line)
             d["sweep_name"] = name
             fh.write(json.dumps(d) + "\n"); fh.flush()
-            print(name, "value %.0f Mbp/s  step %.2f ms  stream %.2f ms  reduce %.2f ms  kmers/s %.3g  probes %d  hits %d  table %.0f MB" % (
+            print(name, "value %.0f Mbp/s  step %.2f ms  stream %.2f ms  reduce %.2f ms  reset %.3f ms  kmers/s %.3g  probes %d  hits %d  table %.0f MB  cpu-parity %s" % (
                 d["value"], d["ms_per_step"], d["step_breakdown_ms"]["stream_kernel"], d["step_breakdown_ms"]["mixture_and_reduce"],
-                d["roofline"]["kmers_per_s"], d["counters"]["n_probes"], d["counters"]["n_hits"], d["db"]["table_mb"]), flush=True)
+                d["step_breakdown_ms"]["reset"], d["roofline"]["kmers_per_s"], d["counters"]["n_probes"], d["counters"]["n_hits"],
+                d["db"]["table_mb"], (d.get("cpu_baseline") or {}).get("parity_on_sample")), flush=True)
         except Exception as e:
             print(name, "FAILED", e, r.stderr[-800:], flush=True)

@@ -16,22 +16,31 @@ from . import _abi
 from ._abi import HsError, check  # noqa: F401  (re-exported)
 
 
+DEVICE_ERRORS = (-2, -3, -6)     # HS_ENODEV, HS_ECUDA, HS_ENOMEM: the GPU path itself is unavailable (never a data problem)
+
+
 class LiteDb:
-    def __init__(self, path, device: int):
+    def __init__(self, path, device: int, tolerate: bool = False):
         """`path`: one .msh, or a list of them for one table over several files (hs_db_from_msh_multi).
-        The files are parsed on a helper thread (host only) while this thread creates the CUDA context."""
+        The files are parsed on a helper thread (host only) while this thread creates the CUDA context.
+        tolerate=True (list form): a file that cannot be opened or parsed is left out instead of failing
+        the whole table; `loaded` lists the indices that made it, `errors` maps the others to messages."""
         L = _abi.load()
         paths = [path] if isinstance(path, str) else list(path)
-        handles, box = [], {}
+        handles, box = {}, {}
+        self.errors = {}
 
         def parse():
-            try:
-                for p in paths:
+            for i, p in enumerate(paths):
+                try:
                     m = C.c_void_p()
                     check(L.hs_msh_open(p.encode(), C.byref(m)))   # hs_last_error() is thread local: check here
-                    handles.append(m)
-            except Exception as e:                                  # noqa: BLE001
-                box["err"] = e
+                    handles[i] = m
+                except HsError as e:
+                    if not tolerate:
+                        box["err"] = e
+                        return
+                    self.errors[i] = e.msg
 
         th = threading.Thread(target=parse)
         th.start()
@@ -40,21 +49,24 @@ class LiteDb:
         finally:
             th.join()
         self._h = C.c_void_p()
+        self.loaded = sorted(handles)
         try:
             if "err" in box:
                 raise box["err"]
             if isinstance(path, str):
                 check(L.hs_db_from_msh(handles[0], C.byref(self._h)))
-            else:
-                arr = (C.c_void_p * len(handles))(*[m.value for m in handles])
-                check(L.hs_db_from_msh_multi(arr, len(handles), C.byref(self._h)))
+            elif self.loaded:
+                arr = (C.c_void_p * len(self.loaded))(*[handles[i].value for i in self.loaded])
+                check(L.hs_db_from_msh_multi(arr, len(self.loaded), C.byref(self._h)))
         finally:
-            for m in handles:
+            for m in handles.values():
                 L.hs_msh_free(m)
         self.info = _abi.DbInfo()
-        check(L.hs_db_info(self._h, C.byref(self.info)))
-        self.n_refs = int(self.info.n_refs)
-        self.n_distinct = int(self.info.n_distinct)
+        self.n_refs = self.n_distinct = 0
+        if self._h:
+            check(L.hs_db_info(self._h, C.byref(self.info)))
+            self.n_refs = int(self.info.n_refs)
+            self.n_distinct = int(self.info.n_distinct)
 
     @property
     def segments(self):
@@ -72,6 +84,11 @@ class LiteDb:
         check(_abi.load().hs_db_ref(self._h, i, C.byref(nm), C.byref(cm), C.byref(ln), C.byref(nh)))
         return ((nm.value or b"").decode("utf-8", "replace"), (cm.value or b"").decode("utf-8", "replace"), ln.value, nh.value)
 
+    def close(self):
+        if self._h:
+            _abi.load().hs_db_free(self._h)
+            self._h = C.c_void_p()
+
 
 class LiteScreen:
     def __init__(self, db: LiteDb, probe_filter: bool = True):
@@ -85,6 +102,19 @@ class LiteScreen:
 
     def feed_fasta(self, path: str, threads: int):
         check(_abi.load().hs_screen_feed_fasta(self._h, path.encode(), threads))
+
+    def set_option(self, key: str, value: int):
+        check(_abi.load().hs_screen_set_option(self._h, key.encode(), int(value)))
+
+    def reset(self):
+        """Forget the query; the handle (arena, pinned ring, result rows) stays allocated."""
+        check(_abi.load().hs_screen_reset(self._h))
+        self._cols = self._hits = None
+
+    def close(self):
+        if self._h:
+            _abi.load().hs_screen_free(self._h)
+            self._h = C.c_void_p()
 
     def flush(self):
         check(_abi.load().hs_screen_flush(self._h))

@@ -38,12 +38,17 @@ Options:
 """
 
 
-def _err(msg: str) -> None:
-    sys.stderr.write("ERROR: %s\n" % msg)
+def _err(msg: str, stderr=None) -> None:
+    (stderr or sys.stderr).write("ERROR: %s\n" % msg)
 
 
-def screen_main(args: List[str], stdout=None) -> int:
+def screen_main(args: List[str], stdout=None, stderr=None, cwd: Optional[str] = None, server=None) -> int:
+    """`mash screen`.  In-process by default; `server` is the resident table server when this runs inside
+    it (hymet_b200/server.py): tables and screens then outlive the call, relative paths are the
+    client's (`cwd`), and stdout/stderr are the client's too."""
     stdout = stdout or sys.stdout
+    stderr = stderr or sys.stderr
+    _e = lambda msg: _err(msg, stderr)
     threads, wta, imin, pmax = 1, False, 0.0, 1.0
     pos: List[str] = []
     i = 0
@@ -57,7 +62,7 @@ def screen_main(args: List[str], stdout=None) -> int:
                 wta = True
             elif a in ("-p", "-i", "-v"):
                 if i + 1 >= len(args):
-                    _err("-%s requires an argument" % a[1])
+                    _e("-%s requires an argument" % a[1])
                     return 1
                 v = args[i + 1]
                 i += 1
@@ -68,23 +73,28 @@ def screen_main(args: List[str], stdout=None) -> int:
                 else:
                     pmax = float(v)
             elif a.startswith("-") and a != "-":
-                _err("Unrecognized option: %s" % a)
+                _e("Unrecognized option: %s" % a)
                 return 1
             else:
                 pos.append(a)
             i += 1
     except ValueError:
-        _err("malformed numeric option value")
+        _e("malformed numeric option value")
         return 1
     if len(pos) < 2:
         stdout.write(USAGE)
         return 0
     db_path, inputs = pos[0], pos[1:]
+    if cwd:
+        rel = lambda p: p if (p == "-" or os.path.isabs(p)) else os.path.join(cwd, p)
+        shown_db, db_path, inputs = db_path, rel(db_path), [rel(p) for p in inputs]
+    else:
+        shown_db = db_path
     if not db_path.endswith(".msh"):
-        _err("%s does not look like a sketch (.msh)" % db_path)
+        _e("%s does not look like a sketch (.msh)" % shown_db)
         return 1
     if threads < 1 or not (0.0 <= pmax <= 1.0) or imin > 1.0:
-        _err("option value out of range")
+        _e("option value out of range")
         return 1
 
     import time
@@ -96,15 +106,22 @@ def screen_main(args: List[str], stdout=None) -> int:
 
     device = int(os.environ.get("HYMET_SCREEN_DEVICE", "0"))
     try:
-        sys.stderr.write("Loading %s...\n" % db_path)
-        db = hs.LiteDb(db_path, device)                  # CUDA context creation overlaps the .msh parse
+        stderr.write("Loading %s...\n" % shown_db)
+        if server is not None:
+            if "-" in inputs:
+                _e("the screen server cannot read the client's standard input")
+                return 1
+            ent = server.table([db_path])                # resident: built on first use only
+            db, scr = ent["db"], server.screen_for(ent)
+        else:
+            db = hs.LiteDb(db_path, device)              # CUDA context creation overlaps the .msh parse
+            scr = hs.LiteScreen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
         mark("cuda_init + load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
-        sys.stderr.write("   %d distinct hashes.\n" % db.n_distinct)
-        scr = hs.LiteScreen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
-        sys.stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
+        stderr.write("   %d distinct hashes.\n" % db.n_distinct)
+        stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
         for p in inputs:
             if p != "-" and not os.path.exists(p):
-                _err("could not open %s for reading." % p)
+                _e("could not open %s for reading." % p)
                 return 1
             scr.feed_fasta(p, threads)
         mark("feed")
@@ -112,19 +129,19 @@ def screen_main(args: List[str], stdout=None) -> int:
         mark("flush")
         st = scr.stats()
         if st["n_records"] == 0:
-            _err("Did not find sequence records in inputs.")
+            _e("Did not find sequence records in inputs.")
             return 1
-        sys.stderr.write("   Estimated distinct k-mers in mixture: %d\n" % st["set_size"])
+        stderr.write("   Estimated distinct k-mers in mixture: %d\n" % st["set_size"])
         if st["set_size"] == 0:
-            sys.stderr.write("WARNING: no valid k-mers in input.\n")
-        sys.stderr.write("Summing shared...\n")
+            stderr.write("WARNING: no valid k-mers in input.\n")
+        stderr.write("Summing shared...\n")
         if wta:
-            sys.stderr.write("Reallocating to winners...\n")
-        sys.stderr.write("Computing coverage medians...\n")
+            stderr.write("Reallocating to winners...\n")
+        stderr.write("Computing coverage medians...\n")
         lines = scr.finish_lines(wta, imin, pmax)
         first = next(lines, None)                 # the reduction runs on the first pull
         mark("finish")
-        sys.stderr.write("Writing output...\n")
+        stderr.write("Writing output...\n")
         if first is not None:
             stdout.write(first)
         for ln in lines:
@@ -134,12 +151,12 @@ def screen_main(args: List[str], stdout=None) -> int:
         if os.environ.get("HYMET_SCREEN_TIMING"):
             prev = t0
             for what, t in marks:
-                sys.stderr.write("[timing] %-40s %8.3f s\n" % (what, t - prev))
+                stderr.write("[timing] %-40s %8.3f s\n" % (what, t - prev))
                 prev = t
-            sys.stderr.write("[timing] %-40s %8.3f s\n" % ("total inside screen_main", prev - t0))
+            stderr.write("[timing] %-40s %8.3f s\n" % ("total inside screen_main", prev - t0))
         return 0
     except hs.HsError as e:
-        _err(e.msg)
+        _e(e.msg)
         return 1
 
 
@@ -243,6 +260,29 @@ def sketch_main(args: List[str], stdout=None) -> int:
     return 0
 
 
+def _via_server(args: List[str]) -> Optional[int]:
+    """Hand `mash screen args` to the resident table server (hymet_b200/server.py) when
+    HYMET_SCREEN_SERVER is 1 (use it if it answers) or auto (start it first if it does not).  None =
+    no server took the request: the caller screens in-process, exactly as without the variable."""
+    if "-" in args or "-h" in args:
+        return None                      # standard input belongs to this process
+    from . import server
+    path = server.default_socket_path()
+    req = {"op": "screen", "argv": list(args), "cwd": os.getcwd()}
+    try:
+        return server.request(path, req)
+    except OSError:
+        pass
+    if os.environ.get("HYMET_SCREEN_SERVER") != "auto":
+        return None
+    try:
+        server.spawn_detached(path, int(os.environ.get("HYMET_SCREEN_DEVICE", "0")))
+        return server.request(path, req)
+    except OSError as e:
+        sys.stderr.write("WARNING: no screen server (%s); screening in-process\n" % e)
+        return None
+
+
 def main(argv: Optional[List[str]] = None) -> int:
     argv = sys.argv[1:] if argv is None else argv
     if not argv or argv[0] in ("-h", "--help", "help"):
@@ -253,6 +293,10 @@ def main(argv: Optional[List[str]] = None) -> int:
         return 0
     if argv[0] == "sketch":
         return sketch_main(argv[1:])
+    if argv[0] == "screen" and os.environ.get("HYMET_SCREEN_SERVER", "0") not in ("", "0"):
+        rc = _via_server(argv[1:])
+        if rc is not None:
+            return rc
     if argv[0] != "screen":
         # HYMET uses nothing else; hand over to a real mash when one exists further down PATH
         me = os.path.realpath(sys.argv[0])

@@ -138,11 +138,13 @@ __device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts
 
 // Warp-cooperative table lookup of ONE HASH PER LANE (K2's "warp-cooperative bucket probe").
 // Eight lanes read one 128-byte bucket with one 16-byte load each -- a single coalesced line per
-// probe -- so a warp works on four probes per round and needs eight rounds for its 32 hashes; the
-// loads of INFLIGHT rounds are issued before the first compare.  Lanes 0-4 of a group hold the ten
-// keys, lanes 5-7 the ids and the overflow flag.  A probe whose home bucket overflowed (a few % at
-// load 0.5) is not chased on the spot by one lane while 31 wait for a DRAM round trip: it is set
-// aside and the warp follows all such chains together, four at a time, after the main rounds.
+// probe, one L1 wavefront instead of the 32 a per-thread load of a random line costs -- so a warp
+// works on four probes per round and needs eight rounds for its 32 hashes; the loads of INFLIGHT
+// rounds are issued before the first compare.  Lanes 0-4 of a group hold the ten keys, lanes 5-7 the
+// ids and the overflow flag.  The common round (no key matches, no bucket overflowed) is two
+// compares and two votes; matches and overflows are resolved in a warp-uniform slow path, and a
+// probe whose home bucket overflowed (1.4 % at load 0.5) is not chased on the spot by one lane while
+// 31 wait for a DRAM round trip: the warp follows all such chains together after the main rounds.
 // Must be called by all 32 lanes (convergent).  Returns the canonical entry id of this lane's hash
 // (kNoEntry: absent, or want == false); `reads` counts bucket lines on the group-leader lanes.
 template <int INFLIGHT>
@@ -150,17 +152,17 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
 {
     static_assert(INFLIGHT == 4 || INFLIGHT == 8, "rounds in flight");
     const uint32_t lane = threadIdx.x & 31u, g = lane & 7u, G = lane >> 3, full = 0xffffffffu;
-    const uint32_t wants = __ballot_sync(full, want);
-    if (!wants) return kNoEntry;                       // warp-uniform
-    uint32_t res[8];                                   // per round, meaningful on every lane of the group
-    uint32_t pend = 0;                                 // rounds whose chain goes on (group-uniform)
-#pragma unroll
-    for (int r = 0; r < 8; r++) res[r] = kNoEntry;
+    const bool special = want && mine == kEmptyKey;           // never stored in a bucket: answered from the view
+    const uint32_t wants = __ballot_sync(full, want && !special);
+    if (!wants) return special ? t.special : kNoEntry;         // warp-uniform
+    const uint32_t myb = bucket_of(mine, t.n_buckets);
+    uint32_t res[8];                                           // per round; only touched when something was found
+    uint32_t pend = 0, any_found = 0;                          // group-uniform / warp-uniform
 
-    // one bucket line for the group's probe: match, id, overflow flag -- all lanes of the group get the same answer
-    auto look = [&](const ulonglong2 &v, uint64_t h, bool &found, bool &over) -> uint32_t {
+    // resolve one bucket line for the group's probe (slow path): id if a key matched, overflow flag
+    auto resolve = [&](const ulonglong2 &v, uint64_t h, bool lv, bool &found, bool &over) -> uint32_t {
         int slot = -1;
-        if (g < 5u) {
+        if (lv && g < 5u) {
             if (v.x == h) slot = 2 * (int)g;
             else if (v.y == h) slot = 2 * (int)g + 1;
         }
@@ -171,7 +173,7 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
         const uint32_t pick = comp == 0 ? (uint32_t)v.x : comp == 1 ? (uint32_t)(v.x >> 32)
                             : comp == 2 ? (uint32_t)v.y : (uint32_t)(v.y >> 32);
         const uint32_t id = __shfl_sync(full, pick, (int)(G * 8u + ((w32 >> 2) & 7u)));
-        over = __shfl_sync(full, (uint32_t)v.y, (int)(G * 8u) + 7) != 0u;   // 32-bit word 30 of the bucket
+        over = lv && __shfl_sync(full, (uint32_t)v.y, (int)(G * 8u) + 7) != 0u;   // 32-bit word 30 of the bucket
         found = m != 0u;
         return id;
     };
@@ -186,56 +188,70 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
         for (int u = 0; u < INFLIGHT; u++) {
             const int src = (r0 + u) * 4 + (int)G;
             h[u] = __shfl_sync(full, mine, src);
-            const bool lv = ((wants >> src) & 1u) && h[u] != kEmptyKey;
+            const uint32_t b = __shfl_sync(full, myb, src);
+            const bool lv = (wants >> src) & 1u;
             live |= lv ? (1u << u) : 0u;
             v[u] = make_ulonglong2(0, 0);
-            if (lv) v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)bucket_of(h[u], t.n_buckets) * kBucketWords) + g);
+            if (lv) v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)b * kBucketWords) + g);
         }
 #pragma unroll
         for (int u = 0; u < INFLIGHT; u++) {
-            bool found, over;
-            const uint32_t id = look(v[u], h[u], found, over);
-            const int src = (r0 + u) * 4 + (int)G;
-            if ((live >> u) & 1u) {
-                if (g == 0u) reads++;
+            const bool lv = (live >> u) & 1u;
+            if (lv && g == 0u) reads++;
+            const bool hit = lv && g < 5u && (v[u].x == h[u] || v[u].y == h[u]);
+            const bool ovf = lv && g == 7u && (uint32_t)v[u].y != 0u;
+            if (__ballot_sync(full, hit | ovf)) {               // rare: some group matched a key or met an overflowed bucket
+                bool found, over;
+                const uint32_t id = resolve(v[u], h[u], lv, found, over);
+                if (!any_found && __ballot_sync(full, found)) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) res[q] = kNoEntry;
+                    any_found = 1;
+                }
                 if (found) res[r0 + u] = id;
                 else if (over) pend |= 1u << (r0 + u);
-            } else if (((wants >> src) & 1u) && h[u] == kEmptyKey) {
-                res[r0 + u] = t.special;
             }
         }
     }
     // chains: every group follows its own pending probes, one bucket per trip, all groups in step
-    int cr = -1;                                       // round being followed by this group (group-uniform)
-    uint32_t cstep = 0;                                // buckets past the home bucket
-    for (;;) {
-        if (cr < 0 && pend) {
-            cr = __ffs(pend) - 1;
-            pend &= pend - 1;
-            cstep = 1;
-        }
-        if (!__any_sync(full, cr >= 0)) break;
-        const int rr = cr < 0 ? 0 : cr;
-        const uint64_t hh = __shfl_sync(full, mine, rr * 4 + (int)G);
-        uint64_t cb = (uint64_t)bucket_of(hh, t.n_buckets) + cstep;
-        if (cb >= t.n_buckets) cb -= t.n_buckets;
-        ulonglong2 v = make_ulonglong2(0, 0);
-        if (cr >= 0) v = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)cb * kBucketWords) + g);
-        bool found, over;
-        const uint32_t id = look(v, hh, found, over);
-        if (cr >= 0) {
-            if (g == 0u) reads++;
-            if (found) {
+    if (__ballot_sync(full, pend != 0u)) {
+        int cr = -1;                                           // round being followed by this group (group-uniform)
+        uint32_t cstep = 0;                                    // buckets past the home bucket
+        for (;;) {
+            if (cr < 0 && pend) {
+                cr = __ffs(pend) - 1;
+                pend &= pend - 1;
+                cstep = 1;
+            }
+            if (!__any_sync(full, cr >= 0)) break;
+            const int rr = cr < 0 ? 0 : cr;
+            const uint64_t hh = __shfl_sync(full, mine, rr * 4 + (int)G);
+            uint64_t cb = (uint64_t)__shfl_sync(full, myb, rr * 4 + (int)G) + cstep;
+            if (cb >= t.n_buckets) cb -= t.n_buckets;
+            ulonglong2 v = make_ulonglong2(0, 0);
+            if (cr >= 0) v = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)cb * kBucketWords) + g);
+            bool found, over;
+            const uint32_t id = resolve(v, hh, cr >= 0, found, over);
+            if (!any_found && __ballot_sync(full, found)) {
 #pragma unroll
-                for (int q = 0; q < 8; q++) if (q == cr) res[q] = id;
-                cr = -1;
-            } else if (!over || cstep + 1 >= t.n_buckets) {
-                cr = -1;
-            } else {
-                cstep++;
+                for (int q = 0; q < 8; q++) res[q] = kNoEntry;
+                any_found = 1;
+            }
+            if (cr >= 0) {
+                if (g == 0u) reads++;
+                if (found) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) if (q == cr) res[q] = id;
+                    cr = -1;
+                } else if (!over || cstep + 1 >= t.n_buckets) {
+                    cr = -1;
+                } else {
+                    cstep++;
+                }
             }
         }
     }
+    if (!any_found) return special ? t.special : kNoEntry;     // warp-uniform: nothing to hand out
     // hand every lane the answer for its own hash: lane (r * 4 + G) <- group G's res[r]
     uint32_t out = kNoEntry;
 #pragma unroll
@@ -243,6 +259,7 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
         const uint32_t x = __shfl_sync(full, res[q], (int)((lane & 3u) * 8u));
         if ((int)(lane >> 2) == q) out = x;
     }
+    if (special) out = t.special;
     return want ? out : kNoEntry;
 }
 
@@ -487,19 +504,19 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_st
                             }
                             const bool want = valid && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key);
                             n_probe += want;
-                            const uint32_t id = coop_probe<4>(a.tab, h[u], want, n_reads);   // all 32 lanes, every trip
+                            const uint32_t id = coop_probe<8>(a.tab, h[u], want, n_reads);   // all 32 lanes, every trip
                             if (id != kNoEntry) {
                                 const uint32_t peers = __match_any_sync(__activemask(), id);
                                 if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id, (uint32_t)__popc(peers));
                                 n_hits++;
                             }
                         }
-                        continue;
-                    }
+                    } else {
 #pragma unroll
-                    for (int u = 0; u < kIlp; u++) {
-                        const int j = half * 16 + q + u;
-                        if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
+                        for (int u = 0; u < kIlp; u++) {
+                            const int j = half * 16 + q + u;
+                            if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
+                        }
                     }
                 }
             }
@@ -657,8 +674,8 @@ __global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_
 }
 
 // K2 alone: one hash per lane, the cooperative lookup above with all eight rounds of loads in flight.
-__global__ void __launch_bounds__(256) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
-                                               uint32_t *out_entry, unsigned long long *stats)
+__global__ void __launch_bounds__(128, 5) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
+                                                  uint32_t *out_entry, unsigned long long *stats)
 {
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t hits = 0, reads = 0;
@@ -750,7 +767,7 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
                          unsigned long long *stats, int sm_count, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_probe<<<grid_for(n, 256, (uint32_t)sm_count * 8u), 256, 0, st>>>(t, hashes, n, out_entry, stats);
+    k_probe<<<grid_for(n, 128, (uint32_t)sm_count * 20u), 128, 0, st>>>(t, hashes, n, out_entry, stats);
     return cudaGetLastError();
 }
 

@@ -180,41 +180,73 @@ def input_files(input_dir: str) -> Tuple[List[str], int]:
 
 # ---------------------------------------------------------------- the fused stage
 def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], threads: int = 8, max_p: float = 0.9,
-              merge: bool = False, device: int = 0, stdout=None) -> int:
-    """jobs: (DB.msh, SCREEN_TAB, FILTERED, SORTED, TOP_HITS, SELECTED) per sketch file."""
+              merge: bool = False, device: int = 0, stdout=None, stderr=None, server=None) -> int:
+    """jobs: (DB.msh, SCREEN_TAB, FILTERED, SORTED, TOP_HITS, SELECTED) per sketch file.
+    `server`: the resident table server when this runs inside it (tables and screens outlive the call)."""
     stdout = stdout or sys.stdout
+    stderr = stderr or sys.stderr
     from . import _lite as hs          # ctypes only: this is a one-shot process, numpy would be 15 % of it
 
     files, n_fna = input_files(input_dir)
-    for j in jobs:
+    # What can go wrong with the DATA goes wrong the way it does in the reference: scripts/mash.sh has no
+    # `set -e`, so a `mash screen` that fails (sketch file missing or malformed -- a deployment without the
+    # custom sketch3.msh is ordinary --, no *.fna, no sequence records) prints its ERROR, leaves an EMPTY
+    # screen.tab, and lines 15-55 still run on it: five empty files, the usual log, exit status 0
+    # (run_hymet_cami.sh:90,95 add `|| true` and `cat ... 2>/dev/null || true` on top).  Only the GPU
+    # path itself being unavailable is fatal here: no device, no library, a CUDA error.
+    results: Dict[int, bytes] = {i: b"" for i in range(len(jobs))}
+    usable = []
+    for i, j in enumerate(jobs):
         if not j[0].endswith(".msh"):
-            sys.stderr.write("ERROR: %s does not look like a sketch (.msh)\n" % j[0])
-            return 1
+            stderr.write("ERROR: %s does not look like a sketch (.msh)\n" % j[0])
+        else:
+            usable.append(i)
     try:
-        try:
-            groups = [(hs.LiteDb([j[0] for j in jobs], device), list(range(len(jobs))))]
-        except hs.HsError as e:
-            if "one at a time" not in e.msg:
-                raise
-            groups = None                      # sketch files with different k / seed: one table each
-        if groups is None:
-            groups = [(hs.LiteDb(j[0], device), [i]) for i, j in enumerate(jobs)]
-        results: Dict[int, bytes] = {}
-        for db, idx in groups:
-            scr = hs.LiteScreen(db)
-            if not files:                      # the shell would hand mash the unexpanded pattern
-                sys.stderr.write("ERROR: could not open %s for reading.\n" % os.path.join(input_dir, "*.fna"))
-                return 1
-            for p in files:
-                scr.feed_fasta(p, threads)
-            scr.flush()
-            if scr.stats()["n_records"] == 0:
-                sys.stderr.write("ERROR: Did not find sequence records in inputs.\n")
-                return 1
-            for seg, (b, e) in zip(idx, db.segments):
-                results[seg] = "".join(scr.finish_lines(False, 0.0, max_p, b, e)).encode("utf-8", "surrogateescape")
+        hs._abi.init(device)                   # no B200, no library: fail before anything is written (no CPU path)
+        groups = []
+        if usable:
+            try:
+                if server is not None:
+                    ent = server.table([jobs[i][0] for i in usable], tolerate=True)
+                    db = ent["db"]
+                else:
+                    ent, db = None, hs.LiteDb([jobs[i][0] for i in usable], device, tolerate=True)
+                for k_, msg in sorted(db.errors.items()):
+                    stderr.write("ERROR: %s\n" % msg)
+                if db.loaded:
+                    groups = [(db, [usable[k_] for k_ in db.loaded], ent)]
+            except hs.HsError as e:
+                if e.code in hs.DEVICE_ERRORS or "one at a time" not in e.msg:
+                    raise
+                # sketch files with different k / seed: one table each
+                for i in usable:
+                    try:
+                        ent = server.table([jobs[i][0]]) if server is not None else None
+                        groups.append((ent["db"] if ent else hs.LiteDb(jobs[i][0], device), [i], ent))
+                    except hs.HsError as e2:
+                        if e2.code in hs.DEVICE_ERRORS:
+                            raise
+                        stderr.write("ERROR: %s\n" % e2.msg)
+        if not files:                          # the shell would hand mash the unexpanded pattern
+            stderr.write("ERROR: could not open %s for reading.\n" % os.path.join(input_dir, "*.fna"))
+            groups = []
+        for db, idx, ent in groups:
+            try:
+                scr = server.screen_for(ent) if ent is not None else hs.LiteScreen(db)
+                for p in files:
+                    scr.feed_fasta(p, threads)
+                scr.flush()
+                if scr.stats()["n_records"] == 0:
+                    stderr.write("ERROR: Did not find sequence records in inputs.\n")
+                    continue
+                for seg, (b, e) in zip(idx, db.segments):
+                    results[seg] = "".join(scr.finish_lines(False, 0.0, max_p, b, e)).encode("utf-8", "surrogateescape")
+            except hs.HsError as e:
+                if e.code in hs.DEVICE_ERRORS:
+                    raise
+                stderr.write("ERROR: %s\n" % e.msg)
     except hs.HsError as e:
-        sys.stderr.write("ERROR: %s\n" % e.msg)
+        stderr.write("ERROR: %s\n" % e.msg)
         return 1
     selected = []
     for i, j in enumerate(jobs):
@@ -232,15 +264,40 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
     return 0
 
 
-def main(argv: Optional[List[str]] = None) -> int:
+def _via_server(argv: List[str]) -> Optional[int]:
+    """HYMET_SCREEN_SERVER=1|auto: let the resident table server run the stage (same files, same log)."""
+    from . import server
+    path = server.default_socket_path()
+    req = {"op": "stage", "argv": list(argv), "cwd": os.getcwd()}
+    try:
+        return server.request(path, req)
+    except OSError:
+        pass
+    if os.environ.get("HYMET_SCREEN_SERVER") != "auto":
+        return None
+    try:
+        server.spawn_detached(path, int(os.environ.get("HYMET_SCREEN_DEVICE", "0")))
+        return server.request(path, req)
+    except OSError as e:
+        sys.stderr.write("WARNING: no screen server (%s); running the stage in-process\n" % e)
+        return None
+
+
+def main(argv: Optional[List[str]] = None, stdout=None, stderr=None, cwd: Optional[str] = None, server=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
+    stdout = stdout or sys.stdout
+    stderr = stderr or sys.stderr
+    if server is None and os.environ.get("HYMET_SCREEN_SERVER", "0") not in ("", "0") and not any(a in ("-h", "--help") for a in argv):
+        rc = _via_server(argv)
+        if rc is not None:
+            return rc
     threads, merge, max_p = 8, False, 0.9
     pos: List[str] = []
     i = 0
     while i < len(argv):
         a = argv[i]
         if a in ("-h", "--help"):
-            sys.stdout.write(__doc__)
+            stdout.write(__doc__)
             return 0
         if a == "--merge":
             merge = True
@@ -251,22 +308,25 @@ def main(argv: Optional[List[str]] = None) -> int:
                 else:
                     max_p = float(argv[i + 1])
             except ValueError:
-                sys.stderr.write("ERROR: malformed numeric option value\n")
+                stderr.write("ERROR: malformed numeric option value\n")
                 return 1
             i += 1
         else:
             pos.append(a)
         i += 1
     if len(pos) < 8 or (len(pos) - 2) % 6:
-        sys.stderr.write(__doc__)
+        stderr.write(__doc__)
         return 2
     try:
         Decimal(pos[1])
     except Exception:
-        sys.stderr.write("ERROR: threshold must be a decimal number\n")
+        stderr.write("ERROR: threshold must be a decimal number\n")
         return 1
+    if cwd:      # served request: relative paths are the client's
+        pos = [p if (i == 1 or os.path.isabs(p)) else os.path.join(cwd, p) for i, p in enumerate(pos)]
     jobs = [pos[2 + 6 * g: 8 + 6 * g] for g in range((len(pos) - 2) // 6)]
-    return run_stage(pos[0], pos[1], jobs, threads, max_p, merge, int(os.environ.get("HYMET_SCREEN_DEVICE", "0")))
+    return run_stage(pos[0], pos[1], jobs, threads, max_p, merge, int(os.environ.get("HYMET_SCREEN_DEVICE", "0")),
+                     stdout=stdout, stderr=stderr, server=server)
 
 
 if __name__ == "__main__":

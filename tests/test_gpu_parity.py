@@ -667,6 +667,43 @@ def test_fused_mash_stage_equals_three_reference_runs(tmp_path):
     assert one == open(outs[2][0], "rb").read()
 
 
+def test_fused_stage_survives_missing_and_broken_sketch_files(tmp_path, golden_dir):
+    """run_hymet_cami.sh:85-97 with data/sketch3.msh absent and sketch2.msh unreadable: scripts/mash.sh has
+    no `set -e`, so the failed `mash screen` leaves an empty screen.tab, lines 15-55 still write their
+    (empty) files and log, and the run goes on with sketch1's candidates.  The fused stage must leave
+    exactly what the three UNMODIFIED mash.sh runs leave (oracle CLI as `mash`)."""
+    from hymet_b200 import stage
+    rng = np.random.default_rng(23)
+    paths, genomes = _three_dbs(tmp_path, rng)
+    open(paths[1], "wb").write(b"this is not a capnp message" * 10)       # sketch2: malformed
+    os.remove(paths[2])                                                   # sketch3: absent
+    indir = tmp_path / "input"; indir.mkdir()
+    (indir / "sample_0.fna").write_bytes(synth.to_fasta(synth.cut_contigs(rng, genomes[:30:2], 300_000, 0.01, median=5000.0), "s"))
+    script = reference_mash_sh(tmp_path, golden_dir)
+    orc.build()
+    tags = ("", "gtdb_", "custom_")
+    od = tmp_path / "out"; od.mkdir()
+    outs = [[str(od / (t + f)) for f in ("screen.tab", "filtered.tab", "sorted.tab", "top_hits.tab", "selected_genomes.txt")]
+            for t in tags]
+    argv = ["--merge", "-p", "4", str(indir), "0.9"]
+    for p, o in zip(paths, outs):
+        argv += [p] + o
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "hymet-mash-stage")] + argv, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert r.stderr.count(b"ERROR") >= 2
+    want_log, want_sel = "", []
+    for j, p in enumerate(paths):
+        got, log = run_mash_sh(tmp_path, script, orc.BIN, "ref%d" % j, indir, p, "0.9")
+        for path, data in zip(outs[j][:4], got[:4]):
+            assert open(path, "rb").read() == data, path
+        want_sel.append(got[4])
+        want_log += log
+    assert want_sel[1] == b"" and want_sel[2] == b"" and want_sel[0].count(b"\n") >= 3
+    assert open(outs[1][4], "rb").read() == b"" and open(outs[2][4], "rb").read() == b""
+    assert open(outs[0][4], "rb").read() == stage.merge_selected(want_sel)
+    assert r.stdout.decode() == want_log
+
+
 # ------------------------------------------------- row a6: plain FASTA files streamed through the pinned ring -------
 @pytest.mark.parametrize("variant", ["plain", "crlf_no_final_newline", "leading_blank_lines", "one_record"])
 def test_file_streaming_blocks_and_giant_records(tmp_path, variant):

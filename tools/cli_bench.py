@@ -56,6 +56,30 @@ def main():
                      "tsv_lines": p.stdout.count(b"\n")})
         gpu_tsv = p.stdout
     out["gpu_cli"] = runs
+    # the same command line against the resident table server (hymet_b200/server.py): first call builds
+    # the table inside the daemon, the following ones attach to it
+    sock = os.path.join(a.dir, "run", "gpu0.sock")
+    senv = dict(os.environ, HYMET_SCREEN_SERVER="1", HYMET_SCREEN_SOCKET=sock)
+    t0 = time.perf_counter()
+    subprocess.run([sys.executable, os.path.join(ROOT, "bin", "hymet-screen-server"), "start"], check=True, capture_output=True, env=senv)
+    out["server_start_s"] = time.perf_counter() - t0
+    served = []
+    try:
+        for r in range(a.reps + 1):
+            t0 = time.perf_counter()
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "mash"), "screen", "-p", str(threads), "-v", "0.9", dbp, fap],
+                               capture_output=True, env=dict(senv, HYMET_SCREEN_TIMING="1"))
+            dt = time.perf_counter() - t0
+            assert p.returncode == 0, p.stderr.decode()
+            served.append({"wall_s": dt, "what": "first call: table built inside the daemon" if r == 0 else "warm: table resident",
+                           "phases": [l for l in p.stderr.decode().splitlines() if l.startswith("[timing]")],
+                           "tsv_identical_to_in_process": p.stdout == gpu_tsv})
+        t0 = time.perf_counter()
+        subprocess.run([sys.executable, "-c", "pass"], check=True)
+        out["python_startup_s"] = time.perf_counter() - t0
+    finally:
+        subprocess.run([sys.executable, os.path.join(ROOT, "bin", "hymet-screen-server"), "stop"], capture_output=True, env=senv)
+    out["gpu_cli_via_server"] = served
     t0 = time.perf_counter()
     subprocess.run([sys.executable, "-c", "import numpy"], check=True)
     out["python_numpy_startup_s"] = time.perf_counter() - t0

@@ -486,6 +486,7 @@ def run_b200(args):
                "dense_range_fraction": db.info.dense_max / 2.0 ** 64, "keys_in_bloom_tier": int(db.info.bloom_keys),
                "table_build_s": db.info.t_build_s},
         "setup_s": t_setup,
+        "host": {"threads_visible_at_start": n_cpus, "threads_per_gpu": host_threads, **hs.host_placement()},
     }
     if world > 1:
         line["exchange"] = {"mode": scr.last_exchange, "pair_record_capacity": scr.cap, "largest_pair_count": st["exchange_max_pairs"],
@@ -595,21 +596,27 @@ def run_b200(args):
         fdir = tempfile.mkdtemp(prefix="hs_bench_%d_" % rank)
         fpath = os.path.join(fdir, "contigs.fna")
         wl.fasta.numpy().tofile(fpath)
-        readers = max(1, min(8, host_threads))
-        scr.set_option("file_readers", readers)
-        scr.set_option("file_block_bytes", 16 << 20)
-
         def step_file():
             scr.reset()
             scr.feed_fasta(fpath, host_threads)
             return scr.finish_hits(args.wta)
 
-        fms, fwall, fstats, fres, _ = timed(step_file, 3, 2)
-        line["e2e_file"] = {"value": 3 * total_bases / (fms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": fms / 3,
-                            "h2d_bytes_per_step": int(fstats[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(fstats[-1]["d2h_bytes"]),
-                            "input": "the same FASTA as a file in the page cache (%d B per GPU)" % wl.fasta.numel(),
-                            "reader_threads_per_gpu": readers,
-                            "ok": bool(results_equal(fres, res))}
+        best_file = None
+        for readers in sorted({max(1, min(8, host_threads)), max(1, min(16, host_threads))}):
+            scr.set_option("file_readers", readers)
+            scr.set_option("file_block_bytes", 16 << 20)
+            fms, fwall, fstats, fres, _ = timed(step_file, 3, 2)
+            ent = {"value": 3 * total_bases / (fms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": fms / 3,
+                   "h2d_bytes_per_step": int(fstats[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(fstats[-1]["d2h_bytes"]),
+                   "input": "the same FASTA as a file in the page cache (%d B per GPU)" % wl.fasta.numel(),
+                   "reader_threads_per_gpu": readers, "ok": bool(results_equal(fres, res))}
+            if best_file is None or ent["value"] > best_file["value"]:
+                ent["other_reader_counts"] = (best_file or {}).get("other_reader_counts", []) + \
+                    ([{"readers": best_file["reader_threads_per_gpu"], "value": best_file["value"]}] if best_file else [])
+                best_file = ent
+            else:
+                best_file.setdefault("other_reader_counts", []).append({"readers": readers, "value": ent["value"]})
+        line["e2e_file"] = best_file
         try:
             os.remove(fpath)
             os.rmdir(fdir)

@@ -58,6 +58,7 @@ SIGNATURES = {
     "hs_last_error": (C.c_char_p, []),
     "hs_init": (C.c_int, [C.c_int]),
     "hs_sm_count": (C.c_int, []),
+    "hs_host_placement": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hs_msh_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "hs_msh_info": (C.c_int, [C.c_void_p, C.POINTER(DbInfo)]),
     "hs_msh_ref": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u64p, u64p,

@@ -9,7 +9,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <ctype.h>
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -35,8 +37,9 @@ using namespace hs;
 namespace {
 
 thread_local std::string g_err;
-int g_device = -1;
-int g_sm = 0;
+// hs_init() binds the CALLING THREAD: one thread per GPU can each build its own db (HYMET_SCREEN_GPUS)
+thread_local int g_device = -1;
+thread_local int g_sm = 0;
 bool g_debug_timing = false;
 
 int fail(int code, const std::string &msg)
@@ -734,6 +737,60 @@ HS_API const char *hs_version(void) { return "hymet-screen-b200 0.1 (sm_100a)"; 
 HS_API const char *hs_last_error(void) { return g_err.c_str(); }
 HS_API int hs_sm_count(void) { return g_sm; }
 
+namespace {
+// Host side of the feed path: the packer/reader threads and the pinned buffers they fill should sit on
+// the NUMA node the GPU hangs off -- on a two-socket 8-GPU box a rank whose pinned text lives on the
+// other socket pulls it across the inter-socket link (round 1: 8 ranks together read host memory at
+// 174 GB/s, a third of what eight PCIe 5 x16 links carry).  Threads inherit the caller's affinity
+// and pinned pages are placed on first touch, so narrowing THIS thread's CPU set to the GPU's node
+// (never widening it, never leaving it empty) is enough.  HYMET_SCREEN_NUMA=0 leaves it alone.
+int g_numa_node = -1, g_numa_cpus = 0;
+void bind_to_gpu_numa_node(int device)
+{
+    g_numa_node = -1; g_numa_cpus = 0;
+    if (const char *e = getenv("HYMET_SCREEN_NUMA")) if (atoi(e) == 0) return;
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    if (node < 0) return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!ok) return;
+    cpu_set_t cur, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int k = sscanf(tok, "%d-%d", &a, &b);
+        if (k == 1) b = a;
+        if (k < 1) continue;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &cur)) CPU_SET(c, &want);
+    }
+    const int n = CPU_COUNT(&want);
+    if (n < 1 || n == CPU_COUNT(&cur)) { g_numa_node = node; g_numa_cpus = CPU_COUNT(&cur); return; }   // nothing to narrow
+    if (sched_setaffinity(0, sizeof want, &want) == 0) { g_numa_node = node; g_numa_cpus = n; }
+}
+}  // namespace
+
+HS_API int hs_host_placement(int *numa_node, int *cpus)
+{
+    if (numa_node) *numa_node = g_numa_node;
+    if (cpus) *cpus = g_numa_cpus;
+    return HS_OK;
+}
+
 HS_API int hs_init(int device)
 {
     int n = 0;
@@ -748,6 +805,7 @@ HS_API int hs_init(int device)
         return fail(HS_ENODEV, std::string("device ") + p.name + " is sm_" + std::to_string(p.major) + std::to_string(p.minor) +
                                    "; this build carries sm_100a code only");
     CU(cudaSetDevice(device));
+    if (g_device != device) bind_to_gpu_numa_node(device);
     g_device = device;
     g_sm = p.multiProcessorCount;
     g_debug_timing = getenv("HYMET_SCREEN_DEBUG_TIMING") != nullptr;
@@ -1254,11 +1312,16 @@ size_t find_record_start(const char *buf, size_t from, size_t n)
 // after its nominal begin and runs to the first record start at or after its nominal end, so
 // blocks are independent of each other) and handed to the device parser.  File -> page-cache
 // copy -> DMA -> parse/pack/hash on the GPU; no host-side parsing at all.
-int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
+// [range_begin, range_end) restricts the call to the records that START in that byte range (a record that
+// starts before range_end is read to its end, the one straddling range_begin belongs to whoever owns the
+// bytes before it), so N callers with adjacent ranges cover the file exactly once.
+int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads, uint64_t range_begin = 0, uint64_t range_end = ~0ull)
 {
     if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    range_end = std::min(range_end, size);
+    if (range_begin >= range_end) return HS_OK;
     const uint64_t B = s->file_block;
-    const uint64_t n_blocks = (size + B - 1) / B;
+    const uint64_t n_blocks = (range_end - range_begin + B - 1) / B;
     int T = std::max(1, std::min(threads, s->file_readers));
     if ((uint64_t)T > n_blocks) T = (int)n_blocks;
     const size_t cap = (size_t)(B + B / 2 + 4096);
@@ -1291,13 +1354,14 @@ int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads)
             char *buf = s->ring.base + slot * s->ring.slot_cap;
             if (cudaEventSynchronize(s->ring.free_ev[slot]) != cudaSuccess) { bail(fail(HS_ECUDA, "ring event")); break; }
             const double t0 = now_s();
-            const uint64_t off0 = j ? j * B - 1 : 0;          // one byte early: is there a newline before the block?
-            const uint64_t nominal_end = std::min(size, (j + 1) * B);
+            const uint64_t nominal_begin = range_begin + j * B;
+            const uint64_t off0 = nominal_begin ? nominal_begin - 1 : 0;   // one byte early: is there a newline before the block?
+            const uint64_t nominal_end = std::min(range_end, nominal_begin + B);
             size_t got = pread_full(fd, buf, (size_t)std::min<uint64_t>(size - off0, nominal_end - off0 + std::min<uint64_t>(65536, B / 4)), off0);
             if (off0 + got < nominal_end) { bail(fail(HS_EIO, "short read")); break; }
             // first record that starts inside this block (block 0 starts at the top of the file)
             size_t b = 0;
-            if (j) {
+            if (nominal_begin) {
                 b = find_record_start(buf, 1, (size_t)(nominal_end - off0));
                 if (b >= nominal_end - off0) continue;        // no record starts here: an earlier block owns these bytes
             }

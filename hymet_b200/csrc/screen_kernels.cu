@@ -173,7 +173,8 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
         const uint32_t pick = comp == 0 ? (uint32_t)v.x : comp == 1 ? (uint32_t)(v.x >> 32)
                             : comp == 2 ? (uint32_t)v.y : (uint32_t)(v.y >> 32);
         const uint32_t id = __shfl_sync(full, pick, (int)(G * 8u + ((w32 >> 2) & 7u)));
-        over = lv && __shfl_sync(full, (uint32_t)v.y, (int)(G * 8u) + 7) != 0u;   // 32-bit word 30 of the bucket
+        const uint32_t flag = __shfl_sync(full, (uint32_t)v.y, (int)(G * 8u) + 7);   // 32-bit word 30 of the bucket
+        over = lv && flag != 0u;               // (the shuffle is unconditional: every lane takes part in it)
         found = m != 0u;
         return id;
     };

@@ -344,6 +344,13 @@ class Screen:
             pass
 
 
+def host_placement() -> dict:
+    """Where hs_init left the calling thread: the GPU's NUMA node and the CPUs it may use."""
+    node, cpus = C.c_int(), C.c_int()
+    check(_abi.load().hs_host_placement(C.byref(node), C.byref(cpus)))
+    return {"numa_node": node.value, "cpus_after_numa_binding": cpus.value}
+
+
 # ---- single stages (parity tests, per-kernel measurement) ---------------------
 def packed_words(n_bases: int) -> int:
     return int(_abi.load().hs_packed_words(n_bases))

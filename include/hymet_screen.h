@@ -92,6 +92,10 @@ const char *hs_last_error(void);
  * A db and its screens stay on the device they were created on, so one process can drive
  * several GPUs: hs_init(0), build db 0, hs_init(1), build db 1, ... */
 int hs_init(int device);
+/* Where hs_init placed the calling thread: it narrows the thread's CPU affinity to the NUMA node the GPU
+ * hangs off (packer/reader threads inherit it, pinned buffers are first-touched there), unless
+ * HYMET_SCREEN_NUMA=0.  numa_node = -1: unknown or left alone; cpus = CPUs the thread may run on. */
+int hs_host_placement(int *numa_node, int *cpus);
 /* Number of SMs of the bound device (148 on B200); 0 before hs_init. */
 int hs_sm_count(void);
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "hs_screen_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hs_screen_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "hs_screen_feed_fasta": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "hs_screen_feed_fasta_range": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int]),
     "hs_screen_feed_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "hs_screen_feed_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     "hs_screen_feed_packed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
@@ -91,6 +92,7 @@ SIGNATURES = {
     "hs_screen_counts_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "hs_screen_counts_scatter_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "hs_screen_counts_absorb": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "hs_screen_absorb_screen": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hs_screen_mixture_get": (C.c_int, [C.c_void_p, u64p, u32p]),
     "hs_screen_mixture_record": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hs_screen_mixture_merge_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
@@ -149,13 +151,17 @@ def check(rc: int) -> None:
         raise HsError(rc, load().hs_last_error().decode("utf-8", "replace"))
 
 
-_initialised_device = None
+_tls = None
 
 
 def init(device: int = 0) -> None:
-    """Bind the process to one B200.  Raises HsError(HS_ENODEV) when there is none."""
-    global _initialised_device
-    if _initialised_device == device:
+    """Bind the CALLING THREAD to one B200 (hs_init is per thread: one thread per GPU can each own a
+    database).  Raises HsError(HS_ENODEV) when there is none."""
+    global _tls
+    if _tls is None:
+        import threading
+        _tls = threading.local()
+    if getattr(_tls, "device", None) == device:
         return
     check(load().hs_init(device))
-    _initialised_device = device
+    _tls.device = device

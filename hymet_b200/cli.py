@@ -113,9 +113,16 @@ def screen_main(args: List[str], stdout=None, stderr=None, cwd: Optional[str] = 
                 return 1
             ent = server.table([db_path])                # resident: built on first use only
             db, scr = ent["db"], server.screen_for(ent)
+            multi = None
         else:
-            db = hs.LiteDb(db_path, device)              # CUDA context creation overlaps the .msh parse
-            scr = hs.LiteScreen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
+            # HYMET_SCREEN_GPUS=N: N GPUs of this box, one table copy each, the inputs cut by bytes
+            n_gpus = max(1, int(os.environ.get("HYMET_SCREEN_GPUS", "1") or "1"))
+            multi = hs.MultiGpu(db_path, range(device, device + n_gpus)) if n_gpus > 1 else None
+            if multi is not None:
+                db = multi.db
+            else:
+                db = hs.LiteDb(db_path, device)          # CUDA context creation overlaps the .msh parse
+                scr = hs.LiteScreen(db, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
         mark("cuda_init + load_db(parse %.3f build %.3f)" % (db.info.t_parse_s, db.info.t_build_s))
         stderr.write("   %d distinct hashes.\n" % db.n_distinct)
         stderr.write("Streaming from %s...\n" % (inputs[0] if len(inputs) == 1 else "%d inputs" % len(inputs)))
@@ -123,7 +130,11 @@ def screen_main(args: List[str], stdout=None, stderr=None, cwd: Optional[str] = 
             if p != "-" and not os.path.exists(p):
                 _e("could not open %s for reading." % p)
                 return 1
-            scr.feed_fasta(p, threads)
+        if multi is not None:
+            scr = multi.screen(inputs, threads, probe_filter=os.environ.get("HYMET_SCREEN_FILTER", "1") != "0")
+        else:
+            for p in inputs:
+                scr.feed_fasta(p, threads)
         mark("feed")
         scr.flush()
         mark("flush")

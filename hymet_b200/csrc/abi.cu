@@ -1492,6 +1492,29 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
     return rc;
 }
 
+HS_API int hs_screen_feed_fasta_range(hs_screen *s, const char *path, uint64_t begin, uint64_t end, int host_threads)
+{
+    if (!s || !path) return fail(HS_EINVAL, "null argument");
+    ON_DEVICE(s->db->device);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(HS_EIO, std::string("could not open ") + path);
+    struct stat sb;
+    char head[256];
+    size_t hn = 0, first = 0;
+    const bool regular = fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0;
+    if (regular) {
+        hn = pread_full(fd, head, sizeof head, 0);
+        while (first < hn && (head[first] == '\n' || head[first] == '\r')) first++;
+    }
+    if (!regular || first >= hn || head[first] != '>') {
+        close(fd);
+        return fail(HS_EUNSUPPORTED, "byte ranges need a plain FASTA file (gzip, FASTQ and pipes cannot be cut): feed it whole");
+    }
+    const int rc = feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads, begin, end);
+    close(fd);
+    return rc;
+}
+
 HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint32_t *inv, uint64_t n_bases)
 {
     if (!s || ((!seq2 || !inv) && n_bases)) return fail(HS_EINVAL, "null argument");
@@ -1620,6 +1643,59 @@ HS_API int hs_screen_counts_absorb(hs_screen *s, const void *d_rows, uint32_t n_
     CU(launch_counts_absorb(sp, s->d_counts, s->db->n_entries, (const unsigned long long *)d_rows, n_rows, cap, skip_row,
                             s->db->sm, s->stream));
     s->st.n_launches++;
+    return HS_OK;
+}
+
+HS_API int hs_screen_absorb_screen(hs_screen *dst, hs_screen *src)
+{
+    if (!dst || !src || dst == src) return fail(HS_EINVAL, "two different screens are needed");
+    if (!dst->flushed || !src->flushed) return fail(HS_ESTATE, "flush both screens first");
+    if (dst->db->n_entries != src->db->n_entries || dst->db->k != src->db->k || dst->db->s != src->db->s)
+        return fail(HS_EINVAL, "the two screens are not over the same sketch database");
+    // src's non-zero counts as (entry id, count) pairs on ITS device, copied device to device (NVLink peer
+    // copy when the GPUs are peers), added on dst's device: the in-process form of the multi-GPU exchange
+    const uint64_t E = src->db->n_entries;
+    ON_DEVICE(src->db->device);
+    uint32_t n = 0;
+    unsigned long long *sp = nullptr, *dp = nullptr;
+    {
+        uint32_t *d_n = src->mix.field(offsetof(MixState, n_out));
+        CU(cudaMemcpyAsync(src->h_sparse, src->d_sparse, sizeof(SparseState), cudaMemcpyDeviceToHost, src->stream));
+        CU(cudaStreamSynchronize(src->stream));
+        const bool listed = src->sparse_enabled && src->touched_valid && src->h_sparse->n_touched <= src->touched_cap;
+        const uint64_t cap = listed ? src->h_sparse->n_touched : E;
+        if (cap) {
+            CU(cudaMalloc((void **)&sp, cap * 8));
+            int rc = hs_screen_counts_compact_async(src, sp, (uint32_t)cap, d_n);
+            if (rc) { cudaFree(sp); return rc; }
+            CU(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, src->stream));
+            CU(cudaStreamSynchronize(src->stream));
+        }
+    }
+    int rc = HS_OK;
+    if (n) {
+        if (cudaSetDevice(dst->db->device) != cudaSuccess || cudaMalloc((void **)&dp, (size_t)n * 8) != cudaSuccess) {
+            cudaSetDevice(src->db->device); cudaFree(sp);
+            return fail(HS_ECUDA, "allocation for the pair exchange failed");
+        }
+        cudaError_t e = cudaMemcpyPeerAsync(dp, dst->db->device, sp, src->db->device, (size_t)n * 8, dst->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
+        if (e != cudaSuccess) rc = fail(HS_ECUDA, std::string("peer copy of the count pairs: ") + cudaGetErrorString(e));
+        if (rc == HS_OK) rc = hs_screen_counts_scatter_add(dst, dp, n);
+        if (rc == HS_OK && cudaStreamSynchronize(dst->stream) != cudaSuccess) rc = fail(HS_ECUDA, "scatter-add of the count pairs failed");
+        cudaFree(dp);
+    }
+    cudaSetDevice(src->db->device);
+    cudaFree(sp);
+    if (rc) return rc;
+    rc = hs_screen_mixture_merge(dst, src->mixture.data(), (uint32_t)src->mixture.size());
+    if (rc) return rc;
+    dst->st.n_bases += src->st.n_bases; dst->st.n_records += src->st.n_records; dst->st.n_positions += src->st.n_positions;
+    dst->st.n_valid_kmers += src->st.n_valid_kmers; dst->st.n_probes += src->st.n_probes;
+    dst->st.n_bucket_reads += src->st.n_bucket_reads; dst->st.n_hits += src->st.n_hits;
+    dst->st.n_mix_inserts += src->st.n_mix_inserts; dst->st.h2d_bytes += src->st.h2d_bytes;
+    dst->st.n_launches += src->st.n_launches;
+    dst->st.ms_stream = std::max(dst->st.ms_stream, src->st.ms_stream);
     return HS_OK;
 }
 

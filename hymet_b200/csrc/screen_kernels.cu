@@ -136,31 +136,62 @@ __device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts
     }
 }
 
-// Warp-cooperative table lookup of ONE HASH PER LANE (K2's "warp-cooperative bucket probe").
+// Warp-cooperative table lookup of NH HASHES PER LANE (K2's "warp-cooperative bucket probe").
 // Eight lanes read one 128-byte bucket with one 16-byte load each -- a single coalesced line per
 // probe, one L1 wavefront instead of the 32 a per-thread load of a random line costs -- so a warp
-// works on four probes per round and needs eight rounds for its 32 hashes; the loads of INFLIGHT
-// rounds are issued before the first compare.  Lanes 0-4 of a group hold the ten keys, lanes 5-7 the
-// ids and the overflow flag.  The common round (no key matches, no bucket overflowed) is two
-// compares and two votes; matches and overflows are resolved in a warp-uniform slow path, and a
-// probe whose home bucket overflowed (1.4 % at load 0.5) is not chased on the spot by one lane while
-// 31 wait for a DRAM round trip: the warp follows all such chains together after the main rounds.
-// Must be called by all 32 lanes (convergent).  Returns the canonical entry id of this lane's hash
-// (kNoEntry: absent, or want == false); `reads` counts bucket lines on the group-leader lanes.
-template <int INFLIGHT>
-__device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine, bool want, uint32_t &reads)
+// works on four probes per round and needs 8 * NH rounds for its 32 * NH hashes.  ALL rounds' loads
+// are issued before the first compare (the kernel waits on HBM latency: lines in flight are what
+// counts), and only the LOW WORDS of what came back are kept -- two registers per round -- which is
+// all the common case needs: lanes 0-4 of a group hold the ten keys, lane 7 the overflow flag, and a
+// round in which no low word matches and no flag is set (nearly all of them) is one vote.  Possible
+// matches and overflowed buckets re-read their line (L1/L2 hit) in a warp-uniform slow path that
+// compares whole keys and fetches the id from lanes 5-7; a probe whose home bucket overflowed (1.4 %
+// at load 0.5) is not chased on the spot by one lane while 31 wait for a DRAM round trip: the warp
+// follows all such chains together, four at a time, after the main rounds.
+// Must be called by all 32 lanes (convergent).  out[i] = canonical entry id of mine[i] (kNoEntry:
+// absent, or want[i] == false); `reads` counts bucket lines read for wanted probes (lane 0 / leaders).
+template <int NH>
+__device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&mine)[NH], const bool (&want)[NH],
+                                           uint32_t (&out)[NH], uint32_t &reads)
 {
-    static_assert(INFLIGHT == 4 || INFLIGHT == 8, "rounds in flight");
+    static_assert(NH >= 1 && NH <= 4, "up to 32 rounds: one bit each in the pending mask");
+    constexpr int R = 8 * NH;
     const uint32_t lane = threadIdx.x & 31u, g = lane & 7u, G = lane >> 3, full = 0xffffffffu;
-    const bool special = want && mine == kEmptyKey;           // never stored in a bucket: answered from the view
-    const uint32_t wants = __ballot_sync(full, want && !special);
-    if (!wants) return special ? t.special : kNoEntry;         // warp-uniform
-    const uint32_t myb = bucket_of(mine, t.n_buckets);
-    uint32_t res[8];                                           // per round; only touched when something was found
-    uint32_t pend = 0, any_found = 0;                          // group-uniform / warp-uniform
+    bool special[NH];
+    uint32_t wants[NH], myb[NH], any_want = 0;
+#pragma unroll
+    for (int i = 0; i < NH; i++) {
+        special[i] = want[i] && mine[i] == kEmptyKey;          // never stored in a bucket: answered from the view
+        wants[i] = __ballot_sync(full, want[i] && !special[i]);
+        any_want |= wants[i];
+        out[i] = special[i] ? t.special : kNoEntry;
+    }
+    if (!any_want) return;                                     // warp-uniform
+    // A lane that wants nothing is probed all the same (its bucket index is a valid address whatever its
+    // hash holds) and its answer dropped at the end: the rounds below carry no per-lane liveness logic.
+#pragma unroll
+    for (int i = 0; i < NH; i++) {
+        myb[i] = bucket_of(mine[i], t.n_buckets);
+        if (lane == 0) reads += (uint32_t)__popc(wants[i]);
+    }
+    const ulonglong2 *line0 = reinterpret_cast<const ulonglong2 *>(t.buckets) + g;   // this lane's 16 bytes of bucket 0
 
-    // resolve one bucket line for the group's probe (slow path): id if a key matched, overflow flag
-    auto resolve = [&](const ulonglong2 &v, uint64_t h, bool lv, bool &found, bool &over) -> uint32_t {
+    uint32_t hlo[R];
+    uint2 klo[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int src = (r & 7) * 4 + (int)G;
+        hlo[r] = __shfl_sync(full, (uint32_t)mine[r >> 3], src);
+        const uint32_t b = __shfl_sync(full, myb[r >> 3], src);
+        const ulonglong2 v = __ldg(line0 + (size_t)b * (kBucketWords / 2));
+        klo[r] = make_uint2((uint32_t)v.x, (uint32_t)v.y);
+    }
+
+    uint32_t res[R];                                           // only touched when something was found
+    uint32_t pend = 0, any_found = 0;                          // group-uniform / warp-uniform
+    // slow path: the whole line of bucket b for the group's probe of hash h -- id if a key matches, overflow flag
+    auto resolve = [&](uint32_t b, uint64_t h, bool lv, bool &found, bool &over) -> uint32_t {
+        const ulonglong2 v = __ldg(line0 + (size_t)b * (kBucketWords / 2));
         int slot = -1;
         if (lv && g < 5u) {
             if (v.x == h) slot = 2 * (int)g;
@@ -178,40 +209,32 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
         found = m != 0u;
         return id;
     };
-
-#pragma unroll 1
-    for (int r0 = 0; r0 < 8; r0 += INFLIGHT) {
-        if (!((wants >> (4 * r0)) & ((INFLIGHT == 8) ? 0xFFFFFFFFu : 0xFFFFu))) continue;   // warp-uniform
-        uint64_t h[INFLIGHT];
-        uint32_t live = 0;
-        ulonglong2 v[INFLIGHT];
+    auto note = [&](int r, bool found, bool over, uint32_t id) {
+        if (!any_found && __ballot_sync(full, found)) {
 #pragma unroll
-        for (int u = 0; u < INFLIGHT; u++) {
-            const int src = (r0 + u) * 4 + (int)G;
-            h[u] = __shfl_sync(full, mine, src);
-            const uint32_t b = __shfl_sync(full, myb, src);
-            const bool lv = (wants >> src) & 1u;
-            live |= lv ? (1u << u) : 0u;
-            v[u] = make_ulonglong2(0, 0);
-            if (lv) v[u] = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)b * kBucketWords) + g);
+            for (int q = 0; q < R; q++) res[q] = kNoEntry;
+            any_found = 1;
         }
+        if (found) {
 #pragma unroll
-        for (int u = 0; u < INFLIGHT; u++) {
-            const bool lv = (live >> u) & 1u;
-            if (lv && g == 0u) reads++;
-            const bool hit = lv && g < 5u && (v[u].x == h[u] || v[u].y == h[u]);
-            const bool ovf = lv && g == 7u && (uint32_t)v[u].y != 0u;
-            if (__ballot_sync(full, hit | ovf)) {               // rare: some group matched a key or met an overflowed bucket
-                bool found, over;
-                const uint32_t id = resolve(v[u], h[u], lv, found, over);
-                if (!any_found && __ballot_sync(full, found)) {
+            for (int q = 0; q < R; q++) if (q == r) res[q] = id;
+        } else if (over) {
+            pend |= 1u << r;
+        }
+    };
+
+    const bool key_lane = g < 5u, flag_lane = g == 7u;
 #pragma unroll
-                    for (int q = 0; q < 8; q++) res[q] = kNoEntry;
-                    any_found = 1;
-                }
-                if (found) res[r0 + u] = id;
-                else if (over) pend |= 1u << (r0 + u);
-            }
+    for (int r = 0; r < R; r++) {
+        const bool maybe = key_lane ? (klo[r].x == hlo[r] || klo[r].y == hlo[r]) : (flag_lane && klo[r].y != 0u);
+        if (__any_sync(full, maybe)) {                          // rare: a key may match, or a bucket overflowed
+            const int src = (r & 7) * 4 + (int)G;
+            const uint64_t h = __shfl_sync(full, mine[r >> 3], src);
+            const uint32_t b = __shfl_sync(full, myb[r >> 3], src);
+            const bool lv = (wants[r >> 3] >> src) & 1u;
+            bool found, over;
+            const uint32_t id = resolve(b, h, lv, found, over);
+            note(r, found, over, id);
         }
     }
     // chains: every group follows its own pending probes, one bucket per trip, all groups in step
@@ -226,42 +249,40 @@ __device__ __forceinline__ uint32_t coop_probe(const TableView &t, uint64_t mine
             }
             if (!__any_sync(full, cr >= 0)) break;
             const int rr = cr < 0 ? 0 : cr;
-            const uint64_t hh = __shfl_sync(full, mine, rr * 4 + (int)G);
-            uint64_t cb = (uint64_t)__shfl_sync(full, myb, rr * 4 + (int)G) + cstep;
-            if (cb >= t.n_buckets) cb -= t.n_buckets;
-            ulonglong2 v = make_ulonglong2(0, 0);
-            if (cr >= 0) v = __ldg(reinterpret_cast<const ulonglong2 *>(t.buckets + (size_t)cb * kBucketWords) + g);
-            bool found, over;
-            const uint32_t id = resolve(v, hh, cr >= 0, found, over);
-            if (!any_found && __ballot_sync(full, found)) {
+            const int src = (rr & 7) * 4 + (int)G;
+            uint64_t hh = 0;
+            uint32_t hb = 0;
 #pragma unroll
-                for (int q = 0; q < 8; q++) res[q] = kNoEntry;
-                any_found = 1;
+            for (int i = 0; i < NH; i++) {                     // (rr >> 3 differs between groups: every lane shuffles every hash)
+                const uint64_t x = __shfl_sync(full, mine[i], src);
+                const uint32_t y = __shfl_sync(full, myb[i], src);
+                if ((rr >> 3) == i) { hh = x; hb = y; }
             }
-            if (cr >= 0) {
-                if (g == 0u) reads++;
-                if (found) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) if (q == cr) res[q] = id;
-                    cr = -1;
-                } else if (!over || cstep + 1 >= t.n_buckets) {
-                    cr = -1;
-                } else {
-                    cstep++;
-                }
+            uint64_t cb = (uint64_t)hb + cstep;
+            if (cb >= t.n_buckets) cb -= t.n_buckets;
+            bool found, over;
+            const uint32_t id = resolve((uint32_t)cb, hh, cr >= 0, found, over);
+            if (cr >= 0 && g == 0u) reads++;
+            const bool was = cr >= 0;
+            note(rr, was && found, false, id);
+            if (was) {
+                if (found || !over || cstep + 1 >= t.n_buckets) cr = -1;
+                else cstep++;
             }
         }
     }
-    if (!any_found) return special ? t.special : kNoEntry;     // warp-uniform: nothing to hand out
-    // hand every lane the answer for its own hash: lane (r * 4 + G) <- group G's res[r]
-    uint32_t out = kNoEntry;
+    if (!any_found) return;                                    // warp-uniform: nothing to hand out
+    // hand every lane the answers for its own hashes: lane (r * 4 + G) <- group G's res[8 i + r]
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-        const uint32_t x = __shfl_sync(full, res[q], (int)((lane & 3u) * 8u));
-        if ((int)(lane >> 2) == q) out = x;
+    for (int i = 0; i < NH; i++) {
+        uint32_t o = kNoEntry;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t x = __shfl_sync(full, res[8 * i + q], (int)((lane & 3u) * 8u));
+            if ((int)(lane >> 2) == q) o = x;
+        }
+        if (want[i] && !special[i]) out[i] = o;
     }
-    if (special) out = t.special;
-    return want ? out : kNoEntry;
 }
 
 __device__ __forceinline__ void mix_insert(const MixView &m, uint64_t *set, uint64_t h)
@@ -495,22 +516,32 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_st
                         }
                     }
                     if (COOP) {
+                        bool valid[kIlp];
 #pragma unroll
                         for (int u = 0; u < kIlp; u++) {
                             const int j = half * 16 + q + u;
-                            const bool valid = (ok >> (31 - j)) & 1u;
-                            if (valid && a.do_mix && h[u] <= mix_tau) {
+                            valid[u] = (ok >> (31 - j)) & 1u;
+                            if (valid[u] && a.do_mix && h[u] <= mix_tau) {
                                 n_mix++;
                                 mix_insert(a.mix, mix_set, h[u]);
                             }
-                            const bool want = valid && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key);
-                            n_probe += want;
-                            const uint32_t id = coop_probe<8>(a.tab, h[u], want, n_reads);   // all 32 lanes, every trip
-                            if (id != kNoEntry) {
-                                const uint32_t peers = __match_any_sync(__activemask(), id);
-                                if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id, (uint32_t)__popc(peers));
-                                n_hits++;
-                            }
+                        }
+                        static_assert(kIlp % 2 == 0, "the cooperative lookup takes the k-mers two at a time");
+#pragma unroll
+                        for (int u = 0; u < kIlp; u += 2) {     // all 32 lanes, every trip: 64 probes, 16 lines in flight per lane
+                            const uint64_t hh[2] = {h[u], h[u + 1]};
+                            const bool want[2] = {valid[u] && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key),
+                                                  valid[u + 1] && a.do_count && (!a.do_filter || h[u + 1] <= a.tab.max_key)};
+                            uint32_t id[2];
+                            n_probe += (uint32_t)want[0] + (uint32_t)want[1];
+                            coop_probe<2>(a.tab, hh, want, id, n_reads);
+#pragma unroll
+                            for (int w2 = 0; w2 < 2; w2++)
+                                if (id[w2] != kNoEntry) {
+                                    const uint32_t peers = __match_any_sync(__activemask(), id[w2]);
+                                    if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id[w2], (uint32_t)__popc(peers));
+                                    n_hits++;
+                                }
                         }
                     } else {
 #pragma unroll
@@ -674,7 +705,8 @@ __global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(n_distinct, (unsigned long long)local);
 }
 
-// K2 alone: one hash per lane, the cooperative lookup above with all eight rounds of loads in flight.
+// K2 alone: two hashes per lane (64 probes per warp and trip, 16 lines in flight per lane).
+constexpr int kProbeNH = 2;
 __global__ void __launch_bounds__(128, 5) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
                                                   uint32_t *out_entry, unsigned long long *stats)
 {
@@ -682,14 +714,22 @@ __global__ void __launch_bounds__(128, 5) k_probe(const TableView t, const uint6
     uint32_t hits = 0, reads = 0;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t base = warp * 32; base < n; base += n_warps * 32) {
-        const bool have = base + lane < n;
-        const uint64_t mine = have ? __ldg(hashes + base + lane) : 0ull;
-        const uint32_t id = coop_probe<8>(t, mine, have, reads);
-        if (have) {
-            if (out_entry) out_entry[base + lane] = id;
-            hits += id != kNoEntry;
+    for (uint64_t base = warp * (32 * kProbeNH); base < n; base += n_warps * (32 * kProbeNH)) {
+        uint64_t mine[kProbeNH];
+        bool have[kProbeNH];
+        uint32_t id[kProbeNH];
+#pragma unroll
+        for (int i = 0; i < kProbeNH; i++) {
+            have[i] = base + 32 * i + lane < n;
+            mine[i] = have[i] ? __ldg(hashes + base + 32 * i + lane) : 0ull;
         }
+        coop_probe<kProbeNH>(t, mine, have, id, reads);
+#pragma unroll
+        for (int i = 0; i < kProbeNH; i++)
+            if (have[i]) {
+                if (out_entry) out_entry[base + 32 * i + lane] = id[i];
+                hits += id[i] != kNoEntry;
+            }
     }
     hits = warp_sum(hits); reads = warp_sum(reads);
     if (lane == 0) {
@@ -768,7 +808,7 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
                          unsigned long long *stats, int sm_count, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_probe<<<grid_for(n, 128, (uint32_t)sm_count * 20u), 128, 0, st>>>(t, hashes, n, out_entry, stats);
+    k_probe<<<grid_for((n + kProbeNH - 1) / kProbeNH, 128, (uint32_t)sm_count * 20u), 128, 0, st>>>(t, hashes, n, out_entry, stats);
     return cudaGetLastError();
 }
 

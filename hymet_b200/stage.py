@@ -195,6 +195,7 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
     # (run_hymet_cami.sh:90,95 add `|| true` and `cat ... 2>/dev/null || true` on top).  Only the GPU
     # path itself being unavailable is fatal here: no device, no library, a CUDA error.
     results: Dict[int, bytes] = {i: b"" for i in range(len(jobs))}
+    n_gpus = max(1, int(os.environ.get("HYMET_SCREEN_GPUS", "1") or "1"))
     usable = []
     for i, j in enumerate(jobs):
         if not j[0].endswith(".msh"):
@@ -206,15 +207,19 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
         groups = []
         if usable:
             try:
+                mg = None
                 if server is not None:
                     ent = server.table([jobs[i][0] for i in usable], tolerate=True)
                     db = ent["db"]
+                elif n_gpus > 1:                   # HYMET_SCREEN_GPUS: one table copy per GPU, inputs cut by bytes
+                    mg = hs.MultiGpu([jobs[i][0] for i in usable], range(device, device + n_gpus), tolerate=True)
+                    ent, db = None, mg.db
                 else:
                     ent, db = None, hs.LiteDb([jobs[i][0] for i in usable], device, tolerate=True)
                 for k_, msg in sorted(db.errors.items()):
                     stderr.write("ERROR: %s\n" % msg)
                 if db.loaded:
-                    groups = [(db, [usable[k_] for k_ in db.loaded], ent)]
+                    groups = [(db, [usable[k_] for k_ in db.loaded], ent, mg)]
             except hs.HsError as e:
                 if e.code in hs.DEVICE_ERRORS or "one at a time" not in e.msg:
                     raise
@@ -222,7 +227,7 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
                 for i in usable:
                     try:
                         ent = server.table([jobs[i][0]]) if server is not None else None
-                        groups.append((ent["db"] if ent else hs.LiteDb(jobs[i][0], device), [i], ent))
+                        groups.append((ent["db"] if ent else hs.LiteDb(jobs[i][0], device), [i], ent, None))
                     except hs.HsError as e2:
                         if e2.code in hs.DEVICE_ERRORS:
                             raise
@@ -230,12 +235,15 @@ def run_stage(input_dir: str, threshold: str, jobs: Sequence[Sequence[str]], thr
         if not files:                          # the shell would hand mash the unexpanded pattern
             stderr.write("ERROR: could not open %s for reading.\n" % os.path.join(input_dir, "*.fna"))
             groups = []
-        for db, idx, ent in groups:
+        for db, idx, ent, mg in groups:
             try:
-                scr = server.screen_for(ent) if ent is not None else hs.LiteScreen(db)
-                for p in files:
-                    scr.feed_fasta(p, threads)
-                scr.flush()
+                if mg is not None:
+                    scr = mg.screen(files, threads)
+                else:
+                    scr = server.screen_for(ent) if ent is not None else hs.LiteScreen(db)
+                    for p in files:
+                        scr.feed_fasta(p, threads)
+                    scr.flush()
                 if scr.stats()["n_records"] == 0:
                     stderr.write("ERROR: Did not find sequence records in inputs.\n")
                     continue

@@ -87,8 +87,8 @@ typedef struct {
 /* ---- library ------------------------------------------------------------ */
 const char *hs_version(void);
 const char *hs_last_error(void);
-/* Select CUDA device `device` (ordinal) for the handles created from now on and for the
- * handle-less entry points.  Fails with HS_ENODEV unless the device is compute capability 10.x.
+/* Select CUDA device `device` (ordinal) for the handles THIS THREAD creates from now on and for the
+ * handle-less entry points it calls.  Fails with HS_ENODEV unless the device is compute capability 10.x.
  * A db and its screens stay on the device they were created on, so one process can drive
  * several GPUs: hs_init(0), build db 0, hs_init(1), build db 1, ... */
 int hs_init(int device);
@@ -153,6 +153,10 @@ int hs_screen_set_option(hs_screen *s, const char *key, int64_t value);
  * parsed, packed and hashed on the GPU; gzip, FASTQ and stdin are packed on the host into
  * pinned 2-bit buffers with `host_threads` threads while the GPU consumes. */
 int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads);
+/* The records of a plain FASTA file that START in the byte range [begin, end): N callers with adjacent
+ * ranges (N GPUs in one process, or N ranks) cover the file exactly once and no k-mer spans two of them.
+ * HS_EUNSUPPORTED for gzip / FASTQ / pipes, which cannot be cut: feed those whole to one screen. */
+int hs_screen_feed_fasta_range(hs_screen *s, const char *path, uint64_t begin, uint64_t end, int host_threads);
 /* Same, text already in host memory. */
 int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads);
 /* Pre-packed HOST buffers (layout: hs_packed_words()).  n_bases positions. */
@@ -201,6 +205,11 @@ int hs_screen_counts_scatter_add(hs_screen *s, const void *d_pairs, uint64_t n_p
  * nothing is added and hs_stats_t.exchange_overflow is set by the next hs_screen_finish -- every rank
  * sees the same records, so every rank takes the same decision.  No host synchronisation. */
 int hs_screen_counts_absorb(hs_screen *s, const void *d_rows, uint32_t n_rows, uint32_t cap, uint32_t skip_row);
+/* Several GPUs in ONE process (HYMET_SCREEN_GPUS): after both are flushed, add src's counts and mixture
+ * into dst -- src's (entry id, count) pairs travel device to device (peer copy over NVLink when the GPUs
+ * are peers).  The two screens must be over the same sketch database (one copy per GPU).  dst then
+ * finishes for everybody. */
+int hs_screen_absorb_screen(hs_screen *dst, hs_screen *src);
 int hs_screen_mixture_get(hs_screen *s, uint64_t *hashes /*[s]*/, uint32_t *n);
 /* Mixture exchange without the host: write this rank's record [length | s hashes, zero padded]
  * ((s + 1) 64-bit words, DEVICE memory) after flush; after the all-gather, merge n_rows such records

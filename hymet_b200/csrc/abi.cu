@@ -412,7 +412,7 @@ struct FilterPlan { uint64_t dense_max; uint64_t words; double keys_above; bool 
 FilterPlan plan_filter(const hs_db *db, const uint64_t *hashes)
 {
     FilterPlan best{db->max_key, 0, 0.0, false};
-    const double kSpace = 18446744073709551616.0, kProbeCost = 8.0, kBloomCost = 1.0, kMaxBits = 64.0 * 8 * 1048576;
+    const double kSpace = 18446744073709551616.0, kProbeCost = 8.0, kBloomCost = 1.0, kMaxBits = 32.0 * 8 * 1048576;   // <= 32 MB: it has to stay in L2 next to the streaming query (64 MB: 16 % of its reads went to DRAM, ncu r02)
     struct R { double mx, size; };
     std::vector<R> r;
     for (uint64_t i = 0; i < db->n_refs; i++)
@@ -432,7 +432,7 @@ FilterPlan plan_filter(const hs_db *db, const uint64_t *hashes)
         const double T = r[i].mx;
         const double above = std::max(0.0, ss[i + 1] - T * sr[i + 1]);
         double bits = 4096.0 * 32;
-        while (bits < above * 24.0 && bits < kMaxBits) bits *= 2;
+        while (bits < above * 16.0 && bits < kMaxBits) bits *= 2;
         const double fp = pow(1.0 - exp(-3.0 * above / bits), 3.0) * 1.5;   // blocked filter: somewhat worse than the textbook rate
         const double p_direct = T / kSpace, p_bloom = ((double)db->max_key - T) / kSpace;
         const double cost = p_direct * kProbeCost + p_bloom * (kBloomCost + fp * kProbeCost);

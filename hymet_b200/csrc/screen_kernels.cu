@@ -176,19 +176,15 @@ __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&
     }
     const ulonglong2 *line0 = reinterpret_cast<const ulonglong2 *>(t.buckets) + g;   // this lane's 16 bytes of bucket 0
 
-    uint32_t hlo[R];
-    uint2 klo[R];
+    uint2 klo[R];                                              // the only per-round state: two registers
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const int src = (r & 7) * 4 + (int)G;
-        hlo[r] = __shfl_sync(full, (uint32_t)mine[r >> 3], src);
-        const uint32_t b = __shfl_sync(full, myb[r >> 3], src);
+        const uint32_t b = __shfl_sync(full, myb[r >> 3], (r & 7) * 4 + (int)G);
         const ulonglong2 v = __ldg(line0 + (size_t)b * (kBucketWords / 2));
         klo[r] = make_uint2((uint32_t)v.x, (uint32_t)v.y);
     }
 
-    uint32_t res[R];                                           // only touched when something was found
-    uint32_t pend = 0, any_found = 0;                          // group-uniform / warp-uniform
+    uint32_t pend = 0;                                         // rounds whose chain goes on (group-uniform)
     // slow path: the whole line of bucket b for the group's probe of hash h -- id if a key matches, overflow flag
     auto resolve = [&](uint32_t b, uint64_t h, bool lv, bool &found, bool &over) -> uint32_t {
         const ulonglong2 v = __ldg(line0 + (size_t)b * (kBucketWords / 2));
@@ -209,32 +205,33 @@ __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&
         found = m != 0u;
         return id;
     };
-    auto note = [&](int r, bool found, bool over, uint32_t id) {
-        if (!any_found && __ballot_sync(full, found)) {
+    // a group found the id of the probe it handled in round r (r may differ between groups): hand it to the
+    // lane that owns the hash -- lane (r & 7) * 4 + G, hash r >> 3 -- right away; nothing is kept per round
+    auto deliver = [&](int r, bool found, uint32_t id) {
+        const int from = (int)((lane & 3u) * 8u);              // a lane of the group that probed for this lane
+        const int fr = __shfl_sync(full, found ? r : -1, from);
+        const uint32_t fid = __shfl_sync(full, id, from);
+        if (fr >= 0 && (fr & 7) == (int)(lane >> 2)) {
 #pragma unroll
-            for (int q = 0; q < R; q++) res[q] = kNoEntry;
-            any_found = 1;
-        }
-        if (found) {
-#pragma unroll
-            for (int q = 0; q < R; q++) if (q == r) res[q] = id;
-        } else if (over) {
-            pend |= 1u << r;
+            for (int i = 0; i < NH; i++)
+                if ((fr >> 3) == i && want[i] && !special[i]) out[i] = fid;
         }
     };
 
     const bool key_lane = g < 5u, flag_lane = g == 7u;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        const bool maybe = key_lane ? (klo[r].x == hlo[r] || klo[r].y == hlo[r]) : (flag_lane && klo[r].y != 0u);
+        const int src = (r & 7) * 4 + (int)G;
+        const uint32_t hlo = __shfl_sync(full, (uint32_t)mine[r >> 3], src);
+        const bool maybe = key_lane ? (klo[r].x == hlo || klo[r].y == hlo) : (flag_lane && klo[r].y != 0u);
         if (__any_sync(full, maybe)) {                          // rare: a key may match, or a bucket overflowed
-            const int src = (r & 7) * 4 + (int)G;
             const uint64_t h = __shfl_sync(full, mine[r >> 3], src);
             const uint32_t b = __shfl_sync(full, myb[r >> 3], src);
             const bool lv = (wants[r >> 3] >> src) & 1u;
             bool found, over;
             const uint32_t id = resolve(b, h, lv, found, over);
-            note(r, found, over, id);
+            if (__any_sync(full, found)) deliver(r, found, id);
+            if (!found && over) pend |= 1u << r;
         }
     }
     // chains: every group follows its own pending probes, one bucket per trip, all groups in step
@@ -262,26 +259,14 @@ __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&
             if (cb >= t.n_buckets) cb -= t.n_buckets;
             bool found, over;
             const uint32_t id = resolve((uint32_t)cb, hh, cr >= 0, found, over);
-            if (cr >= 0 && g == 0u) reads++;
             const bool was = cr >= 0;
-            note(rr, was && found, false, id);
+            if (was && g == 0u) reads++;
+            if (__any_sync(full, was && found)) deliver(rr, was && found, id);
             if (was) {
                 if (found || !over || cstep + 1 >= t.n_buckets) cr = -1;
                 else cstep++;
             }
         }
-    }
-    if (!any_found) return;                                    // warp-uniform: nothing to hand out
-    // hand every lane the answers for its own hashes: lane (r * 4 + G) <- group G's res[8 i + r]
-#pragma unroll
-    for (int i = 0; i < NH; i++) {
-        uint32_t o = kNoEntry;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const uint32_t x = __shfl_sync(full, res[8 * i + q], (int)((lane & 3u) * 8u));
-            if ((int)(lane >> 2) == q) o = x;
-        }
-        if (want[i] && !special[i]) out[i] = o;
     }
 }
 
@@ -356,7 +341,7 @@ constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measure
 // (nearly) every k-mer: the warp looks its hashes up cooperatively (coop_probe), control flow stays
 // warp-uniform and the CTA may use twice the registers (the kernel waits on HBM, not on issue slots)
 template <int KT, int MODE>
-__global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_stream(const StreamArgs a)
+__global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
     constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2, COOP = MODE == 3;
     // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
@@ -418,6 +403,8 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_st
     uint64_t gate = a.do_mix ? mix_tau : 0;
     if (a.do_count) gate = a.do_filter ? (a.tab.max_key > gate ? a.tab.max_key : gate) : ~0ull;
     if (EMIT) gate = ~0ull;   // K1 parity runs want every hash
+    // Bloom-tier instantiation: hashes <= lowgate are handled without the filter (direct probe, mixture insert)
+    const uint64_t lowgate = a.do_mix ? (mix_tau > a.tab.dense_max ? mix_tau : a.tab.dense_max) : a.tab.dense_max;
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
@@ -505,14 +492,15 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_st
 #pragma unroll
                     for (int u = 0; u < kIlp; u++)
                         h[u] = hash_canonical_premul_top(canonical_top_half(fa, fb, fc, ra, rb, rc, q + u), k, a.seed, use64, L);
-                    uint32_t pre[kIlp];
+                    uint32_t pre[kIlp], bbits[kIlp];
 #pragma unroll
                     for (int u = 0; u < kIlp; u++) {
-                        pre[u] = ~0u;
+                        pre[u] = ~0u; bbits[u] = 0u;
                         if (BLOOMB) {   // all kIlp reads are issued before the first one is looked at
-                            uint32_t bw, bb;
-                            bloom_slot(h[u], a.tab.bloom_mask, use64, bw, bb);
-                            if (h[u] > a.tab.dense_max && h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
+                            uint32_t bw;
+                            bloom_slot(h[u], a.tab.bloom_mask, use64, bw, bbits[u]);
+                            pre[u] = 0u;                               // fails the test below: bbits is never 0
+                            if (h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
                         }
                     }
                     if (COOP) {
@@ -542,6 +530,17 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 2 : HS_MIN_CTAS) k_st
                                     if ((uint32_t)(__ffs(peers) - 1) == lane) count_add(a.sparse, a.counts, id[w2], (uint32_t)__popc(peers));
                                     n_hits++;
                                 }
+                        }
+                    } else if (BLOOMB) {
+                        // Most k-mers of a run against such a database lie in the Bloom tier's range and are
+                        // turned away by it: that decision must cost a handful of instructions, so the sink
+                        // (mixture insert, direct probe, the tier's own re-check) is entered only below the
+                        // low gate or when the filter word really has the three bits.
+#pragma unroll
+                        for (int u = 0; u < kIlp; u++) {
+                            const int j = half * 16 + q + u;
+                            const bool enter = h[u] <= lowgate || (pre[u] & bbits[u]) == bbits[u];
+                            if (enter && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
                         }
                     } else {
 #pragma unroll
@@ -707,7 +706,7 @@ __global__ void k_table_canon(const TableView t, const uint64_t *hashes, uint64_
 
 // K2 alone: two hashes per lane (64 probes per warp and trip, 16 lines in flight per lane).
 constexpr int kProbeNH = 2;
-__global__ void __launch_bounds__(128, 5) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
+__global__ void __launch_bounds__(128, 6) k_probe(const TableView t, const uint64_t *hashes, uint64_t n,
                                                   uint32_t *out_entry, unsigned long long *stats)
 {
     const uint32_t lane = threadIdx.x & 31u;
@@ -808,7 +807,7 @@ cudaError_t launch_probe(const TableView &t, const uint64_t *hashes, uint64_t n,
                          unsigned long long *stats, int sm_count, cudaStream_t st)
 {
     if (!n) return cudaSuccess;
-    k_probe<<<grid_for((n + kProbeNH - 1) / kProbeNH, 128, (uint32_t)sm_count * 20u), 128, 0, st>>>(t, hashes, n, out_entry, stats);
+    k_probe<<<grid_for((n + kProbeNH - 1) / kProbeNH, 128, (uint32_t)sm_count * 24u), 128, 0, st>>>(t, hashes, n, out_entry, stats);
     return cudaGetLastError();
 }
 

@@ -66,6 +66,16 @@ def main():
         insts.append({"addr": r[0], "sass": src, "op": m.group(2), "n": int(r[ci["Instructions Executed"]] or 0),
                       "threads": int(r[ci["Thread Instructions Executed"]] or 0), "samples": int(r[ci["# Samples"]] or 0)})
     total = sum(i["n"] for i in insts)
+    # the launch's own counter is the authority for the total (the source page's per-line counts add up to a
+    # few % more: it also attributes replayed issues); the per-line counts give the SHARES
+    raw_total = None
+    try:
+        r2 = subprocess.run(["ncu", "-i", a.report, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+        rr = list(csv.reader(r2.splitlines()))
+        raw_total = float(rr[-1][rr[0].index("smsp__inst_executed.sum")])
+    except Exception:
+        pass
+    scale = (raw_total / total) if raw_total else 1.0
     by_pipe, by_op = {}, {}
     for i in insts:
         p = pipe_of(i["op"])
@@ -73,11 +83,13 @@ def main():
         base = i["op"].split(".")[0]
         by_op[base] = by_op.get(base, 0) + i["n"]
     out = {"kernel": kernel, "report": a.report, "units": a.units, "unit": a.unit_name,
-           "warp_instructions": total, "warp_inst_per_unit": total / a.units,
-           "thread_inst_per_unit": sum(i["threads"] for i in insts) / a.units,
-           "per_pipe_warp_inst_per_unit": {k: v / a.units for k, v in sorted(by_pipe.items(), key=lambda kv: -kv[1])},
+           "warp_instructions": raw_total or total, "warp_instructions_source": "smsp__inst_executed.sum" if raw_total else "source page",
+           "source_page_line_total": total,
+           "warp_inst_per_unit": (raw_total or total) / a.units,
+           "thread_inst_per_unit_x32": 32 * (raw_total or total) / a.units,
+           "per_pipe_warp_inst_per_unit": {k: scale * v / a.units for k, v in sorted(by_pipe.items(), key=lambda kv: -kv[1])},
            "per_pipe_share": {k: v / total for k, v in sorted(by_pipe.items(), key=lambda kv: -kv[1])},
-           "top_opcodes_warp_inst_per_unit": {k: v / a.units for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])[:24]},
+           "top_opcodes_warp_inst_per_unit": {k: scale * v / a.units for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])[:24]},
            "stall_samples_total": sum(i["samples"] for i in insts)}
     print(json.dumps(out, indent=1))
     if a.json:

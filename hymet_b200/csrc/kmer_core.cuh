@@ -341,15 +341,16 @@ HS_HD uint32_t top_word_index64(uint64_t ct, int i, int k)
 template <class Pre>
 HS_HD uint64_t hash_canonical_premul_top(uint64_t ct, int k, uint32_t seed, bool use64, const Pre &pre)
 {
-    struct Adapter {
+    struct Adapter {   // `where` turns (k-mer, word number) into whatever the table accessor addresses by
         const Pre &p; int k;
-        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(top_word_index64(c, i, k), second); }
-        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(top_word_index64(c, i, k), second); }
+        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(p.where(c, i, k), second); }
+        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(p.where(c, i, k), second); }
     };
     return hash_canonical_premul(ct, k, seed, use64, Adapter{pre, k});
 }
 
 struct PremulArithMsb {  // host-side stand-in for the shared-memory tables (tests)
+    HS_HD uint32_t where(uint64_t ct, int i, int k) const { return top_word_index64(ct, i, k); }
     HS_HD uint64_t full(uint32_t index64, bool second) const { return premul_entry_msb(index64 >> 6, second); }
     HS_HD uint32_t low(uint32_t index64, bool second) const { return (uint32_t)full(index64, second); }
 };

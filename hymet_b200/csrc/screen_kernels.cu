@@ -53,21 +53,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase)
 {
     uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    if (mbar_try(bar, phase)) return;   // the usual case: the tile landed long ago
     const long long t0 = clock64();
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
+    for (uint32_t spins = 1;; spins++) {
+        if (mbar_try(bar, phase)) return;
         // a tile that never lands means a broken launch contract: fail loudly, never hang the GPU
-        if (!ok && clock64() - t0 > 4000000000ll) __trap();
-    } while (!ok);
+        // (the clock is looked at once in 256 tries: the spin must not eat the issue slots of the warps that work)
+        if ((spins & 255u) == 0u && clock64() - t0 > 4000000000ll) __trap();
+    }
 }
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v)
@@ -312,18 +319,35 @@ constexpr uint32_t kPreBytes = 256 * 8 * 8;
 static_assert(kPreBytes == 16384 && kPreBytes == kLutBytes, "SmemPremul's loads carry this offset as an immediate");
 struct SmemPremul {
     uint32_t base;  // table address | (lane & 7) * 8
-    __device__ __forceinline__ uint64_t full(uint32_t index64, bool second) const
+    uint32_t k64;   // the constant 64 in a register the compiler cannot see through (below)
+    // Address of word i's entry.  The index byte sits on a byte boundary of the top-aligned k-mer, so it
+    // is ONE byte permute (ALU pipe) and ONE multiply-add by 64 (FMA pipe) instead of a shift and a
+    // three-input logic op (two ALU-pipe instructions): the kernel is bound by the half-rate ALU pipe
+    // (ncu: 74 % busy) while the FMA pipe idles at 26 %.  A multiplier the compiler could see would be
+    // strength-reduced back to a shift/LEA on the ALU pipe.  Partial last words keep the masked form.
+    __device__ __forceinline__ uint32_t where(uint64_t ct, int i, int k) const
+    {
+        if (k - 4 * i >= 4) {
+            const uint32_t w = i < 4 ? (uint32_t)(ct >> 32) : (uint32_t)ct;
+            const uint32_t byte = __byte_perm(w, 0u, 0x4440u + (uint32_t)(3 - (i & 3)));
+            uint32_t addr;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(byte), "r"(k64), "r"(base));
+            return addr;
+        }
+        return top_word_index64(ct, i, k) | base;
+    }
+    __device__ __forceinline__ uint64_t full(uint32_t addr, bool second) const
     {
         uint64_t v;
-        if (second) asm("ld.shared.u64 %0, [%1+16384];" : "=l"(v) : "r"(index64 | base));
-        else asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(index64 | base));
+        if (second) asm("ld.shared.u64 %0, [%1+16384];" : "=l"(v) : "r"(addr));
+        else asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
         return v;
     }
-    __device__ __forceinline__ uint32_t low(uint32_t index64, bool second) const
+    __device__ __forceinline__ uint32_t low(uint32_t addr, bool second) const
     {
         uint32_t v;
-        if (second) asm("ld.shared.u32 %0, [%1+16384];" : "=r"(v) : "r"(index64 | base));
-        else asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(index64 | base));
+        if (second) asm("ld.shared.u32 %0, [%1+16384];" : "=r"(v) : "r"(addr));
+        else asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
         return v;
     }
 };
@@ -344,13 +368,19 @@ template <int KT, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
     constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2, COOP = MODE == 3;
-    // kStages tile buffers, filled kPrefetch tiles ahead by thread 0 through the TMA engine.
+    // kStages tile buffers, filled kPrefetch tiles ahead through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
     // apart (ncu r01: 12 % of warp time sat in __syncthreads with the 2-stage version).
-    constexpr uint32_t kStages = 3, kPrefetch = 1;
+    // WHO issues a tile: whichever warp gets to an iteration first claims the outstanding tile
+    // ordinals (issue_next, compare-and-swap) and issues them.  Round 1 left that to thread 0 with one
+    // tile of look-ahead; warp 0 also does its share of the hashing, so it was usually BEHIND the others,
+    // which then spun on `full` for a tile nobody had asked for yet -- 7 % of all issued instructions
+    // were that spin (ncu r02: 35 try_wait per wait).
+    constexpr uint32_t kStages = 4, kPrefetch = 2;
     __shared__ TileBuf buf[kStages];
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
+    __shared__ uint32_t issue_next;   // ordinal (iteration index of this CTA) of the next tile nobody has issued
     extern __shared__ __align__(16) uint8_t dyn_smem[];  // 2 * kLutBytes: room to align the table to 16 KB
 
     const int k = KT ? KT : a.k;
@@ -362,6 +392,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
             mbar_init(&full[i], 1);
             mbar_init(&empty[i], kCtaThreads / 32);
         }
+        issue_next = kPrefetch;   // the prologue below issues ordinals 0 .. kPrefetch-1
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -378,7 +409,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
     uint32_t lut_lane = lut_addr | ((lane & 7u) << 3);
     asm volatile("mov.u32 %0, %0;" : "+r"(lut_lane));  // one opaque per-thread register: keeps ptxas from
                                                         // splitting it back into uniform base + lane term
-    const SmemPremul L{lut_lane};
+    uint32_t k64 = 64u;
+    asm volatile("mov.u32 %0, %0;" : "+r"(k64));
+    const SmemPremul L{lut_lane, k64};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -412,12 +445,16 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
             if ((uint64_t)tile + (uint64_t)p * gridDim.x < a.n_tiles) issue(tile + p * gridDim.x, p);
 
     for (; tile < a.n_tiles; tile += gridDim.x, it++) {
-        if (tid == 0) {
-            const uint32_t nt = it + kPrefetch;
-            const uint64_t ntile = (uint64_t)a.tile_begin + blockIdx.x + (uint64_t)nt * gridDim.x;
-            if (ntile < a.n_tiles) {
+        if (lane == 0) {
+            // every ordinal up to it + kPrefetch has to be on its way; claim the ones that are not
+            for (;;) {
+                const uint32_t nt = *reinterpret_cast<volatile uint32_t *>(&issue_next);
+                const uint64_t ntile = (uint64_t)a.tile_begin + blockIdx.x + (uint64_t)nt * gridDim.x;
+                if (nt > it + kPrefetch || ntile >= a.n_tiles) break;
+                if (atomicCAS(&issue_next, nt, nt + 1u) != nt) continue;      // another warp took it
                 const uint32_t sb = nt % kStages;
-                if (nt >= kStages) mbar_wait(&empty[sb], ((nt / kStages) - 1u) & 1u);  // its previous tile was consumed
+                // its previous tile (ordinal nt - kStages <= it - 2, so this warp is long past it) was consumed by all
+                if (nt >= kStages) mbar_wait(&empty[sb], ((nt / kStages) - 1u) & 1u);
                 issue((uint32_t)ntile, sb);
             }
         }

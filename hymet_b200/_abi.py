@@ -114,6 +114,7 @@ SIGNATURES = {
     "hs_sketch_packed_device": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
                                           u64p, u32p]),
     "hs_pack_codes_device": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hs_lca_weighted": (C.c_int, [C.c_uint64, u64p, C.POINTER(C.c_int32), f64p, C.c_uint64, u32p, u32p, u32p, f64p, u8p]),
 }
 
 _lib = None

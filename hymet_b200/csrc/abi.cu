@@ -27,6 +27,7 @@
 #include "../../include/hymet_screen.h"
 #include "fasta_pack.h"
 #include "kmer_core.cuh"
+#include "lca_kernels.h"
 #include "msh_capnp.h"
 #include "screen_kernels.h"
 
@@ -2295,4 +2296,43 @@ HS_API int hs_sketch_text(uint32_t k, uint32_t s_, uint32_t seed, const char *te
     int rc = sketch_device(k, s_, seed, dseq, dinv, ps.n_positions, out_hashes, n_out);
     cudaFree(dseq); cudaFree(dinv); cudaFree(dst);
     return rc;
+}
+
+// =============================================================================
+// weighted-LCA vote (classification_cami.py:251-308)
+// =============================================================================
+HS_API int hs_lca_weighted(uint64_t n_q, const uint64_t *q_off, const int32_t *tax, const double *w, uint64_t n_tax,
+                           const uint32_t *names, uint32_t *out_names, uint32_t *out_depth, double *out_conf, uint8_t *out_any)
+{
+    if (n_q && (!q_off || !out_names || !out_depth || !out_conf || !out_any)) return fail(HS_EINVAL, "null argument");
+    NEED_DEVICE();
+    if (!n_q) return HS_OK;
+    const uint64_t n_a = q_off[n_q];
+    if (n_a && (!tax || !w)) return fail(HS_EINVAL, "null argument");
+    if (n_tax && !names) return fail(HS_EINVAL, "null argument");
+    for (uint64_t j = 0; j < n_a; j++)
+        if (tax[j] >= 0 && (uint64_t)tax[j] >= n_tax) return fail(HS_EINVAL, "taxid row out of range");
+    DevBufs d;
+    LcaArgs a;
+    memset(&a, 0, sizeof a);
+    uint64_t *d_off = nullptr;
+    int32_t *d_tax = nullptr;
+    double *d_w = nullptr;
+    uint32_t *d_names = nullptr;
+    CU(d.alloc(&d_off, (n_q + 1) * 8));
+    CU(d.alloc(&d_tax, n_a * 4)); CU(d.alloc(&d_w, n_a * 8)); CU(d.alloc(&d_names, n_tax * kLcaRanks * 4));
+    CU(d.alloc(&a.s_tax, n_a * 4)); CU(d.alloc(&a.s_w, n_a * 8)); CU(d.alloc(&a.s_name, n_a * 4)); CU(d.alloc(&a.s_nw, n_a * 8));
+    CU(d.alloc(&a.out_names, n_q * kLcaRanks * 4)); CU(d.alloc(&a.out_depth, n_q * 4));
+    CU(d.alloc(&a.out_conf, n_q * 8)); CU(d.alloc(&a.out_any, n_q));
+    CU(cudaMemcpy(d_off, q_off, (n_q + 1) * 8, cudaMemcpyHostToDevice));
+    if (n_a) { CU(cudaMemcpy(d_tax, tax, n_a * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d_w, w, n_a * 8, cudaMemcpyHostToDevice)); }
+    if (n_tax) CU(cudaMemcpy(d_names, names, n_tax * kLcaRanks * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemset(a.out_names, 0, n_q * kLcaRanks * 4));
+    a.n_q = n_q; a.q_off = d_off; a.tax = d_tax; a.w = d_w; a.names = d_names;
+    CU(launch_weighted_lca(a, g_sm, 0));
+    CU(cudaMemcpy(out_names, a.out_names, n_q * kLcaRanks * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_depth, a.out_depth, n_q * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_conf, a.out_conf, n_q * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_any, a.out_any, n_q, cudaMemcpyDeviceToHost));
+    return HS_OK;
 }

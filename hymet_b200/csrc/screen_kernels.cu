@@ -436,6 +436,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
     uint64_t gate = a.do_mix ? mix_tau : 0;
     if (a.do_count) gate = a.do_filter ? (a.tab.max_key > gate ? a.tab.max_key : gate) : ~0ull;
     if (EMIT) gate = ~0ull;   // K1 parity runs want every hash
+    const uint32_t gate_hi = (uint32_t)(gate >> 32);
     // Bloom-tier instantiation: hashes <= lowgate are handled without the filter (direct probe, mixture insert)
     const uint64_t lowgate = a.do_mix ? (mix_tau > a.tab.dense_max ? mix_tau : a.tab.dense_max) : a.tab.dense_max;
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
@@ -446,15 +447,20 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
 
     for (; tile < a.n_tiles; tile += gridDim.x, it++) {
         if (lane == 0) {
-            // every ordinal up to it + kPrefetch has to be on its way; claim the ones that are not
+            // Ordinals up to it + kPrefetch should be on their way; claim the ones that are not.  The tile this
+            // warp is about to wait for (ordinal it) MUST be issued, so for it the stage's release is waited
+            // for; look-ahead tiles are only taken when their stage is already free -- otherwise the warp goes
+            // on hashing and whoever comes by next tries again (round 2, first form: the fastest warp span
+            // here for the slowest one, 4 % of all issued instructions).
             for (;;) {
                 const uint32_t nt = *reinterpret_cast<volatile uint32_t *>(&issue_next);
                 const uint64_t ntile = (uint64_t)a.tile_begin + blockIdx.x + (uint64_t)nt * gridDim.x;
                 if (nt > it + kPrefetch || ntile >= a.n_tiles) break;
-                if (atomicCAS(&issue_next, nt, nt + 1u) != nt) continue;      // another warp took it
                 const uint32_t sb = nt % kStages;
-                // its previous tile (ordinal nt - kStages <= it - 2, so this warp is long past it) was consumed by all
-                if (nt >= kStages) mbar_wait(&empty[sb], ((nt / kStages) - 1u) & 1u);
+                const uint32_t par = ((nt / kStages) - 1u) & 1u;   // parity of the phase that frees the stage (ordinal nt - kStages consumed by all)
+                if (nt > it && nt >= kStages && !mbar_try(&empty[sb], par)) break;
+                if (atomicCAS(&issue_next, nt, nt + 1u) != nt) continue;      // another warp took it
+                if (nt >= kStages) mbar_wait(&empty[sb], par);
                 issue((uint32_t)ntile, sb);
             }
         }
@@ -583,7 +589,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
 #pragma unroll
                         for (int u = 0; u < kIlp; u++) {
                             const int j = half * 16 + q + u;
-                            if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
+                            // high words first: one compare turns away all but ~1 k-mer in a thousand
+                            if ((uint32_t)(h[u] >> 32) <= gate_hi)
+                                if (h[u] <= gate && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
                         }
                     }
                 }

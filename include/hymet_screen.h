@@ -273,6 +273,16 @@ int hs_sketch_packed_device(uint32_t k, uint32_t s, uint32_t seed, const void *d
  * invalid).  Runs on `cuda_stream` (NULL = default stream) and returns without syncing. */
 int hs_pack_codes_device(const void *d_codes, uint64_t n, void *d_seq2, void *d_inv, void *cuda_stream);
 
+/* ---- the classifier's weighted-LCA vote ----------------------------------------
+ * /root/reference/scripts/classification_cami.py:251-308 (_weighted_lca, _process_one) for n_q queries
+ * at once, one GPU thread per query, bit-exact with the reference's double arithmetic (sums in dict
+ * insertion order, first maximum wins).  Alignments of query q are [q_off[q], q_off[q+1]); tax[j] = row of
+ * `names` for the target's taxid or -1, w[j] = coverage x reference abundance; names[n_tax][8] = name id
+ * per rank (superkingdom..strain), 0 = none.  out_names[q][0..out_depth[q]) = chosen names, out_depth = 0
+ * means "Unknown"; out_any[q] = some alignment had a taxid. */
+int hs_lca_weighted(uint64_t n_q, const uint64_t *q_off, const int32_t *tax, const double *w, uint64_t n_tax,
+                    const uint32_t *names, uint32_t *out_names, uint32_t *out_depth, double *out_conf, uint8_t *out_any);
+
 #ifdef __cplusplus
 }
 #endif

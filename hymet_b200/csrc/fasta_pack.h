@@ -26,6 +26,12 @@ inline uint64_t pack_words_bound(uint64_t n_text) { return n_text / 32 + 4; }
 // flagged invalid.  Returns the number of words written.
 uint64_t pack_text_span(const char *text, size_t n, uint64_t *seq, uint32_t *inv, PackStats *st);
 
+// Which implementation pack_text_span uses: 0 scalar, 1 AVX2 line by line, 2 AVX-512 (VBMI2) runs of
+// 64-byte blocks across lines.  Default -1 = the best the host supports; tests pin lower levels to
+// compare them bit for bit.
+void set_pack_level(int level);
+int pack_level();
+
 // Split [text, text+n) into <= parts spans that each begin at a line starting with
 // '>' (FASTA).  FASTQ input ('@' first) is returned as a single span.
 std::vector<std::pair<size_t, size_t>> split_records(const char *text, size_t n, int parts, size_t min_span);

@@ -213,16 +213,32 @@ HS_HD uint64_t premul_filler(int nb, bool second)
     return (uint64_t)(0x41414141u & ~((1u << (8 * nb)) - 1u)) * c;
 }
 
-// `Pre::full(cl, i, second)`: 64-bit product of word i's letters; `Pre::low`: its low 32 bits.
+// A tail of 1..5 letters (k mod 16, e.g. k = 21: the HYMET default) is one lane of at most ten bits:
+// its whole contribution  rotl64(lane * c1, 31) * c2  -- two table reads, an add, a rotate and a 64-bit
+// multiply, about a tenth of the loop -- fits a table of 4^r 64-bit entries (8 KB at r = 5).
+// x holds the r letters, first letter most significant, in its low 2r bits.
+HS_HD bool tail_table_applies(int k) { return (k & 15) >= 1 && (k & 15) <= 5; }
+HS_HD uint64_t tail_entry(uint32_t x, int r)
+{
+    uint64_t lane = 0;
+    for (int i = 0; i < r; i++) lane |= (uint64_t)((0x54474341u >> (8 * ((x >> (2 * (r - 1 - i))) & 3u))) & 0xFFu) << (8 * i);
+    uint64_t k1 = lane * kMurmurC1;
+    k1 = (k1 << 31) | (k1 >> 33);
+    return k1 * kMurmurC2;
+}
+
+// `Pre::full(cl, i, second)`: 64-bit product of word i's letters; `Pre::low`: its low 32 bits;
+// `Pre::kTail` / `Pre::tail(cl, k)`: the finished tail term when a table of it exists.
 template <class Pre>
 HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use64, const Pre &pre)
 {
+    const bool tail_tab = Pre::kTail && tail_table_applies(k);
     uint64_t m[4];
 #pragma unroll
     for (int l = 0; l < 4; l++) {
         const int nb = k - 8 * l;
         uint64_t p = 0;
-        if (nb > 0) {
+        if (nb > 0 && !(tail_tab && l == 2 * (k >> 4))) {
             p = pre.full(cl, 2 * l, (l & 1) != 0);
             if (nb > 4) {   // only the high word changes: one 32-bit add (filler folded in), no carry chain
                 const uint32_t hi = (uint32_t)(p >> 32) + pre.low(cl, 2 * l + 1, (l & 1) != 0) -
@@ -249,7 +265,10 @@ HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use
     }
     if (k & 15) {
         if ((k & 15) > 8) { uint64_t k2 = m[(t + 1) & 3]; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
-        uint64_t k1 = m[t & 3]; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        uint64_t k1;
+        if (tail_tab) { k1 = pre.tail(cl, k); }
+        else { k1 = m[t & 3]; k1 = rotl64(k1, 31); k1 *= c2; }
+        h1 ^= k1;
     }
     h1 ^= (uint64_t)k; h2 ^= (uint64_t)k;
     h1 += h2; h2 += h1;
@@ -259,6 +278,8 @@ HS_HD uint64_t hash_canonical_premul(uint64_t cl, int k, uint32_t seed, bool use
 }
 
 struct PremulArith {  // host-side stand-in for the shared-memory tables (tests)
+    static constexpr bool kTail = false;
+    HS_HD uint64_t tail(uint64_t, int) const { return 0; }
     HS_HD uint64_t full(uint64_t cl, int i, bool second) const { return premul_entry((uint32_t)(cl >> (8 * i)) & 0xFFu, second); }
     HS_HD uint32_t low(uint64_t cl, int i, bool second) const { return (uint32_t)full(cl, i, second); }
 };
@@ -339,17 +360,32 @@ HS_HD uint32_t top_word_index64(uint64_t ct, int i, int k)
 }
 
 template <class Pre>
+struct TopAdapter {   // `where` turns (k-mer, word number) into whatever the table accessor addresses by
+    static constexpr bool kTail = Pre::kTail;
+    const Pre &p; int k;
+    HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(p.where(c, i, k), second); }
+    HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(p.where(c, i, k), second); }
+    HS_HD uint64_t tail(uint64_t c, int kk) const { return p.tail(c, kk); }
+};
+
+template <class Pre>
 HS_HD uint64_t hash_canonical_premul_top(uint64_t ct, int k, uint32_t seed, bool use64, const Pre &pre)
 {
-    struct Adapter {   // `where` turns (k-mer, word number) into whatever the table accessor addresses by
-        const Pre &p; int k;
-        HS_HD uint64_t full(uint64_t c, int i, bool second) const { return p.full(p.where(c, i, k), second); }
-        HS_HD uint32_t low(uint64_t c, int i, bool second) const { return p.low(p.where(c, i, k), second); }
-    };
-    return hash_canonical_premul(ct, k, seed, use64, Adapter{pre, k});
+    return hash_canonical_premul(ct, k, seed, use64, TopAdapter<Pre>{pre, k});
+}
+
+// the tail's letters inside a TOP-aligned k-mer: letters 16*(k>>4) .. k-1 end at bit 64-2k, and start at
+// the top of one of the two 32-bit halves (letter 0 or letter 16), so the index is one right shift
+HS_HD uint32_t top_tail_index(uint64_t ct, int k)
+{
+    const int r = k & 15;
+    const uint32_t w = (k >> 4) ? (uint32_t)ct : (uint32_t)(ct >> 32);
+    return w >> (32 - 2 * r);
 }
 
 struct PremulArithMsb {  // host-side stand-in for the shared-memory tables (tests)
+    static constexpr bool kTail = true;
+    HS_HD uint64_t tail(uint64_t ct, int k) const { return tail_entry(top_tail_index(ct, k), k & 15); }
     HS_HD uint32_t where(uint64_t ct, int i, int k) const { return top_word_index64(ct, i, k); }
     HS_HD uint64_t full(uint32_t index64, bool second) const { return premul_entry_msb(index64 >> 6, second); }
     HS_HD uint32_t low(uint32_t index64, bool second) const { return (uint32_t)full(index64, second); }

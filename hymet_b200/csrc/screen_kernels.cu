@@ -53,6 +53,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef HS_WAIT_SLEEP
+#define HS_WAIT_SLEEP 100   // ns between tries of a warp that is ahead of its CTA (0: spin)
+#endif
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase)
 {
     uint32_t ok;
@@ -68,12 +71,17 @@ __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t phase)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
 {
     if (mbar_try(bar, phase)) return;   // the usual case: the tile landed long ago
-    const long long t0 = clock64();
+    // A warp that waits here has run ahead of the slowest warp of its CTA by the whole ring (the tile it wants
+    // cannot be issued before its stage is released), so it should get out of the way: spinning on try_wait
+    // with a clock read per trip was 3.9 % of all issued warp instructions of the kernel (ncu r02, 13 trips per
+    // wait), taken from the issue slots of the very warps it was waiting for.
     for (uint32_t spins = 1;; spins++) {
+#if HS_WAIT_SLEEP
+        __nanosleep(HS_WAIT_SLEEP);
+#endif
         if (mbar_try(bar, phase)) return;
         // a tile that never lands means a broken launch contract: fail loudly, never hang the GPU
-        // (the clock is looked at once in 256 tries: the spin must not eat the issue slots of the warps that work)
-        if ((spins & 255u) == 0u && clock64() - t0 > 4000000000ll) __trap();
+        if (spins > (1u << 24)) __trap();
     }
 }
 
@@ -159,7 +167,7 @@ __device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts
 // absent, or want[i] == false); `reads` counts bucket lines read for wanted probes (lane 0 / leaders).
 template <int NH>
 __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&mine)[NH], const bool (&want)[NH],
-                                           uint32_t (&out)[NH], uint32_t &reads)
+                                           uint32_t (&out)[NH], uint32_t &reads, const uint32_t *home = nullptr)
 {
     static_assert(NH >= 1 && NH <= 4, "up to 32 rounds: one bit each in the pending mask");
     constexpr int R = 8 * NH;
@@ -178,7 +186,7 @@ __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&
     // hash holds) and its answer dropped at the end: the rounds below carry no per-lane liveness logic.
 #pragma unroll
     for (int i = 0; i < NH; i++) {
-        myb[i] = bucket_of(mine[i], t.n_buckets);
+        myb[i] = home ? home[i] : bucket_of(mine[i], t.n_buckets);   // (the caller may have prefetched the home buckets)
         if (lane == 0) reads += (uint32_t)__popc(wants[i]);
     }
     const ulonglong2 *line0 = reinterpret_cast<const ulonglong2 *>(t.buckets) + g;   // this lane's 16 bytes of bucket 0
@@ -317,9 +325,23 @@ static_assert(sizeof(TileBuf) % 16 == 0, "tile buffers must keep 16-byte alignme
 constexpr uint32_t kLutBytes = 16384;   // alignment and size of one table
 constexpr uint32_t kPreBytes = 256 * 8 * 8;
 static_assert(kPreBytes == 16384 && kPreBytes == kLutBytes, "SmemPremul's loads carry this offset as an immediate");
+constexpr uint32_t kTailBytes = 8192;   // 4^5 finished tail terms (kmer_core.cuh: tail_entry), right behind the two tables
+template <bool TAIL>
 struct SmemPremul {
+    static constexpr bool kTail = TAIL;
     uint32_t base;  // table address | (lane & 7) * 8
     uint32_t k64;   // the constant 64 in a register the compiler cannot see through (below)
+    uint32_t lut;   // table address alone (16 KB aligned): the tail table has no lane copies
+    // finished tail term of a top-aligned k-mer: one shift, one AND-OR, one 64-bit load
+    __device__ __forceinline__ uint64_t tail(uint64_t ct, int k) const
+    {
+        const int r = k & 15;
+        const uint32_t w = (k >> 4) ? (uint32_t)ct : (uint32_t)(ct >> 32);
+        const uint32_t addr = ((w >> (29 - 2 * r)) & (((1u << (2 * r)) - 1u) << 3)) | lut;
+        uint64_t v;
+        asm("ld.shared.u64 %0, [%1+32768];" : "=l"(v) : "r"(addr));
+        return v;
+    }
     // Address of word i's entry.  The index byte sits on a byte boundary of the top-aligned k-mer, so it
     // is ONE byte permute (ALU pipe) and ONE multiply-add by 64 (FMA pipe) instead of a shift and a
     // three-input logic op (two ALU-pipe instructions): the kernel is bound by the half-rate ALU pipe
@@ -358,6 +380,14 @@ struct SmemPremul {
 #ifndef HS_MIN_CTAS
 #define HS_MIN_CTAS 4   // 48 KB of shared memory per CTA
 #endif
+#ifndef HS_COOP_PREFETCH
+#define HS_COOP_PREFETCH 1
+#endif
+#ifndef HS_TAIL_TABLE
+#define HS_TAIL_TABLE 1
+#endif
+// compile-time k with a 1..5 letter tail (k = 21): the tail term comes from its own table
+__host__ __device__ constexpr bool stream_tail_table(int kt) { return HS_TAIL_TABLE && kt > 0 && (kt & 15) >= 1 && (kt & 15) <= 5; }
 constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
 
 // MODE: 0 = screen, 1 = K1 parity (emit every hash), 2 = screen with the Bloom reads of a group of
@@ -368,6 +398,7 @@ template <int KT, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
     constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2, COOP = MODE == 3;
+    constexpr bool kTailTab = stream_tail_table(KT);
     // kStages tile buffers, filled kPrefetch tiles ahead through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
@@ -401,9 +432,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
     {
         uint32_t dyn_size;
         asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_size));
-        if (lut_addr + 2 * kPreBytes > dyn_addr + dyn_size) __trap();  // launch did not leave room for the aligned tables
+        if (lut_addr + 2 * kPreBytes + (kTailTab ? kTailBytes : 0u) > dyn_addr + dyn_size) __trap();  // launch did not leave room for the aligned tables
         uint64_t *t = reinterpret_cast<uint64_t *>(dyn_smem + (lut_addr - dyn_addr));
         for (uint32_t i = tid; i < 2 * 256 * 8; i += kCtaThreads) t[i] = premul_entry_msb((i >> 3) & 255u, i >= 256 * 8);
+        if (kTailTab)
+            for (uint32_t i = tid; i < (1u << (2 * (KT & 15))); i += kCtaThreads) t[2 * 256 * 8 + i] = tail_entry(i, KT & 15);
     }
     __syncthreads();
     uint32_t lut_lane = lut_addr | ((lane & 7u) << 3);
@@ -411,7 +444,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                                                         // splitting it back into uniform base + lane term
     uint32_t k64 = 64u;
     asm volatile("mov.u32 %0, %0;" : "+r"(k64));
-    const SmemPremul L{lut_lane, k64};
+    const SmemPremul<kTailTab> L{lut_lane, k64, lut_addr};
 
     auto issue = [&](uint32_t tile, uint32_t b) {
         // tile 0 has no halo (positions before the chunk do not exist)
@@ -439,6 +472,7 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
     const uint32_t gate_hi = (uint32_t)(gate >> 32);
     // Bloom-tier instantiation: hashes <= lowgate are handled without the filter (direct probe, mixture insert)
     const uint64_t lowgate = a.do_mix ? (mix_tau > a.tab.dense_max ? mix_tau : a.tab.dense_max) : a.tab.dense_max;
+    const uint32_t lowgate_hi = (uint32_t)(lowgate >> 32), max_hi = (uint32_t)(a.tab.max_key >> 32);
     uint32_t n_valid = 0, n_probe = 0, n_reads = 0, n_hits = 0, n_mix = 0;
     uint32_t tile = a.tile_begin + blockIdx.x, it = 0;
     if (tid == 0)
@@ -543,7 +577,8 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                             uint32_t bw;
                             bloom_slot(h[u], a.tab.bloom_mask, use64, bw, bbits[u]);
                             pre[u] = 0u;                               // fails the test below: bbits is never 0
-                            if (h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
+                            // (high words only: a superset of h <= max_key, and the word index is masked into range)
+                            if ((uint32_t)(h[u] >> 32) <= max_hi) pre[u] = __ldg(a.tab.bloom + bw);
                         }
                     }
                     if (COOP) {
@@ -558,14 +593,27 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                             }
                         }
                         static_assert(kIlp % 2 == 0, "the cooperative lookup takes the k-mers two at a time");
+                        // The cooperative rounds keep 64 lines in flight per warp (their registers); the trip's other 64
+                        // used to start only after those had come back from HBM.  Prefetches cost no registers: all 128
+                        // home buckets of the trip are requested into L2 right away, and the second pair of lookups --
+                        // like every chain step -- finds its lines there or already on the way.
+                        uint32_t home[kIlp];
+#pragma unroll
+                        for (int u = 0; u < kIlp; u++) {
+                            home[u] = bucket_of(h[u], a.tab.n_buckets);
+#if HS_COOP_PREFETCH
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tab.buckets + (size_t)home[u] * kBucketWords));
+#endif
+                        }
 #pragma unroll
                         for (int u = 0; u < kIlp; u += 2) {     // all 32 lanes, every trip: 64 probes, 16 lines in flight per lane
                             const uint64_t hh[2] = {h[u], h[u + 1]};
+                            const uint32_t hb[2] = {home[u], home[u + 1]};
                             const bool want[2] = {valid[u] && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key),
                                                   valid[u + 1] && a.do_count && (!a.do_filter || h[u + 1] <= a.tab.max_key)};
                             uint32_t id[2];
                             n_probe += (uint32_t)want[0] + (uint32_t)want[1];
-                            coop_probe<2>(a.tab, hh, want, id, n_reads);
+                            coop_probe<2>(a.tab, hh, want, id, n_reads, hb);
 #pragma unroll
                             for (int w2 = 0; w2 < 2; w2++)
                                 if (id[w2] != kNoEntry) {
@@ -582,7 +630,8 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
 #pragma unroll
                         for (int u = 0; u < kIlp; u++) {
                             const int j = half * 16 + q + u;
-                            const bool enter = h[u] <= lowgate || (pre[u] & bbits[u]) == bbits[u];
+                            // (high word of the low gate: a superset; the sink repeats every test exactly)
+                            const bool enter = (uint32_t)(h[u] >> 32) <= lowgate_hi || (pre[u] & bbits[u]) == bbits[u];
                             if (enter && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
                         }
                     } else {
@@ -634,7 +683,8 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
             cudaFuncAttributes fa;
             if ((e = cudaFuncGetAttributes(&fa, k_stream<KT, MODE>)) != cudaSuccess) return e;
             const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
-            const uint32_t d = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes;
+            const uint32_t d = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes +
+                               (stream_tail_table(KT) ? kTailBytes : 0u);
             if ((e = cudaFuncSetAttribute(k_stream<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d)) != cudaSuccess) return e;
             int o = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_stream<KT, MODE>, kCtaThreads, d);

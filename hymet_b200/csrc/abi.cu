@@ -12,6 +12,7 @@
 #include <ctype.h>
 #include <fcntl.h>
 #include <sched.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -347,7 +348,7 @@ struct hs_screen {
     Ingest ingest;
     int ingest_mode = 2;   // 0 = host packer only, 1 = device parser only, 2 = both compete for chunks (pinned text)
     uint64_t text_chunk = (uint64_t)256 << 20;   // gzip / stdin input: bytes inflated per hand-over to the packers
-    int ingest_batch = 0;  // spans per device-ingest submission (0 = 3 next to packer threads, 4 alone)
+    int ingest_batch = 0;  // spans per device-ingest submission (0 = 2 next to packer threads, 4 alone)
     FileRing ring;
     // plain FASTA files: nominal bytes per reader block and reader threads.  Pinning the ring costs
     // ~0.5 ms per MB once per handle (measured), which a one-shot `mash screen` pays in full: the
@@ -355,6 +356,7 @@ struct hs_screen {
     // 8 readers x 16 MB (28 ms per GB, bench.py's e2e_file)
     uint64_t file_block = (uint64_t)8 << 20;
     int file_readers = 4;
+    int file_mode = -1;   // plain FASTA files: 0 pread ring + device parser, 1 mmap + host packers, -1 by host capability
     std::mutex ingest_mu;                       // one thread at a time hands a span to the device parser
     std::mutex giant_mu;                        // records larger than a ring slot take the host path, one at a time
     uint32_t *d_counts = nullptr;
@@ -1047,6 +1049,7 @@ HS_API int hs_screen_set_option(hs_screen *s, const char *key, int64_t value)
     else if (!strcmp(key, "ingest_batch")) s->ingest_batch = value < 1 ? 1 : (value > 8 ? 8 : (int)value);
     else if (!strcmp(key, "text_chunk_bytes")) s->text_chunk = value > 4096 ? (uint64_t)value : 4096;
     else if (!strcmp(key, "file_block_bytes")) s->file_block = value > 65536 ? (uint64_t)value : 65536;
+    else if (!strcmp(key, "file_mode")) s->file_mode = value < 0 ? -1 : (value ? 1 : 0);
     else if (!strcmp(key, "file_readers")) s->file_readers = value < 1 ? 1 : (value > 16 ? 16 : (int)value);
     else if (!strcmp(key, "batch_bloom")) s->batch_bloom = value != 0;
     else if (!strcmp(key, "coop_probe")) s->coop_probe = value != 0;
@@ -1188,6 +1191,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     std::atomic<size_t> next{0};
     std::atomic<int> rc_all{HS_OK};
     std::atomic<int> dev_us_per_span{350};  // measured pace of the device-ingest worker
+    std::atomic<int> pack_us_per_span{(int)(s->chunk_text / 5000) + 1};   // pace of one packer thread (EMA; ~5 GB/s to start with)
     std::string err_all;
     std::mutex err_mu;
     auto worker = [&](int t) {
@@ -1225,6 +1229,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
                 pack_text_span(text + spans[i].first, len, g.seq, g.inv, &ps);
                 const double t1 = now_s();
                 my_ms = 1e3 * (t1 - t0);
+                pack_us_per_span.store((pack_us_per_span.load() * 3 + (int)(1e3 * my_ms)) / 4);
                 std::lock_guard<std::mutex> lk(s->mu);
                 const double t2 = now_s();
                 s->st.n_bases += ps.n_seq_bases;
@@ -1247,8 +1252,24 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
         cudaSetDevice(s->db->device);
         // consecutive spans are contiguous text: take a few at a time so that the parser and
         // stream kernels run on >= 48 MB launches (fewer, fuller waves; fewer host wake-ups)
-        const size_t batch = s->ingest_batch ? (size_t)s->ingest_batch : (threads > 0 ? 3 : 4);
+        const size_t batch = s->ingest_batch ? (size_t)s->ingest_batch : (threads > 0 ? 2 : 4);
         for (;;) {
+            if (threads > 0) {
+                // The mirror image of the packers' rule: a batch taken now completes after everything already
+                // queued on this path (raw text moves at ~1 byte per base over PCIe).  If the packer threads
+                // would be through with ALL that is left before then, taking it only lengthens the tail --
+                // with the AVX-512 packer the feed used to return after 9 ms and the GPU worked off this
+                // path's backlog for another 6.
+                const size_t nx = next.load();
+                if (nx >= spans.size()) break;
+                int busy = 0;
+                for (int q = 0; q < s->ingest.n_slots; q++)
+                    if (s->ingest.slots[q].done && cudaEventQuery(s->ingest.slots[q].done) == cudaErrorNotReady) busy++;
+                cudaGetLastError();
+                const double rest_ms = (double)(spans.size() - nx) * pack_us_per_span.load() * 1e-3 / threads;
+                const double mine_ms = (double)(busy + 1) * (double)batch * dev_us_per_span.load() * 1e-3 + 0.3;
+                if (rest_ms < mine_ms) break;
+            }
             const size_t i = next.fetch_add(batch);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;
             const size_t last = std::min(spans.size(), i + batch) - 1;
@@ -1422,6 +1443,31 @@ int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads, uint64_t 
     return HS_OK;
 }
 
+// Row a6 for a plain FASTA file, second form: map the file and let the host packer threads read the page
+// cache where it lies -- no copy into a pinned ring, and 3/8 of a byte per base over PCIe instead of a
+// whole one.  Worth it when the packers are fast (AVX-512 hosts: pack_level() == 2); the pread ring feeds
+// the device parser otherwise.  Same range rule as feed_file_stream.
+bool file_wants_mmap(const hs_screen *s, int threads) { return s->file_mode == 1 || (s->file_mode < 0 && pack_level() >= 2 && threads >= 4); }
+
+int feed_file_mmap(hs_screen *s, int fd, uint64_t size, int threads, uint64_t range_begin = 0, uint64_t range_end = ~0ull)
+{
+    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    range_end = std::min(range_end, size);
+    if (range_begin >= range_end) return HS_OK;
+    void *m = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) return fail(HS_EIO, "mmap failed");
+    madvise(m, (size_t)size, MADV_SEQUENTIAL);
+    const char *t = (const char *)m;
+    // a record belongs to the range in which its first byte falls
+    auto cut = [&](uint64_t pos) -> uint64_t { return pos == 0 ? 0 : (pos >= size ? size : find_record_start(t, (size_t)pos, (size_t)size)); };
+    const uint64_t b = cut(range_begin), e = cut(range_end);
+    int rc = HS_OK;
+    if (e > b) rc = feed_text_impl(s, t + b, (size_t)(e - b), threads);
+    // the packers have read everything (their H2D copies come from pinned staging, not from the mapping)
+    munmap(m, (size_t)size);
+    return rc;
+}
+
 }  // namespace
 
 HS_API int hs_screen_feed_text(hs_screen *s, const char *text, size_t n, int host_threads)
@@ -1445,7 +1491,8 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
             size_t first = 0;
             while (first < hn && (head[first] == '\n' || head[first] == '\r')) first++;
             if (first < hn && head[first] == '>') {   // not gzip (1f 8b), not FASTQ
-                const int rc = feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads);
+                const int rc = file_wants_mmap(s, host_threads) ? feed_file_mmap(s, fd, (uint64_t)sb.st_size, host_threads)
+                                                                : feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads);
                 close(fd);
                 return rc;
             }
@@ -1511,7 +1558,8 @@ HS_API int hs_screen_feed_fasta_range(hs_screen *s, const char *path, uint64_t b
         close(fd);
         return fail(HS_EUNSUPPORTED, "byte ranges need a plain FASTA file (gzip, FASTQ and pipes cannot be cut): feed it whole");
     }
-    const int rc = feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads, begin, end);
+    const int rc = file_wants_mmap(s, host_threads) ? feed_file_mmap(s, fd, (uint64_t)sb.st_size, host_threads, begin, end)
+                                                    : feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads, begin, end);
     close(fd);
     return rc;
 }

@@ -167,7 +167,7 @@ __device__ __forceinline__ void count_add(const SparseView &sp, uint32_t *counts
 // absent, or want[i] == false); `reads` counts bucket lines read for wanted probes (lane 0 / leaders).
 template <int NH>
 __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&mine)[NH], const bool (&want)[NH],
-                                           uint32_t (&out)[NH], uint32_t &reads, const uint32_t *home = nullptr)
+                                           uint32_t (&out)[NH], uint32_t &reads)
 {
     static_assert(NH >= 1 && NH <= 4, "up to 32 rounds: one bit each in the pending mask");
     constexpr int R = 8 * NH;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void coop_probe(const TableView &t, const uint64_t (&
     // hash holds) and its answer dropped at the end: the rounds below carry no per-lane liveness logic.
 #pragma unroll
     for (int i = 0; i < NH; i++) {
-        myb[i] = home ? home[i] : bucket_of(mine[i], t.n_buckets);   // (the caller may have prefetched the home buckets)
+        myb[i] = bucket_of(mine[i], t.n_buckets);
         if (lane == 0) reads += (uint32_t)__popc(wants[i]);
     }
     const ulonglong2 *line0 = reinterpret_cast<const ulonglong2 *>(t.buckets) + g;   // this lane's 16 bytes of bucket 0
@@ -380,14 +380,20 @@ struct SmemPremul {
 #ifndef HS_MIN_CTAS
 #define HS_MIN_CTAS 4   // 48 KB of shared memory per CTA
 #endif
-#ifndef HS_COOP_PREFETCH
-#define HS_COOP_PREFETCH 1
+#ifndef HS_BLOOM_HI_GATE
+#define HS_BLOOM_HI_GATE 1
 #endif
 #ifndef HS_TAIL_TABLE
 #define HS_TAIL_TABLE 1
 #endif
 // compile-time k with a 1..5 letter tail (k = 21): the tail term comes from its own table
-__host__ __device__ constexpr bool stream_tail_table(int kt) { return HS_TAIL_TABLE && kt > 0 && (kt & 15) >= 1 && (kt & 15) <= 5; }
+#ifndef HS_TAIL_MODES
+#define HS_TAIL_MODES 0x3   // bit m: instantiation MODE m uses the table (it takes 8 KB from the L1 of every CTA)
+#endif
+__host__ __device__ constexpr bool stream_tail_table(int kt, int mode)
+{
+    return HS_TAIL_TABLE && ((HS_TAIL_MODES >> mode) & 1) && kt > 0 && (kt & 15) >= 1 && (kt & 15) <= 5;
+}
 constexpr int kIlp = HS_ILP;   // k-mers hashed side by side per thread (measured, ms per Gbp: 1: 5.33, 2: 5.02, 4: 4.83, 8: 6.47)
 
 // MODE: 0 = screen, 1 = K1 parity (emit every hash), 2 = screen with the Bloom reads of a group of
@@ -398,7 +404,7 @@ template <int KT, int MODE>
 __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_stream(const StreamArgs a)
 {
     constexpr bool EMIT = MODE == 1, BLOOMB = MODE == 2, COOP = MODE == 3;
-    constexpr bool kTailTab = stream_tail_table(KT);
+    constexpr bool kTailTab = stream_tail_table(KT, MODE);
     // kStages tile buffers, filled kPrefetch tiles ahead through the TMA engine.
     // full[s]: the bytes of stage s have landed; empty[s]: all 8 warps copied their words of
     // stage s to registers.  No CTA-wide barrier in the loop: warps drift up to two tiles
@@ -578,7 +584,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                             bloom_slot(h[u], a.tab.bloom_mask, use64, bw, bbits[u]);
                             pre[u] = 0u;                               // fails the test below: bbits is never 0
                             // (high words only: a superset of h <= max_key, and the word index is masked into range)
+#if HS_BLOOM_HI_GATE
                             if ((uint32_t)(h[u] >> 32) <= max_hi) pre[u] = __ldg(a.tab.bloom + bw);
+#else
+                            if (h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
+#endif
                         }
                     }
                     if (COOP) {
@@ -593,27 +603,17 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                             }
                         }
                         static_assert(kIlp % 2 == 0, "the cooperative lookup takes the k-mers two at a time");
-                        // The cooperative rounds keep 64 lines in flight per warp (their registers); the trip's other 64
-                        // used to start only after those had come back from HBM.  Prefetches cost no registers: all 128
-                        // home buckets of the trip are requested into L2 right away, and the second pair of lookups --
-                        // like every chain step -- finds its lines there or already on the way.
-                        uint32_t home[kIlp];
-#pragma unroll
-                        for (int u = 0; u < kIlp; u++) {
-                            home[u] = bucket_of(h[u], a.tab.n_buckets);
-#if HS_COOP_PREFETCH
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(a.tab.buckets + (size_t)home[u] * kBucketWords));
-#endif
-                        }
+                        // (Measured dead end: requesting all 128 home buckets of the trip with prefetch.global.L2 before
+                        // the first cooperative round -- no registers, the second pair of lookups would find its lines in
+                        // L2 -- made the kernel 1.5x SLOWER, 37.8 -> 55.8 ms per Gbp.)
 #pragma unroll
                         for (int u = 0; u < kIlp; u += 2) {     // all 32 lanes, every trip: 64 probes, 16 lines in flight per lane
                             const uint64_t hh[2] = {h[u], h[u + 1]};
-                            const uint32_t hb[2] = {home[u], home[u + 1]};
                             const bool want[2] = {valid[u] && a.do_count && (!a.do_filter || h[u] <= a.tab.max_key),
                                                   valid[u + 1] && a.do_count && (!a.do_filter || h[u + 1] <= a.tab.max_key)};
                             uint32_t id[2];
                             n_probe += (uint32_t)want[0] + (uint32_t)want[1];
-                            coop_probe<2>(a.tab, hh, want, id, n_reads, hb);
+                            coop_probe<2>(a.tab, hh, want, id, n_reads);
 #pragma unroll
                             for (int w2 = 0; w2 < 2; w2++)
                                 if (id[w2] != kNoEntry) {
@@ -631,7 +631,11 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                         for (int u = 0; u < kIlp; u++) {
                             const int j = half * 16 + q + u;
                             // (high word of the low gate: a superset; the sink repeats every test exactly)
+#if HS_BLOOM_HI_GATE
                             const bool enter = (uint32_t)(h[u] >> 32) <= lowgate_hi || (pre[u] & bbits[u]) == bbits[u];
+#else
+                            const bool enter = h[u] <= lowgate || (pre[u] & bbits[u]) == bbits[u];
+#endif
                             if (enter && (!decltype(check)::value || ((ok >> (31 - j)) & 1u))) sink(j, h[u], pre[u]);
                         }
                     } else {
@@ -684,7 +688,7 @@ static cudaError_t launch_stream_t(const StreamArgs &a, int sm_count, cudaStream
             if ((e = cudaFuncGetAttributes(&fa, k_stream<KT, MODE>)) != cudaSuccess) return e;
             const uint32_t start = 1024u + (((uint32_t)fa.sharedSizeBytes + 15u) & ~15u);
             const uint32_t d = (((start + kLutBytes - 1) & ~(kLutBytes - 1)) - start) + 2 * kPreBytes +
-                               (stream_tail_table(KT) ? kTailBytes : 0u);
+                               (stream_tail_table(KT, MODE) ? kTailBytes : 0u);
             if ((e = cudaFuncSetAttribute(k_stream<KT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d)) != cudaSuccess) return e;
             int o = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_stream<KT, MODE>, kCtaThreads, d);

@@ -142,7 +142,10 @@ int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
  * "ingest" 0/1/2 = host packer only / device parser only / both compete (default; packer
  * threads join when at least six were asked for); "file_readers", "file_block_bytes" = reader
  * threads and nominal block size of the pinned ring that streams plain FASTA files (defaults
- * 4 x 8 MiB: sized for a one-shot process, pinning costs ~0.5 ms per MB); "text_chunk_bytes" =
+ * 4 x 8 MiB: sized for a one-shot process, pinning costs ~0.5 ms per MB); "file_mode" 0/1/-1 = plain
+ * FASTA files go through that ring to the device parser / are mapped and packed by the host threads
+ * where the page cache holds them / chosen by host capability (default: mapped when the packer has
+ * its AVX-512 path and at least four threads); "text_chunk_bytes" =
  * bytes of gzip / stdin FASTA inflated per hand-over to the packer threads (default 256 MiB;
  * cut at record starts, FASTQ is read whole); "ingest_slots" (1-4), "ingest_batch" (1-8) = depth
  * and granularity of the device parser's raw-text queue. */

@@ -729,11 +729,17 @@ def test_file_streaming_blocks_and_giant_records(tmp_path, variant):
     open(path, "wb").write(text)
     want = odb.screen_text(text, threads=2)
     assert int(want.shared.sum()) >= 1000
-    for block, readers in ((65536, 3), (1 << 20, 2), (16 << 20, 4)):
+    # file_mode 0: pread ring -> device parser; 1: the file mapped and packed by the host threads (16 KiB spans:
+    # hundreds of them, so both the 64-byte block path of the packer and its line path meet every boundary)
+    for mode, block, readers in ((0, 65536, 3), (0, 1 << 20, 2), (0, 16 << 20, 4), (1, 0, 4), (1, 16384, 5)):
         scr = hs.Screen(db)
-        scr.set_option("file_block_bytes", block)
-        scr.set_option("file_readers", readers)
-        scr.feed_fasta(path, 4)
+        scr.set_option("file_mode", mode)
+        if mode == 0:
+            scr.set_option("file_block_bytes", block)
+            scr.set_option("file_readers", readers)
+        elif block:
+            scr.set_option("chunk_bases", block)
+        scr.feed_fasta(path, readers if mode else 4)
         res = scr.finish(False)
         assert res.shared.tolist() == want.shared.tolist(), (variant, block)
         assert res.median.tolist() == want.median.tolist()

@@ -34,12 +34,46 @@ def run(label, thr, reps=4):
 
 for mode, name in ((0, "host"), (2, "hybrid"), (1, "device")):
     scr.set_option("ingest", mode)
-    for chunk in (4, 8, 16, 32):
+    for chunk in (16,):
         scr.set_option("chunk_bases", chunk << 20)
-        for thr in ((nthreads, nthreads - 2, nthreads // 2) if mode != 1 else (nthreads,)):
+        for thr in (nthreads,):
             run("%s chunk %2d MB" % (name, chunk), thr)
         if mode == 1:
             break
+scr.set_option("ingest", 2); scr.set_option("chunk_bases", 16 << 20)
+for slots in (2, 4):
+    for batch in (1, 2, 3):
+        scr.set_option("ingest_slots", slots); scr.set_option("ingest_batch", batch)
+        run("hybrid 16 MB slots %d batch %d" % (slots, batch), nthreads)
+scr.set_option("ingest_slots", 4); scr.set_option("ingest_batch", 3)
+
+# the same text as a FILE in the page cache
+import tempfile
+fdir = tempfile.mkdtemp(prefix="hs_e2e_")
+fpath = os.path.join(fdir, "contigs.fna")
+wl.fasta.numpy().tofile(fpath)
+def run_file(label, thr, reps=4):
+    best = None
+    for rep in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        scr.reset()
+        scr.feed_fasta(fpath, thr)
+        t1 = time.perf_counter()
+        r = scr.finish_hits()
+        t2 = time.perf_counter()
+        if rep and (best is None or t2 - t0 < best[0]):
+            best = (t2 - t0, t1 - t0, t2 - t1, r.stats)
+    tot, feed, fin, st = best
+    print("%-34s thr=%2d total %6.2f ms feed %6.2f finish %5.2f -> %6.1f Gbp/s  launches %4d stream %5.2f ms h2d %4d MB" % (
+        label, thr, 1e3 * tot, 1e3 * feed, 1e3 * fin, wl.n_bases / tot / 1e9, st["n_launches"], st["ms_stream"], st["h2d_bytes"] >> 20), flush=True)
+scr.set_option("file_mode", 0); scr.set_option("file_readers", 8); scr.set_option("file_block_bytes", 16 << 20)
+run_file("file: pread ring + device parser", nthreads)
+scr.set_option("file_mode", 1)
+for chunk in (8, 16):
+    scr.set_option("chunk_bases", chunk << 20)
+    run_file("file: mmap + host packers %d MB" % chunk, nthreads)
+os.remove(fpath); os.rmdir(fdir)
 scr.set_option("ingest", 0); scr.set_option("chunk_bases", 16 << 20)
 
 # host packer alone on the pinned text, per thread count and level

@@ -515,10 +515,25 @@ def run_b200(args):
                 return solo.finish_hits(args.wta)
 
             n_solo = max(2, min(args.steps, 5))
-            sms, _, _, sres, _ = timed(step_solo, n_solo, 2, collective=False)
+            sms, _, sstats, sres, _ = timed(step_solo, n_solo, 2, collective=False)
+            s_stream = sum(x["ms_stream"] for x in sstats) / len(sstats)
+            s_fixed = sum(x["ms_reduce"] + x["ms_reset"] for x in sstats) / len(sstats)
             line["single_gpu_same_workload"] = {"value": n_solo * total_bases / (sms * 1e-3) / 1e6, "unit": UNIT,
                                                 "ms_per_step": sms / n_solo, "steps": n_solo,
+                                                "stream_kernel_ms": s_stream, "mixture_reduce_reset_ms": s_fixed,
                                                 "what": "all %d shards screened by rank 0 alone, same table, same run" % world}
+            # where the strong-scaling loss goes: step = T1 / N + (what does not divide by N)
+            t1, tn = sms / n_solo, ms / args.steps
+            line["scaling_loss"] = {
+                "efficiency_vs_same_run_single_gpu": t1 / (world * tn),
+                "ideal_ms_per_step": t1 / world, "actual_ms_per_step": tn, "excess_ms": tn - t1 / world,
+                "attribution_ms": {
+                    "stream_kernel_above_its_share": ms_stream - s_stream / world,
+                    "replicated_mixture_reduce_reset (does not shrink with N; its single-GPU share is already in the ideal)":
+                        (ms_reduce + ms_reset) - s_fixed / world,
+                    "exchange_host_gaps_result_copy": (tn - ms_stream - ms_reduce - ms_reset) - (t1 - s_stream - s_fixed) / world},
+                "note": "stream_kernel_above_its_share = smaller launches (tile quantisation over 592 CTAs, per-launch table fill) and "
+                        "rank imbalance; the all-gather of (hash id, count) records runs underneath the mixture finaliser"}
             line["parity_vs_single"] = ("bit-exact (shared, median, set size, identity, p-value of all %d sketches; %d shared hashes)"
                                         % (n_sketches, int(res.shared.sum()))) if results_equal(sres, res) else "MISMATCH"
             solo.close()

@@ -812,6 +812,7 @@ HS_API int hs_init(int device)
     g_device = device;
     g_sm = p.multiProcessorCount;
     g_debug_timing = getenv("HYMET_SCREEN_DEBUG_TIMING") != nullptr;
+    if (const char *e = getenv("HYMET_PACK_STREAMING")) set_pack_streaming(atoi(e) != 0);
     return HS_OK;
 }
 
@@ -1194,17 +1195,26 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     std::atomic<int> pack_us_per_span{(int)(s->chunk_text / 5000) + 1};   // pace of one packer thread (EMA; ~5 GB/s to start with)
     std::string err_all;
     std::mutex err_mu;
-    auto worker = [&](int t) {
+    // Each side may leave the rest of the spans to the other (below); `device_quit` and `packers_alive` make
+    // sure the two never do so at the same time: whoever wants to stop announces it first and then looks at
+    // the other's announcement (sequentially consistent atomics: at least one of them sees the other's).
+    std::atomic<bool> device_quit{!use_device};
+    std::atomic<int> packers_alive{threads};
+    auto worker = [&](int t, bool may_yield) {
         cudaSetDevice(s->db->device);
         int flip = 0;
         double my_ms = 4.0;  // how long this thread needs to pack one span
         for (;;) {
-            if (use_device) {
+            if (use_device && may_yield && !device_quit.load()) {
                 // do not start a span the DMA + device parser would finish before we do: near the end
                 // of the input a slow packer thread would otherwise be the tail of the whole feed
                 const size_t nx = next.load();
                 if (nx >= spans.size()) break;
-                if ((double)(spans.size() - nx) * dev_us_per_span.load() * 1e-3 < my_ms) break;
+                if ((double)(spans.size() - nx) * dev_us_per_span.load() * 1e-3 < my_ms) {
+                    packers_alive.fetch_sub(1);
+                    if (!device_quit.load()) return;     // the device worker is still there and will see one packer fewer
+                    packers_alive.fetch_add(1);          // it has stopped taking spans: stay
+                }
             }
             const size_t i = next.fetch_add(1);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;
@@ -1245,6 +1255,7 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
                 break;
             }
         }
+        if (may_yield) packers_alive.fetch_sub(1);
     };
     // the device-ingest worker competes with the packer threads for spans: it costs no CPU
     // (one cudaMemcpyAsync + kernel launches per span) and is throttled by its raw-text slots
@@ -1266,9 +1277,14 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
                 for (int q = 0; q < s->ingest.n_slots; q++)
                     if (s->ingest.slots[q].done && cudaEventQuery(s->ingest.slots[q].done) == cudaErrorNotReady) busy++;
                 cudaGetLastError();
-                const double rest_ms = (double)(spans.size() - nx) * pack_us_per_span.load() * 1e-3 / threads;
+                const int alive = packers_alive.load();
+                const double rest_ms = (double)(spans.size() - nx) * pack_us_per_span.load() * 1e-3 / (alive > 0 ? alive : 1);
                 const double mine_ms = (double)(busy + 1) * (double)batch * dev_us_per_span.load() * 1e-3 + 0.3;
-                if (rest_ms < mine_ms) break;
+                if (alive > 0 && rest_ms < mine_ms) {
+                    device_quit.store(true);
+                    if (packers_alive.load() > 0) break;   // somebody is left to take the rest
+                    device_quit.store(false);              // the last packer has just left it to us
+                }
             }
             const size_t i = next.fetch_add(batch);
             if (i >= spans.size() || rc_all.load() != HS_OK) break;
@@ -1293,12 +1309,21 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
         }
     };
     if (threads == 1 && !use_device) {
-        worker(0);
+        worker(0, false);
     } else {
         std::vector<std::thread> pool;
         if (use_device) pool.emplace_back(device_worker);
-        for (int t = 0; t < threads; t++) pool.emplace_back(worker, t);
+        for (int t = 0; t < threads; t++) pool.emplace_back(worker, t, true);
         for (auto &th : pool) th.join();
+    }
+    // belt and braces: every span is fed exactly once whatever the two sides decided
+    if (rc_all == HS_OK && next.load() < spans.size()) {
+        while (s->staging.size() < 2) {
+            Staging g;
+            CU(cudaEventCreateWithFlags(&g.free_ev, cudaEventDisableTiming));
+            s->staging.push_back(g);
+        }
+        worker(0, false);
     }
     if (rc_all != HS_OK) return fail(rc_all, err_all);
     return HS_OK;

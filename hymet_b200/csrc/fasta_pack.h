@@ -31,6 +31,8 @@ uint64_t pack_text_span(const char *text, size_t n, uint64_t *seq, uint32_t *inv
 // compare them bit for bit.
 void set_pack_level(int level);
 int pack_level();
+// AVX-512 path: write the packed words with non-temporal stores (output that only a DMA engine reads next)
+void set_pack_streaming(bool on);
 
 // Split [text, text+n) into <= parts spans that each begin at a line starting with
 // '>' (FASTA).  FASTQ input ('@' first) is returned as a single span.

@@ -128,9 +128,11 @@ def test_sparse_record_exchange_protocol_world2():
 
 def test_record_helpers():
     assert hd.next_cap(0, 4096, 10 ** 6) == 4096
-    assert hd.next_cap(276_000, 1 << 20, 5 * 10 ** 7) == 1 << 19          # C2: a quarter million pairs -> 4 MB records
-    assert hd.next_cap(276_000, 1 << 19, 5 * 10 ** 7) == 1 << 19          # stays
-    assert hd.next_cap(600_000, 1 << 19, 5 * 10 ** 7) == 1 << 20          # overflow: grows
+    assert hd.next_cap(276_000, 1 << 20, 5 * 10 ** 7) == 393_216          # C2: a quarter million pairs -> 3 MB records
+    assert hd.next_cap(276_000, 393_216, 5 * 10 ** 7) == 393_216          # stays
+    assert hd.next_cap(300_000, 393_216, 5 * 10 ** 7) == 393_216          # ... also when the count moves a little
+    assert hd.next_cap(600_000, 393_216, 5 * 10 ** 7) == 786_432          # overflow: grows
+    assert hd.next_cap(1_467_217, 1 << 22, 3 * 10 ** 8) == 1_835_008      # C3 at two GPUs: 14 MB instead of 32
     assert hd.next_cap(10 ** 6, 4096, 5000) == 5000                        # never more than one pair per entry
     ids = np.array([0, 7, 2 ** 31 + 5], np.int64); cnt = np.array([1, 2 ** 32 - 1, 9], np.uint32)
     i2, c2 = hd.unpack_pairs(hd.pack_pairs(ids, cnt))

@@ -45,7 +45,8 @@ class Stats(C.Structure):
                 ("n_launches", C.c_uint32), ("n_mix_passes", C.c_uint32),
                 ("ms_stream", C.c_float), ("ms_reduce", C.c_float), ("ms_reset", C.c_float),
                 ("reduce_path", C.c_uint32), ("n_touched", C.c_uint32), ("n_hit_refs", C.c_uint32),
-                ("n_pairs", C.c_uint32), ("exchange_overflow", C.c_uint32), ("exchange_max_pairs", C.c_uint32)]
+                ("n_pairs", C.c_uint32), ("exchange_overflow", C.c_uint32), ("exchange_max_pairs", C.c_uint32),
+                ("mix_unsettled", C.c_uint32)]
 
     def asdict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -87,6 +88,7 @@ SIGNATURES = {
     "hs_pack_text_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint64, u64p,
                                       C.POINTER(Stats)]),
     "hs_screen_flush": (C.c_int, [C.c_void_p]),
+    "hs_screen_flush_async": (C.c_int, [C.c_void_p]),
     "hs_screen_counts_devptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), u64p]),
     "hs_screen_counts_compact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
     "hs_screen_counts_compact_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),

@@ -383,6 +383,9 @@ struct hs_screen {
     MixEngine mix;
     std::vector<uint64_t> mixture;  // settled s smallest distinct hashes, ascending
     bool flushed = false;
+    bool flush_pending = false;   // hs_screen_flush_async: selection enqueued, verdict read after the next synchronisation
+    bool flush_parsed = false;    // ... and it fetched the device parser's totals
+    int force_unsettled = 0;      // tests: the next mixture record says "not settled" (HYMET_SCREEN_FORCE_UNSETTLED)
     uint32_t *d_shared = nullptr, *d_median = nullptr;
     double *d_identity = nullptr, *d_pvalue = nullptr;
     unsigned long long *d_best_score = nullptr, *d_best_len = nullptr;
@@ -613,6 +616,7 @@ int screen_zero(hs_screen *s)
     s->mix.passes = 1;
     s->mixture.clear();
     s->flushed = false;
+    s->flush_pending = false;
     s->chunks.clear();
     if (s->copy_stream) CU(cudaStreamSynchronize(s->copy_stream));
     s->arena.reset();
@@ -998,6 +1002,7 @@ HS_API int hs_screen_new(hs_db *db, hs_screen **out)
     if (const char *e = getenv("HYMET_SCREEN_TOUCHED_CAP")) s->touched_cap = (uint32_t)std::max(1ll, atoll(e));   // tests: force the fallbacks
     if (const char *e = getenv("HYMET_SCREEN_PAIR_CAP")) s->pair_cap = (uint32_t)std::max(1ll, atoll(e));
     if (const char *e = getenv("HYMET_SCREEN_SPARSE")) s->sparse_enabled = atoi(e) != 0;
+    if (const char *e = getenv("HYMET_SCREEN_FORCE_UNSETTLED")) s->force_unsettled = atoi(e);
     CUB(cudaMalloc((void **)&s->d_sparse, sizeof(SparseState)));
     CUB(cudaMemsetAsync(s->d_sparse, 0, sizeof(SparseState), s->stream));
     CUB(cudaHostAlloc((void **)&s->h_sparse, sizeof(SparseState), cudaHostAllocDefault));
@@ -1612,12 +1617,79 @@ HS_API int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const 
     return launch_chunk(s, c, true, true);
 }
 
+namespace {
+
+// what hs_screen_flush does once the stream has been synchronised: counters, timings, state
+int flush_epilogue(hs_screen *s, bool parsed)
+{
+    unsigned long long *h = s->h_stats, *t = s->h_stats + ST_COUNT;
+    if (parsed) { s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2]; }
+    s->st.n_valid_kmers = h[ST_VALID]; s->st.n_probes = h[ST_PROBES]; s->st.n_bucket_reads = h[ST_BUCKETS];
+    s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
+    s->st.n_mix_passes = s->mix.passes;
+    s->st.n_mixture = s->mixture.size();
+    s->st.set_size = set_size_of(s->mixture, s->db->use64, s->db->seg_s[0]);
+    int rc = collect_stream_ms(s);
+    if (rc) return rc;
+    if (s->rst_pending) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, s->rst0, s->rst1));
+        s->st.ms_reset = ms;
+        s->rst_pending = false;
+    }
+    return HS_OK;
+}
+
+}  // namespace
+
+// Rows a8-a10 without waiting: the device-side selection of the local bottom-s is ENQUEUED, its result and
+// the counters travel to pinned memory behind it, and nothing is looked at until the caller's next
+// synchronisation (hs_screen_finish*), which then completes the flush.  In between the caller may
+// enqueue the whole multi-GPU exchange -- hs_screen_mixture_record reads the selection where it lies on
+// the device -- so that one screen is ONE host synchronisation and the host runs ahead of the GPU from
+// the first feed to the result.  If the selection does not hold (set overflowed, fewer than s values
+// below tau, a crowded bin) the record says so, every rank sees it after the all-gather
+// (hs_stats_t.mix_unsettled), and the caller falls back to hs_screen_flush + the synchronous exchange.
+HS_API int hs_screen_flush_async(hs_screen *s)
+{
+    if (!s) return fail(HS_EINVAL, "null handle");
+    ON_DEVICE(s->db->device);
+    if (s->flushed || s->flush_pending) return HS_OK;
+    if (!s->mix.fast_select) return hs_screen_flush(s);
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaEventRecord(s->red0, s->stream));
+    const bool parsed = s->ingest.ready && s->ingest.counters_used;
+    CU(cudaMemcpyAsync(s->h_stats, s->d_stats, ST_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+    if (parsed) {
+        CU(cudaMemcpyAsync(s->h_stats + ST_COUNT, s->ingest.d_totals, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemsetAsync(s->ingest.d_totals, 0, 4 * sizeof(unsigned long long), s->stream));
+    }
+    MixEngine &m = s->mix;
+    CU(launch_mix_select(m.view(~0ull), m.s, m.use64, m.d_hist, m.d_cand, m.sel_pad, m.d_scratch, s->stream));
+    s->st.n_launches += 4;
+    CU(cudaMemcpyAsync(m.h_cand, m.d_cand, (size_t)m.s * 8, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(m.h_state, m.d_state, sizeof(MixState), cudaMemcpyDeviceToHost, s->stream));
+    s->flush_pending = true;
+    s->flush_parsed = parsed;
+    return HS_OK;
+}
+
 HS_API int hs_screen_flush(hs_screen *s)
 {
     if (!s) return fail(HS_EINVAL, "null handle");
     ON_DEVICE(s->db->device);
     if (s->flushed) return HS_OK;
     std::lock_guard<std::mutex> lk(s->mu);
+    if (s->flush_pending) {
+        // an enqueued selection is abandoned (its verdict was "not settled", or the caller changed its mind):
+        // the iterative finaliser below starts from the same device state
+        CU(cudaStreamSynchronize(s->stream));
+        if (s->flush_parsed) {   // the parser totals were folded into h_stats and cleared on the device: keep them
+            unsigned long long *t = s->h_stats + ST_COUNT;
+            s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2];
+        }
+        s->flush_pending = false;
+    }
     CU(cudaEventRecord(s->red0, s->stream));
     // the counters are final once the streaming launches are (re-offer passes count elsewhere): fetch
     // them with the first synchronisation of the mixture finaliser instead of one of their own
@@ -1639,22 +1711,11 @@ HS_API int hs_screen_flush(hs_screen *s)
     if (rc) return rc;
     CU(cudaEventRecord(s->red1, s->stream));
     CU(cudaEventSynchronize(s->red1));   // mix_finalize ended on a synchronisation: nothing is left to wait for
-    if (parsed) { s->st.n_positions += t[0]; s->st.n_bases += t[1]; s->st.n_records += t[2]; }
-    s->st.n_valid_kmers = h[ST_VALID]; s->st.n_probes = h[ST_PROBES]; s->st.n_bucket_reads = h[ST_BUCKETS];
-    s->st.n_hits = h[ST_HITS]; s->st.n_mix_inserts = h[ST_MIXINS];
-    s->st.n_mix_passes = s->mix.passes;
-    s->st.n_mixture = s->mixture.size();
-    s->st.set_size = set_size_of(s->mixture, s->db->use64, s->db->seg_s[0]);
-    rc = collect_stream_ms(s);
+    rc = flush_epilogue(s, parsed);
     if (rc) return rc;
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
     s->st.ms_reduce = ms;
-    if (s->rst_pending) {
-        CU(cudaEventElapsedTime(&ms, s->rst0, s->rst1));
-        s->st.ms_reset = ms;
-        s->rst_pending = false;
-    }
     s->flushed = true;
     return HS_OK;
 }
@@ -1786,6 +1847,14 @@ HS_API int hs_screen_mixture_record(hs_screen *s, void *d_record)
 {
     if (!s || !d_record) return fail(HS_EINVAL, "null argument");
     ON_DEVICE(s->db->device);
+    if (s->flush_pending) {
+        // the selection is still on its way: the record is cut out of it on the device, verdict included
+        CU(launch_mix_record(s->mix.view(~0ull), s->db->s, s->mix.sel_pad, s->mix.d_cand, (unsigned long long *)d_record,
+                             s->force_unsettled, s->stream));
+        s->force_unsettled = 0;
+        s->st.n_launches++;
+        return HS_OK;
+    }
     if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
     // [length | s hashes, zero padded]: what every rank contributes to the mixture all-gather.  The
     // settled local mixture is <= s values; it goes up from pinned memory on the screen's stream and
@@ -1802,7 +1871,7 @@ HS_API int hs_screen_mixture_merge_device(hs_screen *s, const void *d_rows, uint
 {
     if (!s || !d_rows || !n_rows) return fail(HS_EINVAL, "null argument");
     ON_DEVICE(s->db->device);
-    if (!s->flushed) return fail(HS_ESTATE, "call hs_screen_flush first");
+    if (!s->flushed && !s->flush_pending) return fail(HS_ESTATE, "call hs_screen_flush first");
     const uint32_t sc = s->db->s;
     uint32_t need = 2;
     while (need < (uint64_t)n_rows * sc) need <<= 1;
@@ -1872,6 +1941,7 @@ int enqueue_reduce(hs_screen *s, bool wta, bool dense)
         a.lengths = db->d_lengths; a.seg_begin = db->d_seg_begin; a.n_seg = (uint32_t)n_seg;
         a.shared = s->d_shared; a.median = s->d_median; a.plain = s->d_plain; a.hit = s->d_hit;
         a.seg_start = s->d_seg_start; a.seg_fill = s->d_seg_fill; a.depths = s->d_depths; a.pair_cap = s->pair_cap;
+        a.ref_scale = (E && N <= E) ? (uint64_t)((((unsigned __int128)N) << 64) / ((unsigned __int128)E + 1)) : 0;
         CU(launch_sparse_reduce(a, wta, db->sm, s->stream));
         s->st.n_launches += wta ? 7 : 4;
         return HS_OK;
@@ -1967,7 +2037,8 @@ int finish_core(hs_screen *s, bool wta, bool hits)
     // Single-GPU order: the per-sketch reduction needs only counts[], so it is enqueued BEFORE the
     // mixture is settled and runs underneath the host round trips of that (flush); a caller that
     // flushed first (multi-GPU: flush -> exchange -> finish) gets it here, after the exchange.
-    const bool early = !s->flushed;
+    const bool pending = s->flush_pending;
+    const bool early = !s->flushed && !pending;
     bool dense = !(s->sparse_enabled && s->touched_valid);
     int rc;
     if (early) {
@@ -1975,21 +2046,51 @@ int finish_core(hs_screen *s, bool wta, bool hits)
         if ((rc = enqueue_reduce(s, wta, dense)) != HS_OK) return rc;
         CU(cudaEventRecord(s->red3, s->stream));
     }
-    rc = hs_screen_flush(s);
-    if (rc) return rc;
+    if (!pending) {
+        rc = hs_screen_flush(s);
+        if (rc) return rc;
+        CU(cudaEventRecord(s->red0, s->stream));
+    }   // (pending: red0 was recorded by hs_screen_flush_async -- the exchange in between is part of the figure)
     if (early) {
         float ems = 0;
         CU(cudaEventElapsedTime(&ems, s->red2, s->red3));   // flush synchronised the stream
         s->st.ms_reduce += ems;
     }
-    CU(cudaEventRecord(s->red0, s->stream));
     if (!early && (rc = enqueue_reduce(s, wta, dense)) != HS_OK) return rc;
     if ((rc = hits ? enqueue_hits(s, dense) : enqueue_stats_and_copy(s)) != HS_OK) return rc;
     CU(cudaEventRecord(s->red1, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, s->red0, s->red1));
-    s->st.ms_reduce += ms;
+    s->st.ms_reduce = pending ? ms : s->st.ms_reduce + ms;
+    s->st.mix_unsettled = 0;
+    if (pending) {
+        // the one synchronisation of this screen has happened: complete the flush from what came back with it
+        const MixState &hs_ = *s->mix.h_state;
+        const bool held = !s->force_unsettled && !hs_.overflow && !hs_.sel_too_many && hs_.n_out <= s->mix.sel_pad &&
+                          (hs_.n_unique >= s->mix.s || hs_.tau == ~0ull);
+        s->force_unsettled = 0;   // (tests; the multi-GPU path has already spent it in its mixture record)
+        const bool all_held = s->mixture_on_device ? !s->h_sparse->mix_unsettled : held;
+        if (!all_held) {
+            if (s->mixture_on_device) {
+                // some rank's selection fell through: every rank knows (the gathered records say so) and the
+                // CALLER redoes flush + mixture exchange synchronously; the counts were absorbed and stay
+                s->st.mix_unsettled = 1;
+                s->st.exchange_overflow = s->h_sparse->xchg_overflow;
+                s->st.exchange_max_pairs = s->h_sparse->xchg_max;
+                return HS_OK;
+            }
+            rc = hs_screen_flush(s);              // single process: the iterative finaliser, then everything again
+            if (rc) return rc;
+            return finish_core(s, wta, hits);
+        }
+        s->mixture.assign(s->mix.h_cand, s->mix.h_cand + std::min(hs_.n_unique, s->mix.s));
+        if (hs_.has_max && s->mixture.size() < s->mix.s) s->mixture.push_back(~0ull);
+        s->flush_pending = false;
+        rc = flush_epilogue(s, s->flush_parsed);
+        if (rc) return rc;
+        s->flushed = true;
+    }
     if (s->mixture_on_device) {   // the merged mixture and its set size arrive with the results
         const uint32_t nm = std::min<uint32_t>(s->h_sparse->n_mix, db->s);
         s->mixture.assign(s->h_mixture, s->h_mixture + nm);

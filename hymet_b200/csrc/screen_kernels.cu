@@ -380,6 +380,10 @@ struct SmemPremul {
 #ifndef HS_MIN_CTAS
 #define HS_MIN_CTAS 4   // 48 KB of shared memory per CTA
 #endif
+#ifndef HS_BLOOM_LD
+#define HS_BLOOM_LD __ldcg    // the Bloom tier's filter words are read through L2 only: with them out of L1 the
+                              // tail-term table pays in that instantiation too (tiny-genome DB: 6.30 -> 6.18 ms; with __ldg 6.50)
+#endif
 #ifndef HS_BLOOM_HI_GATE
 #define HS_BLOOM_HI_GATE 1
 #endif
@@ -388,7 +392,8 @@ struct SmemPremul {
 #endif
 // compile-time k with a 1..5 letter tail (k = 21): the tail term comes from its own table
 #ifndef HS_TAIL_MODES
-#define HS_TAIL_MODES 0x3   // bit m: instantiation MODE m uses the table (it takes 8 KB from the L1 of every CTA)
+#define HS_TAIL_MODES 0x7   // bit m: instantiation MODE m uses the table (it takes 8 KB from the L1 of every CTA: not the
+                            // probe-everything kernel, which lives on L1/L2 traffic)
 #endif
 __host__ __device__ constexpr bool stream_tail_table(int kt, int mode)
 {
@@ -585,9 +590,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                             pre[u] = 0u;                               // fails the test below: bbits is never 0
                             // (high words only: a superset of h <= max_key, and the word index is masked into range)
 #if HS_BLOOM_HI_GATE
-                            if ((uint32_t)(h[u] >> 32) <= max_hi) pre[u] = __ldg(a.tab.bloom + bw);
+                            if ((uint32_t)(h[u] >> 32) <= max_hi) pre[u] = HS_BLOOM_LD(a.tab.bloom + bw);
 #else
-                            if (h[u] <= a.tab.max_key) pre[u] = __ldg(a.tab.bloom + bw);
+                            if (h[u] <= a.tab.max_key) pre[u] = HS_BLOOM_LD(a.tab.bloom + bw);
 #endif
                         }
                     }
@@ -605,7 +610,9 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
                         static_assert(kIlp % 2 == 0, "the cooperative lookup takes the k-mers two at a time");
                         // (Measured dead end: requesting all 128 home buckets of the trip with prefetch.global.L2 before
                         // the first cooperative round -- no registers, the second pair of lookups would find its lines in
-                        // L2 -- made the kernel 1.5x SLOWER, 37.8 -> 55.8 ms per Gbp.)
+                        // L2 -- made the kernel 1.5x SLOWER, 37.8 -> 55.8 ms per Gbp.  So did software pipelining --
+                        // request a pair's lines, hash the next pair, then look: the flight's state (16 x 2 registers
+                        // + hashes + buckets) went to local memory at 120 registers, 2 CTAs per SM: 81 ms.)
 #pragma unroll
                         for (int u = 0; u < kIlp; u += 2) {     // all 32 lanes, every trip: 64 probes, 16 lines in flight per lane
                             const uint64_t hh[2] = {h[u], h[u + 1]};
@@ -1863,9 +1870,20 @@ __device__ __forceinline__ bool sparse_ok(const SparseView &sp, uint32_t &n)
     return sparse_list(sp, n) && !__ldcg(&sp.st->wrapped);
 }
 
-// reference that owns entry e: the largest i with offsets[i] <= e (offsets[0] = 0 <= e < offsets[n_refs])
-__device__ __forceinline__ uint32_t ref_of_entry(const uint64_t *offsets, uint32_t n_refs, uint64_t e)
+// reference that owns entry e: the largest i with offsets[i] <= e (offsets[0] = 0 <= e < offsets[n_refs]).
+// Sketches of one database nearly all hold s hashes, so e * n_refs / E is the answer or next to it: two
+// loads instead of the ~18 dependent ones of a binary search over 300 000 offsets (the search stays as
+// the fallback for databases with uneven sketch sizes).
+__device__ __forceinline__ uint32_t ref_of_entry(const uint64_t *offsets, uint32_t n_refs, uint64_t e, uint64_t scale = 0)
 {
+    if (scale) {
+        uint32_t g = (uint32_t)__umul64hi(e, scale);
+        if (g >= n_refs) g = n_refs - 1;
+        const uint64_t a = __ldg(offsets + g), b = __ldg(offsets + g + 1);
+        if (a <= e && e < b) return g;
+        if (e >= b && g + 2 <= n_refs && e < __ldg(offsets + g + 2)) return g + 1;
+        if (e < a && g > 0 && __ldg(offsets + g - 1) <= e) return g - 1;
+    }
     uint32_t lo = 0, hi = n_refs;
     while (hi - lo > 1u) {
         const uint32_t mid = (lo + hi) >> 1;
@@ -1883,7 +1901,7 @@ __device__ __forceinline__ uint32_t chain_winner(const SparseReduceArgs &a, uint
     unsigned long long best_s = 0, best_l = 0;
     uint32_t best_i = kNoEntry;
     for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) {
-        const uint32_t i = ref_of_entry(a.offsets, a.n_refs, e);
+        const uint32_t i = ref_of_entry(a.offsets, a.n_refs, e, a.ref_scale);
         if (i < lo || i >= hi) continue;
         const uint32_t sh = a.plain[i];
         const uint64_t size = a.offsets[i + 1] - a.offsets[i];
@@ -1915,7 +1933,7 @@ __global__ void __launch_bounds__(256) k_sparse_walk(const SparseReduceArgs a)
         const uint32_t c = __ldcg(a.counts + t);
         if (!c) continue;
         if (!WTA) {
-            for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) visit(ref_of_entry(a.offsets, a.n_refs, e), c);
+            for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) visit(ref_of_entry(a.offsets, a.n_refs, e, a.ref_scale), c);
         } else {
             for (uint32_t j = 0; j < a.n_seg; j++) {
                 const uint32_t w = chain_winner(a, t, j);
@@ -2132,7 +2150,9 @@ __global__ void __launch_bounds__(256) k_mixture_gather(const unsigned long long
         uint64_t v = kEmptyKey;
         if (x < n_rows * s_cap) {
             const uint32_t r = x / s_cap, i = x % s_cap;
-            const uint32_t len = (uint32_t)min((unsigned long long)s_cap, rows[r * stride]);
+            const unsigned long long len64 = rows[r * stride];
+            if (len64 == kMixUnsettled) { if (i == 0) atomicExch(&st->mix_unsettled, 1u); }   // that rank's selection fell through
+            const uint32_t len = len64 == kMixUnsettled ? 0u : (uint32_t)min((unsigned long long)s_cap, len64);
             if (i < len) {
                 v = rows[r * stride + 1 + i];
                 if (v == kEmptyKey) atomicExch(&st->mix_has_max, 1u);
@@ -2164,12 +2184,36 @@ __global__ void k_mixture_finish(const uint64_t *sorted, const uint32_t *n_uniqu
     }
 }
 
+// the device-side selection's own verdict (the host applies the same test to the state it gets back)
+__global__ void __launch_bounds__(256) k_mix_record(const MixView v, uint32_t s, uint32_t sel_pad, const uint64_t *cand,
+                                                    unsigned long long *record, int force_unsettled)
+{
+    const MixState *st = v.st;
+    const bool ok = !force_unsettled && !st->overflow && !st->sel_too_many && st->n_out <= sel_pad &&
+                    (st->n_unique >= s || st->tau == ~0ull);
+    uint32_t n = min(st->n_unique, s);
+    for (uint32_t i = threadIdx.x; i < s; i += blockDim.x) record[1 + i] = (ok && i < n) ? cand[i] : 0ull;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (ok && st->has_max && n < s) record[1 + n++] = kEmptyKey;   // hash == 2^64-1 present
+        record[0] = ok ? (unsigned long long)n : kMixUnsettled;
+    }
+}
+
+cudaError_t launch_mix_record(const MixView &v, uint32_t s, uint32_t sel_pad, const uint64_t *cand, unsigned long long *record,
+                              int force_unsettled, cudaStream_t st)
+{
+    k_mix_record<<<1, 256, 0, st>>>(v, s, sel_pad, cand, record, force_unsettled);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mixture_merge(const unsigned long long *rows, uint32_t n_rows, uint32_t s_cap, uint32_t s,
                                  const uint32_t *seg_s, uint32_t n_seg, bool use64, uint64_t *work, uint32_t work_cap,
                                  uint64_t *scratch, uint64_t *out, SparseState *st, cudaStream_t stm)
 {
     if ((uint64_t)n_rows * s_cap > work_cap) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(&st->mix_has_max, 0, sizeof(uint32_t), stm);
+    static_assert(offsetof(SparseState, mix_unsettled) == offsetof(SparseState, mix_has_max) + 4, "cleared together");
+    cudaError_t e = cudaMemsetAsync(&st->mix_has_max, 0, 2 * sizeof(uint32_t), stm);
     if (e != cudaSuccess) return e;
     k_mixture_gather<<<grid_for(work_cap, 256, 148 * 4), 256, 0, stm>>>(rows, n_rows, s_cap, work, work_cap, st);
     if ((e = launch_sort_unique(work, work_cap, scratch, &st->n_mix, stm)) != cudaSuccess) return e;

@@ -44,7 +44,7 @@ struct SparseState {
     uint32_t xchg_max;      // multi-GPU: the largest pair count among the ranks' records
     uint32_t n_mix;         // merged mixture length (device-side merge)
     uint32_t mix_has_max;   // the value 2^64-1 is in the merged mixture (it doubles as the sort padding)
-    uint32_t pad;
+    uint32_t mix_unsettled; // some rank's mixture record said "not settled" (device-side selection fell through)
     unsigned long long set_size[8];   // S10 per source file, when the mixture was merged on the device
 };
 struct SparseView {
@@ -183,6 +183,7 @@ struct SparseReduceArgs {
     uint32_t *seg_start, *seg_fill;// n_refs each
     uint32_t *depths;              // pair_cap
     uint32_t pair_cap;
+    uint64_t ref_scale;            // floor(2^64 * n_refs / stored hashes): first guess of an entry's reference (0: none)
 };
 cudaError_t launch_sparse_reduce(const SparseReduceArgs &a, bool wta, int sm_count, cudaStream_t st);
 // counts[touched[i]] = 0 for the recorded ids; the second launch clears every count instead when the
@@ -209,6 +210,11 @@ cudaError_t launch_counts_absorb(const SparseView &sp, uint32_t *counts, uint64_
 cudaError_t launch_mixture_merge(const unsigned long long *rows, uint32_t n_rows, uint32_t s_cap, uint32_t s,
                                  const uint32_t *seg_s, uint32_t n_seg, bool use64, uint64_t *work, uint32_t work_cap,
                                  uint64_t *scratch, uint64_t *out, SparseState *st, cudaStream_t stm);
+// this rank's record for the mixture all-gather, written on the device from the device-side selection:
+// [length | s hashes, zero padded], or length = kMixUnsettled when the selection did not hold
+constexpr unsigned long long kMixUnsettled = ~0ull;
+cudaError_t launch_mix_record(const MixView &v, uint32_t s, uint32_t sel_pad, const uint64_t *cand, unsigned long long *record,
+                              int force_unsettled, cudaStream_t st);
 
 // ---- device-side packer (codes -> 2-bit words + invalid mask) -------------------
 cudaError_t launch_pack_codes(const uint8_t *codes, uint64_t n, uint64_t *seq, uint32_t *inv, uint64_t n_words_alloc,

@@ -148,8 +148,10 @@ class DistributedScreen:
     all-gathers those, and enqueues two library calls that consume the gathered buffers where they
     lie: hs_screen_mixture_merge_device (sort + unique + set size on the device) and
     hs_screen_counts_absorb (ONE launch over all ranks' pairs).  The host never looks at the gathered
-    data: between the last feed and the result copy the only synchronisations are the mixture
-    finaliser's own and the final one of hs_screen_finish.
+    data, and since round 2 it does not wait for the mixture finaliser either (hs_screen_flush_async: the
+    selection's verdict travels inside the mixture record): between the last feed and the results there
+    is ONE synchronisation, the final one of hs_screen_finish, so the host enqueues all of this while the
+    stream kernel is still running.
 
     `cap` follows the previous screen (next_cap).  If any rank's record is too small the absorb
     kernel adds nothing and says so in the stats that come back with the results; every rank sees the
@@ -175,6 +177,10 @@ class DistributedScreen:
         if self.exchange_mode == "sparse":      # forced: room for every entry, never falls back
             self.cap = int(max(4096, db.n_entries))
         self._rec = self._all = self._mix = self._mix_all = None
+        # one host synchronisation per screen (hs_screen_flush_async): the host enqueues the whole exchange and
+        # the reduction while the stream kernel still runs.  HYMET_SCREEN_SYNC_FREE=0 restores the round trip.
+        self.sync_free = os.environ.get("HYMET_SCREEN_SYNC_FREE", "1") != "0"
+        self.n_unsettled = 0
 
     def __getattr__(self, name):      # feed_*, reset, stats, set_option ...
         return getattr(self.scr, name)
@@ -208,7 +214,10 @@ class DistributedScreen:
                 self._all = torch.empty(self.world * n_rec, dtype=torch.int64, device=dev)
             self.scr.counts_compact_async(self._rec[1:].data_ptr(), cap, self._rec.data_ptr())
             work = dist.all_gather_into_tensor(self._all, self._rec, async_op=True)
-        self.scr.flush()                                  # host round trips of the mixture finaliser: the collective runs underneath
+        if sparse and self.sync_free:
+            self.scr.flush_async()                        # bottom-s selection enqueued; its verdict travels inside the record
+        else:
+            self.scr.flush()                              # host round trips of the mixture finaliser: the collective runs underneath
         self.scr.mixture_record(self._mix.data_ptr())
         dist.all_gather_into_tensor(self._mix_all, self._mix)             # world x (1 + s) words
         self.scr.mixture_merge_device(self._mix_all.data_ptr(), self.world)
@@ -229,6 +238,16 @@ class DistributedScreen:
     def _finish(self, wta, fin):
         self.exchange()
         res = fin(wta)
+        if self.world > 1 and res.stats.get("mix_unsettled"):
+            # some rank's device-side selection did not hold (every rank read that from the same gathered
+            # records): settle the mixtures the slow way and exchange them again; the counts are already merged
+            self.n_unsettled += 1
+            with torch.cuda.stream(self._tstream):
+                self.scr.flush()
+                self.scr.mixture_record(self._mix.data_ptr())
+                dist.all_gather_into_tensor(self._mix_all, self._mix)
+                self.scr.mixture_merge_device(self._mix_all.data_ptr(), self.world)
+            res = fin(wta)
         if self.world > 1 and self.last_exchange == "sparse":
             most = int(res.stats["exchange_max_pairs"])
             if self.exchange_mode != "sparse":

@@ -257,6 +257,10 @@ class Screen:
     def flush(self):
         check(_abi.load().hs_screen_flush(self._h))
 
+    def flush_async(self):
+        """Enqueue the bottom-s selection without waiting; the next finish completes the flush."""
+        check(_abi.load().hs_screen_flush_async(self._h))
+
     def counts_devptr(self):
         p, n = C.c_void_p(), C.c_uint64()
         check(_abi.load().hs_screen_counts_devptr(self._h, C.byref(p), C.byref(n)))

@@ -82,6 +82,8 @@ typedef struct {
     uint32_t exchange_overflow; /* multi-GPU: a rank's pair record was too small, nothing was added
                                    (hs_screen_counts_absorb): redo the exchange densely */
     uint32_t exchange_max_pairs; /* multi-GPU: largest pair count among the ranks' records (sizes the next one) */
+    uint32_t mix_unsettled;      /* multi-GPU after hs_screen_flush_async: some rank's bottom-s selection did not hold; the
+                                    counts are merged, the mixture is not: hs_screen_flush, exchange the mixture again, finish again */
 } hs_stats_t;
 
 /* ---- library ------------------------------------------------------------ */
@@ -184,6 +186,12 @@ int hs_pack_text_device(const char *text, size_t n, uint64_t *seq2, uint32_t *in
 
 /* rows a8-a10 complete: wait for the stream, settle the local mixture bottom-s. */
 int hs_screen_flush(hs_screen *s);
+/* The same without waiting: the device-side selection of the bottom-s is enqueued, and the next
+ * hs_screen_finish / _finish_hits completes the flush with its own (single) synchronisation.  In between,
+ * hs_screen_mixture_record, hs_screen_mixture_merge_device, hs_screen_counts_compact_async and
+ * hs_screen_counts_absorb may be enqueued: a whole multi-GPU screen then synchronises with the host
+ * once.  See hs_stats_t.mix_unsettled for the (rare) fallback. */
+int hs_screen_flush_async(hs_screen *s);
 
 /* Multi-GPU seam: after flush, counts[] (uint32, one per stored hash
  * entry id; device pointer) may be summed across ranks in place, and every rank's local

@@ -355,6 +355,35 @@ def test_reset_and_chunked_feeds_agree(c1_case):
     assert c.median.tolist() == (2 * a.median).tolist()
 
 
+@pytest.mark.parametrize("wta", [False, True])
+def test_flush_async_completes_in_finish(c1_case, wta, monkeypatch):
+    """hs_screen_flush_async: the bottom-s selection is enqueued and the next finish completes the flush
+    with its single synchronisation -- same mixture, set size and rows as the waiting flush; and when the
+    selection is made to report "not settled" a single process falls back to the iterative finaliser."""
+    offsets, hashes, lengths, fasta = c1_case
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    ref = hs.Screen(db)
+    ref.feed_text(fasta, 2)
+    want = ref.finish(wta)
+    want_mix = ref.mixture().tolist()
+    ref.close()
+    for forced in (False, True):
+        if forced:
+            monkeypatch.setenv("HYMET_SCREEN_FORCE_UNSETTLED", "1")
+        scr = hs.Screen(db)
+        monkeypatch.delenv("HYMET_SCREEN_FORCE_UNSETTLED", raising=False)
+        for rep in range(2):          # the same handle again after a reset
+            scr.feed_text(fasta, 2)
+            scr.flush_async()
+            got = scr.finish(wta)
+            assert got.shared.tolist() == want.shared.tolist() and got.median.tolist() == want.median.tolist()
+            assert got.set_size == want.set_size and scr.mixture().tolist() == want_mix
+            assert got.identity.tolist() == want.identity.tolist() and got.pvalue.tolist() == want.pvalue.tolist()
+            assert got.stats["n_valid_kmers"] == want.stats["n_valid_kmers"] and got.stats["n_bases"] == want.stats["n_bases"]
+            scr.reset()
+        scr.close()
+
+
 # ---------------------------------------------------------------- drop-in -------
 def write_db(tmp_path, genomes, k, s, **kw):
     offsets, hashes, lengths = build_db(genomes, k, s)

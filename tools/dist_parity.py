@@ -36,6 +36,13 @@ def main():
     # the same handle three times: the record is sized from the previous screen (first: too small -> dense
     # fallback, then sparse)
     runs += [(False, "auto", auto), (True, "auto", auto), (False, "auto", auto)]
+    # the sync-free flush's fallback: ONE rank's device-side selection is made to report "not settled";
+    # every rank must notice (the verdict travels in the gathered records) and redo the mixture exchange
+    if rank == world - 1:
+        os.environ["HYMET_SCREEN_FORCE_UNSETTLED"] = "1"
+    forced = hd.DistributedScreen(db, local, exchange="sparse", stream_ptr=stream.cuda_stream)
+    os.environ.pop("HYMET_SCREEN_FORCE_UNSETTLED", None)
+    runs += [(True, "sparse+unsettled", forced), (False, "sparse+settled", forced)]
     for wta, mode, handle in runs:
         scr = handle or hd.DistributedScreen(db, local, exchange=mode, stream_ptr=stream.cuda_stream)
         if handle:
@@ -52,10 +59,16 @@ def main():
             print("world=%d wta=%d exchange=%s(%s) shared_total=%d parity=%s" % (world, wta, mode, scr.last_exchange,
                                                                                   int(res.shared.sum()), same), flush=True)
             ok = ok and same
+        if mode == "sparse+unsettled" and scr.n_unsettled != 1:
+            print("rank %d: the forced unsettled selection was not noticed (n_unsettled=%d)" % (rank, scr.n_unsettled), flush=True)
+            ok = False
+        if mode == "sparse+settled" and scr.n_unsettled != 1:
+            print("rank %d: a settled screen fell back (n_unsettled=%d)" % (rank, scr.n_unsettled), flush=True)
+            ok = False
         if not handle:
             scr.scr.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.broadcast(flag, 0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if int(flag[0]) else 1)

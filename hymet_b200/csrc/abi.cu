@@ -1178,7 +1178,12 @@ int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
     size_t first = 0;
     while (first < n && (text[first] == '\n' || text[first] == '\r')) first++;
     const bool fasta = first < n && text[first] != '@';
-    const bool device_ok = fasta && s->ingest_mode != 0 && is_pinned_host(text) && is_pinned_host(text + n - 1);
+    // (a single record of a GiB or more cannot go through the device parser's 32-bit offsets: such a feed is
+    // packed on the host as a whole)
+    size_t longest = 0;
+    for (const auto &sp : spans) longest = std::max(longest, sp.second - sp.first);
+    const bool device_ok = fasta && s->ingest_mode != 0 && longest < ((size_t)1 << 28) && is_pinned_host(text) &&
+                           is_pinned_host(text + n - 1);
     const bool use_device = device_ok;
     if (s->ingest_mode == 1 && device_ok) threads = 0;          // device parser only
     // a handful of packer threads next to the DMA engine only adds host-memory traffic (8 GPUs x 4
@@ -1531,8 +1536,8 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
     }
     // gzip / stdin / FASTQ: decompress on this thread in chunks of whole FASTA records and hand every
     // chunk to the host packer threads, so memory stays bounded and the GPU works on chunk i while
-    // chunk i+1 is being inflated.  FASTQ cannot be cut safely ('@' also starts quality lines): it is
-    // read to the end first, as before.
+    // chunk i+1 is being inflated.  FASTQ is cut where the packer's own walk sees a header (record_starts:
+    // '@' also starts quality lines), so read sets stay bounded in memory and use every packer thread too.
     gzFile f = strcmp(path, "-") == 0 ? gzdopen(0, "rb") : gzopen(path, "rb");
     if (!f) return fail(HS_EIO, std::string("could not open ") + path);
     gzbuffer(f, 1 << 20);
@@ -1542,7 +1547,7 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
     bool fastq = false, first = true, eof = false;
     int rc = HS_OK;
     while (!eof && rc == HS_OK) {
-        while (len < target || fastq) {   // fill up to one chunk (everything, for FASTQ)
+        while (len < target) {   // fill up to one chunk
             if (buf.size() - len < ((size_t)1 << 22)) buf.resize(std::max(buf.size() * 2, len + ((size_t)1 << 23)));
             const int r = gzread(f, buf.data() + len, 1u << 22);
             if (r < 0) { gzclose(f); return fail(HS_EIO, std::string("read error on ") + path); }
@@ -1557,8 +1562,13 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
         size_t cut = len;
         if (!eof) {   // last record start in the buffer: everything before it is whole records
             cut = 0;
-            for (size_t i = len - 1; i > 0; i--)
-                if (buf[i] == '>' && buf[i - 1] == '\n') { cut = i; break; }
+            if (fastq) {   // '@' also starts quality lines: only the packer's own walk knows a header from one
+                const std::vector<size_t> starts = record_starts(buf.data(), len, 1);
+                if (starts.size() > 1) cut = starts.back();
+            } else {
+                for (size_t i = len - 1; i > 0; i--)
+                    if (buf[i] == '>' && buf[i - 1] == '\n') { cut = i; break; }
+            }
             if (!cut) { target = len + chunk; continue; }   // one record larger than the chunk: keep reading
         }
         rc = feed_text_impl(s, buf.data(), cut, host_threads);

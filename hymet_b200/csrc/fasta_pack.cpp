@@ -371,13 +371,72 @@ uint64_t pack_text_span(const char *t, size_t n, uint64_t *seq, uint32_t *inv, P
     return wr.w;
 }
 
+// Offsets of the header lines AS pack_text_span SEES THEM, thinned to at least min_gap bytes apart (the first
+// one is always there).  Same control flow as the packer without the packing: a line that starts with '>' or
+// '@' outside a FASTQ quality block is a header and resets the packer completely, so the text can be cut in
+// front of any of them -- which is what makes FASTQ splittable although '@' also starts quality lines.
+std::vector<size_t> record_starts(const char *t, size_t n, size_t min_gap)
+{
+    std::vector<size_t> out;
+    enum { SEEK_HDR, IN_SEQ } state = SEEK_HDR;
+    bool fastq = false;
+    uint64_t rec_len = 0;
+    size_t i = 0;
+    while (i < n) {
+        const char *nl = (const char *)memchr(t + i, '\n', n - i);
+        const size_t j = nl ? (size_t)(nl - t) : n;
+        const char c0 = t[i];
+        if (c0 == '>' || c0 == '@') {
+            if (out.empty() || i - out.back() >= min_gap) out.push_back(i);
+            state = IN_SEQ;
+            fastq = (c0 == '@');
+            rec_len = 0;
+            i = j + 1;
+            continue;
+        }
+        if (state == SEEK_HDR) { i = j + 1; continue; }
+        if (c0 == '+') {
+            i = j + 1;
+            if (fastq) {
+                uint64_t q = 0;
+                while (i < n && q < rec_len) {
+                    if (t[i] != '\n' && t[i] != '\r') q++;
+                    i++;
+                }
+                nl = i < n ? (const char *)memchr(t + i, '\n', n - i) : nullptr;
+                i = nl ? (size_t)(nl - t) + 1 : n;
+            }
+            state = SEEK_HDR;
+            continue;
+        }
+        size_t L = j - i;
+        if (L && t[i + L - 1] == '\r') L--;
+        rec_len += L;
+        i = j + 1;
+    }
+    return out;
+}
+
 std::vector<std::pair<size_t, size_t>> split_records(const char *t, size_t n, int parts, size_t min_span)
 {
     std::vector<std::pair<size_t, size_t>> out;
     size_t first = 0;
     while (first < n && (t[first] == '\n' || t[first] == '\r')) first++;
     if (parts < 1) parts = 1;
-    if (first < n && t[first] != '>') parts = 1;  // FASTQ ('@' also occurs in quality lines): do not split
+    if (first < n && t[first] != '>' && parts > 1) {
+        // FASTQ ('@' also occurs in quality lines): cut where the packer's own walk sees a header
+        size_t span = n / (size_t)parts + 1;
+        if (span < min_span) span = min_span;
+        const std::vector<size_t> starts = record_starts(t, n, span);
+        size_t beg = 0;
+        for (size_t q = 1; q < starts.size(); q++) {
+            if (starts[q] <= beg) continue;
+            out.emplace_back(beg, starts[q]);
+            beg = starts[q];
+        }
+        if (beg < n || out.empty()) out.emplace_back(beg, n);
+        return out;
+    }
     size_t span = n / (size_t)parts + 1;
     if (span < min_span) span = min_span;
     size_t beg = 0;

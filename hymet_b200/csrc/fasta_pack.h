@@ -34,8 +34,12 @@ int pack_level();
 // AVX-512 path: write the packed words with non-temporal stores (output that only a DMA engine reads next)
 void set_pack_streaming(bool on);
 
-// Split [text, text+n) into <= parts spans that each begin at a line starting with
-// '>' (FASTA).  FASTQ input ('@' first) is returned as a single span.
+// Offsets of the header lines as pack_text_span sees them ('>' / '@' at a line start outside a FASTQ
+// quality block), thinned to >= min_gap bytes apart.  The text may be cut in front of any of them.
+std::vector<size_t> record_starts(const char *text, size_t n, size_t min_gap);
+
+// Split [text, text+n) into about `parts` spans that each begin at a record header: a line starting with
+// '>' (FASTA), or a header found by record_starts (FASTQ, where '@' may also start a quality line).
 std::vector<std::pair<size_t, size_t>> split_records(const char *text, size_t n, int parts, size_t min_span);
 
 // Whole file (plain or gzip, "-" = stdin) into memory.

@@ -419,6 +419,12 @@ __global__ void __launch_bounds__(kCtaThreads, MODE == 3 ? 3 : HS_MIN_CTAS) k_st
     // tile of look-ahead; warp 0 also does its share of the hashing, so it was usually BEHIND the others,
     // which then spun on `full` for a tile nobody had asked for yet -- 7 % of all issued instructions
     // were that spin (ncu r02: 35 try_wait per wait).
+    // (Measured alternative: a ring PER WARP -- every warp streams its own 32-word slices and refills them itself,
+    // nothing shared, no warp ever waits for another.  With the shared ring the leading warps sleep 15 % of their
+    // time at the ring's end (32 sleep-and-retry trips per tile wait); with private rings nobody waits -- and the
+    // kernel is no faster: 4.43 vs 4.40 ms per Gbp, 6.22 vs 6.18 on the Bloom tier, 5.24 vs 5.21 at k = 31.  The
+    // other three CTAs of the SM fill the sleepers' issue slots; the limit is the ALU pipe, not the number of
+    // warps awake.)
     constexpr uint32_t kStages = 4, kPrefetch = 2;
     __shared__ TileBuf buf[kStages];
     __shared__ __align__(8) uint64_t full[kStages], empty[kStages];

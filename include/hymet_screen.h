@@ -149,7 +149,7 @@ int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
  * where the page cache holds them / chosen by host capability (default: mapped when the packer has
  * its AVX-512 path and at least four threads); "text_chunk_bytes" =
  * bytes of gzip / stdin FASTA inflated per hand-over to the packer threads (default 256 MiB;
- * cut at record starts, FASTQ is read whole); "ingest_slots" (1-4), "ingest_batch" (1-8) = depth
+ * cut at record starts -- FASTQ too, where the packer's own walk tells a header from a quality line that starts with '@'); "ingest_slots" (1-4), "ingest_batch" (1-8) = depth
  * and granularity of the device parser's raw-text queue. */
 int hs_screen_set_option(hs_screen *s, const char *key, int64_t value);
 

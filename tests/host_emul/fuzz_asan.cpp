@@ -83,6 +83,21 @@ int main(int argc, char **argv)
             size_t pos = 0;
             for (auto &p : sp) { if (p.first != pos || p.second < p.first) { printf("bad split\n"); return 2; } pos = p.second; }
             if (n && pos != n) { printf("split does not cover the text\n"); return 3; }
+            // Cutting in front of a header the packer sees changes nothing: same records, bases, positions.  Holds
+            // for FASTQ-first text (cut by the packer's own walk) and for FASTA without '@' records; a FASTA-first
+            // file with FASTQ records inside is cut at "\n>" without looking at quality blocks (not a format).
+            size_t first = 0;
+            while (first < n && (txt[first] == '\n' || txt[first] == '\r')) first++;
+            if (first < n && (txt[first] == '@' || !memchr(txt, '@', n))) {
+                hs::PackStats parts_st;
+                for (auto &p : sp) hs::pack_text_span(txt + p.first, p.second - p.first, seq, inv, &parts_st);
+                if (parts_st.n_records != st.n_records || parts_st.n_seq_bases != st.n_seq_bases || parts_st.n_positions != st.n_positions) {
+                    printf("packing the %zu spans of split_records differs from packing the text (round %d, mode %d, %zu bytes): "
+                           "records %llu/%llu bases %llu/%llu\n", sp.size(), t, mode, n, (unsigned long long)parts_st.n_records,
+                           (unsigned long long)st.n_records, (unsigned long long)parts_st.n_seq_bases, (unsigned long long)st.n_seq_bases);
+                    return 5;
+                }
+            }
             free(txt); free(seq); free(inv);
         }
         printf("ok %llu levels %d\n", total, levels_seen);

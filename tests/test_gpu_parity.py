@@ -853,6 +853,39 @@ def test_gzip_input_is_inflated_in_chunks_of_whole_records(tmp_path):
         scr.close()
 
 
+@pytest.mark.parametrize("multiline", [False, True])
+def test_fastq_is_cut_at_whole_records_and_packed_by_all_threads(tmp_path, multiline):
+    """A read set (FASTQ: plain, gzip) is inflated in bounded chunks and split across the packer threads at
+    record headers found by the packer's own walk -- quality lines that start with '@', '>' or '+' included:
+    same result as the equivalent FASTA, for every chunk size."""
+    import gzip
+    from tests.test_host_emul import make_fastq
+    rng = np.random.default_rng(53)
+    genomes = [synth.random_genome(rng, 60_000) for _ in range(6)]
+    offsets, hashes, lengths = build_db(genomes, 21, 1000)
+    db = hs.Database.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    odb = orc.OracleDB.from_arrays(21, 1000, 42, offsets, hashes, lengths)
+    reads = synth.cut_contigs(rng, genomes[:4], 500_000, 0.01, median=300.0)
+    seqs = [synth.ASCII[c].tobytes().decode() for c in reads]
+    fq = make_fastq(seqs, multiline=multiline).encode()
+    fa = "".join(">r%d\n%s\n" % (i, q) for i, q in enumerate(seqs)).encode()
+    want = odb.screen_text(fa, threads=2)
+    plain, gz = str(tmp_path / "reads.fq"), str(tmp_path / "reads.fq.gz")
+    open(plain, "wb").write(fq)
+    with gzip.open(gz, "wb") as fh:
+        fh.write(fq)
+    for path, chunk, threads in ((plain, 1 << 28, 4), (gz, 3000, 3), (gz, 70_000, 5)):
+        scr = hs.Screen(db)
+        scr.set_option("text_chunk_bytes", chunk)
+        scr.set_option("chunk_bases", 20_000)       # dozens of spans per chunk
+        scr.feed_fasta(path, threads)
+        res = scr.finish(False)
+        assert res.shared.tolist() == want.shared.tolist() and res.median.tolist() == want.median.tolist(), (path, chunk)
+        assert res.set_size == want.set_size and res.stats["n_valid_kmers"] == want.n_kmers
+        assert res.stats["n_records"] == len(seqs) and res.stats["n_bases"] == sum(len(q) for q in seqs)
+        scr.close()
+
+
 @pytest.mark.parametrize("k,s", [(21, 1000), (31, 5000), (16, 400)])
 def test_gpu_sketch_of_real_sequence(golden_dir, k, s):
     """`mash sketch` on the GPU against the oracle on real contigs (60 records of the Zymo fixture:

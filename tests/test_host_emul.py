@@ -150,6 +150,27 @@ def test_split_records_preserves_kmers(emul):
     assert np.array_equal(whole, parts)
 
 
+@pytest.mark.parametrize("multiline,crlf", [(False, False), (True, False), (True, True)])
+def test_split_fastq_records_preserves_kmers(emul, multiline, crlf):
+    """FASTQ is splittable although '@' also starts quality lines: split_records cuts where the packer's own
+    walk (record_starts) sees a header.  Packing the spans one by one gives the k-mers of the whole text."""
+    rng = random.Random(5)
+    recs = ["".join(rng.choice("ACGT") for _ in range(rng.choice([0, 1, 30, 75, 150, 400]))) for _ in range(300)]
+    fq = make_fastq(recs, multiline, crlf, True).encode()
+    bounds = (C.c_uint64 * 256)()
+    for parts, min_span in ((7, 1), (40, 1), (3, 5000)):
+        n = emul.emul_split(fq, len(fq), parts, min_span, bounds, 128)
+        assert 2 <= n <= 128, n
+        spans = [(bounds[2 * i], bounds[2 * i + 1]) for i in range(n)]
+        assert spans[0][0] == 0 and spans[-1][1] == len(fq)
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(n - 1))
+        assert all(fq[b:b + 1] == b"@" for b, _ in spans)
+        whole, st = emul_hashes(emul, fq, 21)
+        got = [emul_hashes(emul, fq[b:e], 21) for b, e in spans]
+        assert np.array_equal(whole, np.concatenate([g[0] for g in got]))
+        assert st[0] == sum(g[1][0] for g in got) == len(recs)
+
+
 @pytest.mark.parametrize("k", list(range(1, 33)))
 def test_premultiplied_table_hash_equals_murmur(emul, k):
     """The streaming kernel takes the first multiply of every 64-bit murmur lane from a table of

@@ -439,7 +439,12 @@ def run_b200(args):
                     "frac": issue_achieved / issue_peak,
                     "definition": "warp instructions per k-mer (static: %s) x k-mers/s measured here, over SMs x 4 schedulers x "
                                   "the SM clock sampled during this run" % prof.get("source", "profiles/"),
-                    "warp_inst_per_kmer": inst_per_kmer, "sm_count": n_sm, "sm_clock_mhz": sm_clock_hz / 1e6}
+                    "warp_inst_per_kmer": inst_per_kmer, "sm_count": n_sm, "sm_clock_mhz": sm_clock_hz / 1e6,
+                    "ncu_static": {"issue_active_frac": (prof.get("issue_active_pct") or 0) / 100.0,
+                                   "alu_pipe_frac": (prof.get("alu_pipe_pct") or 0) / 100.0,
+                                   "fma_pipe_frac": (prof.get("fma_pipe_pct") or 0) / 100.0,
+                                   "note": "same kernel under ncu --set full: the half-rate ALU pipe (shifts, logic, carry adds) "
+                                           "is the busiest unit; issue slots and ALU pipe bound the kernel at the same level"}}
     else:
         roofline = {"kernel": "k_stream<%d>" % args.k, "bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s",
                     "frac": hbm_achieved / peak,

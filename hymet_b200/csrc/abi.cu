@@ -238,7 +238,7 @@ struct MixEngine {
         CU(cudaHostAlloc((void **)&h_state, sizeof(MixState), cudaHostAllocDefault));
         CU(cudaMalloc((void **)&d_cand, (size_t)cand_cap * 8));
         CU(cudaMalloc((void **)&d_scratch, (size_t)cand_cap * 8));
-        CU(cudaMalloc((void **)&d_hist, 2048 * sizeof(uint32_t)));
+        CU(cudaMalloc((void **)&d_hist, (2 * 2048 + 8) * sizeof(uint32_t)));   // bin counts | bin starts | last bin
         sel_pad = 2048;
         while (sel_pad < s + 1024) sel_pad <<= 1;
         if (sel_pad > cand_cap) sel_pad = cand_cap;

@@ -1123,7 +1123,10 @@ __global__ void __launch_bounds__(256) k_mix_hist(const MixView v, int use64, ui
         if (sh[i]) atomicAdd(hist + i, sh[i]);
 }
 
-__global__ void __launch_bounds__(1024) k_mix_pick(const MixView v, int use64, uint32_t s, const uint32_t *hist)
+// hist[0..2047] = bin counts (in), fill counters (out: zeroed); hist[2048 + b] = where bin b starts in the
+// output (exclusive prefix sums), hist[2048 + 2048] = index of the last bin collected
+constexpr uint32_t kSelStart = kSelBins, kSelFirst = 2 * kSelBins;
+__global__ void __launch_bounds__(1024) k_mix_pick(const MixView v, int use64, uint32_t s, uint32_t *hist, uint32_t out_cap)
 {
     __shared__ uint32_t tot[32];
     __shared__ uint32_t first;
@@ -1144,52 +1147,94 @@ __global__ void __launch_bounds__(1024) k_mix_pick(const MixView v, int use64, u
     const uint32_t cum1 = before + inc, cum0 = cum1 - b;        // through bins 2t+1 and 2t
     if (cum0 >= s) atomicMin(&first, 2 * threadIdx.x);
     else if (cum1 >= s) atomicMin(&first, 2 * threadIdx.x + 1);
+    hist[kSelStart + 2 * threadIdx.x] = cum0 - a;               // the collect pass is a counting sort by bin
+    hist[kSelStart + 2 * threadIdx.x + 1] = cum0;
+    hist[2 * threadIdx.x] = 0; hist[2 * threadIdx.x + 1] = 0;   // ... with these as its fill counters
     __syncthreads();
+    const uint32_t f = first < kSelBins ? first : kSelBins - 1; // fewer than s values in all: take every bin
+    if (threadIdx.x == f / 2) {
+        MixState *st = v.st;
+        const uint32_t n = (f & 1u) ? cum1 : cum0;
+        st->n_out = n;
+        st->n_unique = n;                                       // the live set holds every value once
+        st->sel_too_many = n > out_cap ? 1u : 0u;
+        hist[kSelFirst] = f;
+    }
     if (threadIdx.x == 0) {
         MixState *st = v.st;
         const unsigned long long width = sel_width(st, use64 != 0);
-        unsigned long long thr = st->tau;                        // fewer than s values in all: take everything
+        unsigned long long thr = st->tau;
         if (first + 1 < kSelBins) {
             const unsigned long long t = (unsigned long long)(first + 1) * width - 1ull;
             if (t < thr) thr = t;
         }
         st->sel_thr = thr;
-        st->n_out = 0;
-        st->sel_too_many = 0;
     }
 }
 
-__global__ void __launch_bounds__(256) k_mix_collect_sel(const MixView v, uint64_t *out, uint32_t out_cap)
+// counting sort by bin: the bins are value ranges in ascending order, so after this pass the output is sorted
+// up to the order inside each bin
+__global__ void __launch_bounds__(256) k_mix_collect_sel(const MixView v, int use64, uint32_t *hist, uint64_t *out, uint32_t out_cap)
 {
-    const unsigned long long thr = v.st->sel_thr;
+    const unsigned long long tau = v.st->tau, width = sel_width(v.st, use64 != 0);
+    const uint32_t last = hist[kSelFirst];
     const uint64_t *set = v.sets[v.st->cur & 1u];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= v.mask; i += gridDim.x * blockDim.x) {
         const uint64_t x = set[i];
-        if (x != kEmptyKey && x <= thr) {
-            const uint32_t p = atomicAdd(&v.st->n_out, 1u);
-            if (p < out_cap) out[p] = x; else v.st->sel_too_many = 1u;
-        }
+        if (x == kEmptyKey || x > tau) continue;
+        const unsigned long long bb = x / width;
+        const uint32_t b = bb < kSelBins ? (uint32_t)bb : kSelBins - 1;
+        if (b > last) continue;
+        const uint32_t p = hist[kSelStart + b] + atomicAdd(&hist[b], 1u);
+        if (p < out_cap) out[p] = x;
     }
+}
+
+// ... which one warp per bin then establishes (bitonic network in shared memory, <= 512 values per bin: a bin
+// holds ~130 of a quarter-full set; a crowded one sends the host to the iterative path).  The single-CTA sort
+// of all s + slack candidates this replaces was 0.25 ms at s = 10 000 -- the largest kernel after the stream.
+constexpr uint32_t kBinSortMax = 512;
+__global__ void __launch_bounds__(256) k_mix_binsort(const MixView v, const uint32_t *hist, uint64_t *out, uint32_t out_cap)
+{
+    __shared__ uint64_t sm[8][kBinSortMax];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint32_t bin = blockIdx.x * 8u + w;
+    if (bin > hist[kSelFirst] || v.st->sel_too_many) return;
+    const uint32_t beg = hist[kSelStart + bin];
+    const uint32_t end = bin + 1 < kSelBins ? hist[kSelStart + bin + 1] : v.st->n_out;
+    const uint32_t L = end - beg;
+    if (L < 2 || end > out_cap) return;
+    if (L > kBinSortMax) { if (lane == 0) v.st->sel_too_many = 1u; return; }
+    uint32_t n_pad = 32;
+    while (n_pad < L) n_pad <<= 1;
+    uint64_t *a = sm[w];
+    for (uint32_t i = lane; i < n_pad; i += 32) a[i] = i < L ? out[beg + i] : kEmptyKey;
+    __syncwarp();
+    for (uint32_t kk = 2; kk <= n_pad; kk <<= 1)
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < n_pad; i += 32) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const uint64_t x = a[i], y = a[p];
+                    if ((x > y) == ((i & kk) == 0)) { a[i] = y; a[p] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    for (uint32_t i = lane; i < L; i += 32) out[beg + i] = a[i];
 }
 
 cudaError_t launch_mix_select(const MixView &v, uint32_t s, bool use64, uint32_t *hist, uint64_t *out, uint32_t n_pad,
                               uint64_t *scratch, cudaStream_t st)
 {
+    (void)scratch;
     cudaError_t e = cudaMemsetAsync(hist, 0, kSelBins * sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     const uint32_t cap = v.mask + 1u;
     k_mix_hist<<<grid_for(cap, 256, 148 * 2), 256, 0, st>>>(v, use64 ? 1 : 0, hist);
-    k_mix_pick<<<1, 1024, 0, st>>>(v, use64 ? 1 : 0, s, hist);
-    k_mix_collect_sel<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(v, out, n_pad);
-    static bool attr = false;
-    if (!attr) {
-        e = cudaFuncSetAttribute(k_sort_unique, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortSmemMax * sizeof(uint64_t)));
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
-    const bool in_smem = n_pad <= kSortSmemMax;
-    k_sort_unique<<<1, 1024, in_smem ? n_pad * sizeof(uint64_t) : 0, st>>>(out, 0, &v.st->n_out, n_pad, in_smem ? nullptr : scratch,
-                                                                          &v.st->n_unique);
+    k_mix_pick<<<1, 1024, 0, st>>>(v, use64 ? 1 : 0, s, hist, n_pad);
+    k_mix_collect_sel<<<grid_for(cap, 256, 148 * 8), 256, 0, st>>>(v, use64 ? 1 : 0, hist, out, n_pad);
+    k_mix_binsort<<<kSelBins / 8, 256, 0, st>>>(v, hist, out, n_pad);
     return cudaGetLastError();
 }
 
@@ -1920,32 +1965,85 @@ __device__ __forceinline__ uint32_t chain_winner(const SparseReduceArgs &a, uint
     return best_i;
 }
 
+// Per-CTA aggregation of the walk's updates.  The references with hits are few (hundreds) and often adjacent
+// (strains of one species sit next to each other in a RefSeq-ordered sketch file), so millions of
+// atomicAdd(shared + ref) land on a handful of cache lines: at s = 10 000 (2.76 M present hashes, 500
+// references with hits, all in 16 lines) the two walks took 0.41 ms each.  Each CTA first counts per reference
+// in a small shared-memory table and then touches global memory once per (CTA, reference).
+constexpr uint32_t kAggSlots = 2048, kAggEmpty = 0xFFFFFFFFu;
+struct CtaAgg { uint32_t key[kAggSlots], val[kAggSlots], cur[kAggSlots]; };   // 24 KB
+
+__device__ __forceinline__ int agg_insert(CtaAgg &g, uint32_t i)   // slot of reference i, claimed if new; -1: no room nearby
+{
+    uint32_t h = (i * 2654435761u) >> 21;
+    for (int tries = 0; tries < 32; tries++) {
+        const uint32_t old = atomicCAS(&g.key[h], kAggEmpty, i);
+        if (old == kAggEmpty || old == i) return (int)h;
+        h = (h + 1) & (kAggSlots - 1);
+    }
+    return -1;
+}
+__device__ __forceinline__ int agg_find(const CtaAgg &g, uint32_t i)   // after all inserts: same probe path, no claims
+{
+    uint32_t h = (i * 2654435761u) >> 21;
+    for (int tries = 0; tries < 32; tries++) {
+        const uint32_t k = g.key[h];
+        if (k == i) return (int)h;
+        if (k == kAggEmpty) return -1;
+        h = (h + 1) & (kAggSlots - 1);
+    }
+    return -1;
+}
+
 template <bool WTA, bool SCATTER>
 __global__ void __launch_bounds__(256) k_sparse_walk(const SparseReduceArgs a)
 {
+    __shared__ CtaAgg g;
     uint32_t n;
-    if (!sparse_ok(a.sp, n)) return;
-    auto visit = [&](uint32_t i, uint32_t c) {
-        if (SCATTER) {
-            const uint32_t pos = a.seg_start[i] + atomicAdd(a.seg_fill + i, 1u);
-            if (pos < a.pair_cap) a.depths[pos] = c;
-        } else {
-            const uint32_t old = atomicAdd(a.shared + i, 1u);
-            if (!WTA && old == 0u) a.hit[atomicAdd(&a.sp.st->n_hit, 1u)] = i;   // at most n_refs appends
-        }
-    };
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        const uint32_t t = a.sp.touched[p];
-        const uint32_t c = __ldcg(a.counts + t);
-        if (!c) continue;
-        if (!WTA) {
-            for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) visit(ref_of_entry(a.offsets, a.n_refs, e, a.ref_scale), c);
-        } else {
-            for (uint32_t j = 0; j < a.n_seg; j++) {
-                const uint32_t w = chain_winner(a, t, j);
-                if (w != kNoEntry) visit(w, c);
+    if (!sparse_ok(a.sp, n)) return;                       // (the same answer in every thread of every CTA)
+    for (uint32_t q = threadIdx.x; q < kAggSlots; q += blockDim.x) { g.key[q] = kAggEmpty; g.val[q] = 0; g.cur[q] = 0; }
+    __syncthreads();
+    // the (reference, count) pairs of this thread's present hashes, in a fixed order: f(reference, count) for each
+    auto walk = [&](auto &&f) {
+        for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+            const uint32_t t = a.sp.touched[p];
+            const uint32_t c = __ldcg(a.counts + t);
+            if (!c) continue;
+            if (!WTA) {
+                for (uint32_t e = t; e != kNoEntry; e = __ldg(a.next + e)) f(ref_of_entry(a.offsets, a.n_refs, e, a.ref_scale), c);
+            } else {
+                for (uint32_t j = 0; j < a.n_seg; j++) {
+                    const uint32_t w = chain_winner(a, t, j);
+                    if (w != kNoEntry) f(w, c);
+                }
             }
         }
+    };
+    auto count_global = [&](uint32_t i, uint32_t add) {
+        const uint32_t old = atomicAdd(a.shared + i, add);
+        if (!WTA && old == 0u) a.hit[atomicAdd(&a.sp.st->n_hit, 1u)] = i;   // at most n_refs appends
+    };
+    // pass A: per-CTA counts (a reference that finds no slot nearby goes straight to global memory)
+    walk([&](uint32_t i, uint32_t) {
+        const int sl = agg_insert(g, i);
+        if (sl >= 0) atomicAdd(&g.val[sl], 1u);
+        else if (!SCATTER) count_global(i, 1u);
+    });
+    __syncthreads();
+    if constexpr (!SCATTER) {
+        for (uint32_t q = threadIdx.x; q < kAggSlots; q += blockDim.x)
+            if (g.key[q] != kAggEmpty) count_global(g.key[q], g.val[q]);
+    } else {
+        // scatter: reserve this CTA's stretch of every reference's segment, then hand the slots out locally
+        for (uint32_t q = threadIdx.x; q < kAggSlots; q += blockDim.x)
+            if (g.key[q] != kAggEmpty) g.val[q] = atomicAdd(a.seg_fill + g.key[q], g.val[q]);
+        __syncthreads();
+        walk([&](uint32_t i, uint32_t c) {
+            const int sl = agg_find(g, i);
+            const uint32_t off = sl >= 0 ? g.val[sl] + atomicAdd(&g.cur[sl], 1u) : atomicAdd(a.seg_fill + i, 1u);
+            const uint32_t pos = a.seg_start[i] + off;
+            if (pos < a.pair_cap) a.depths[pos] = c;
+        });
     }
 }
 

@@ -132,7 +132,7 @@ cudaError_t launch_mix_maintain(const MixView &v, cudaStream_t st);
 // tau (2048 bins) -> smallest threshold with >= s values under it -> collect -> sort + unique.
 // out[] (capacity n_pad, a power of two >= s + slack) ends up ascending and distinct, st->n_unique
 // long; st->sel_too_many is raised when more than n_pad values lay under the threshold.
-cudaError_t launch_mix_select(const MixView &v, uint32_t s, bool use64, uint32_t *hist /*2048*/, uint64_t *out,
+cudaError_t launch_mix_select(const MixView &v, uint32_t s, bool use64, uint32_t *hist /*2 * 2048 + 8*/, uint64_t *out,
                               uint32_t n_pad, uint64_t *scratch, cudaStream_t st);
 // sort ascending + unique in place (n <= cap_pow2 handled by padding); *n_unique out
 cudaError_t launch_sort_unique(uint64_t *data, uint32_t n, uint64_t *scratch, uint32_t *n_unique, cudaStream_t st);

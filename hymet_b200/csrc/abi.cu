@@ -1169,7 +1169,7 @@ bool is_pinned_host(const void *p)
 
 int feed_text_impl(hs_screen *s, const char *text, size_t n, int threads)
 {
-    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (s->flushed || s->flush_pending) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     if (threads < 0) threads = 0;
     if (threads > 64) threads = 64;
     const int parts = (int)std::min<uint64_t>(1u << 20, n / s->chunk_text + 1);
@@ -1374,7 +1374,7 @@ size_t find_record_start(const char *buf, size_t from, size_t n)
 // bytes before it), so N callers with adjacent ranges cover the file exactly once.
 int feed_file_stream(hs_screen *s, int fd, uint64_t size, int threads, uint64_t range_begin = 0, uint64_t range_end = ~0ull)
 {
-    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (s->flushed || s->flush_pending) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     range_end = std::min(range_end, size);
     if (range_begin >= range_end) return HS_OK;
     const uint64_t B = s->file_block;
@@ -1486,7 +1486,7 @@ bool file_wants_mmap(const hs_screen *s, int threads) { return s->file_mode == 1
 
 int feed_file_mmap(hs_screen *s, int fd, uint64_t size, int threads, uint64_t range_begin = 0, uint64_t range_end = ~0ull)
 {
-    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (s->flushed || s->flush_pending) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     range_end = std::min(range_end, size);
     if (range_begin >= range_end) return HS_OK;
     void *m = mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
@@ -1517,7 +1517,7 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
     if (!s || !path) return fail(HS_EINVAL, "null argument");
     ON_DEVICE(s->db->device);
     // plain FASTA in a regular file: stream it through the pinned ring to the device parser
-    if (s->ingest_mode != 0 && strcmp(path, "-") != 0) {
+    if (strcmp(path, "-") != 0) {
         const int fd = open(path, O_RDONLY);
         struct stat sb;
         if (fd >= 0 && fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0) {
@@ -1526,8 +1526,10 @@ HS_API int hs_screen_feed_fasta(hs_screen *s, const char *path, int host_threads
             size_t first = 0;
             while (first < hn && (head[first] == '\n' || head[first] == '\r')) first++;
             if (first < hn && head[first] == '>') {   // not gzip (1f 8b), not FASTQ
-                const int rc = file_wants_mmap(s, host_threads) ? feed_file_mmap(s, fd, (uint64_t)sb.st_size, host_threads)
-                                                                : feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads);
+                // ("ingest" 0 = host packer only: the mapped form IS the host path, minus a copy)
+                const int rc = (s->ingest_mode == 0 || file_wants_mmap(s, host_threads))
+                                   ? feed_file_mmap(s, fd, (uint64_t)sb.st_size, host_threads)
+                                   : feed_file_stream(s, fd, (uint64_t)sb.st_size, host_threads);
                 close(fd);
                 return rc;
             }
@@ -1608,7 +1610,7 @@ HS_API int hs_screen_feed_packed(hs_screen *s, const uint64_t *seq2, const uint3
 {
     if (!s || ((!seq2 || !inv) && n_bases)) return fail(HS_EINVAL, "null argument");
     ON_DEVICE(s->db->device);
-    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (s->flushed || s->flush_pending) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     std::lock_guard<std::mutex> lk(s->mu);
     s->st.n_bases += n_bases;
     return feed_host_chunk(s, seq2, inv, n_bases, nullptr);
@@ -1618,7 +1620,7 @@ HS_API int hs_screen_feed_packed_device(hs_screen *s, const void *d_seq2, const 
 {
     if (!s || ((!d_seq2 || !d_inv) && n_bases)) return fail(HS_EINVAL, "null argument");
     ON_DEVICE(s->db->device);
-    if (s->flushed) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
+    if (s->flushed || s->flush_pending) return fail(HS_ESTATE, "screen already flushed; call hs_screen_reset first");
     if (((uintptr_t)d_seq2 & 15) || ((uintptr_t)d_inv & 15)) return fail(HS_EINVAL, "packed device buffers must be 16-byte aligned");
     std::lock_guard<std::mutex> lk(s->mu);
     s->st.n_bases += n_bases;

@@ -138,8 +138,9 @@ int hs_screen_new(hs_db *db, hs_screen **out);
 int hs_screen_set_stream(hs_screen *s, void *cuda_stream);
 /* Options: "filter" 1/0 = skip probes for hashes above the db's largest key (exact;
  * default 1); "batch_bloom" 1/0 = issue the Bloom-tier reads of four k-mers together (default 1);
- * "sparse" 1/0 = O(present hashes) reduction and reset (default 1; 0 = always the dense kernels); "keep_query" 1/0 = keep packed chunks in HBM until finish (default 1,
- * needed if the mixture threshold must be revisited); "chunk_bases" = host packer
+ * "sparse" 1/0 = O(present hashes) reduction and reset (default 1; 0 = always the dense kernels); "keep_query" 1 = keep packed chunks in HBM until finish
+ * (needed if the mixture threshold must be revisited; 0 is refused with HS_EUNSUPPORTED: one screen holds 3/8 byte per query
+ * base in HBM, i.e. ~480 Gbp fit a 180 GB B200 -- split larger read sets across screens and GPUs); "chunk_bases" = host packer
  * chunk size; "piece_bases" = positions per upload+launch piece of packed host feeds;
  * "ingest" 0/1/2 = host packer only / device parser only / both compete (default; packer
  * threads join when at least six were asked for); "file_readers", "file_block_bytes" = reader

@@ -760,9 +760,12 @@ def test_file_streaming_blocks_and_giant_records(tmp_path, variant):
     assert int(want.shared.sum()) >= 1000
     # file_mode 0: pread ring -> device parser; 1: the file mapped and packed by the host threads (16 KiB spans:
     # hundreds of them, so both the 64-byte block path of the packer and its line path meet every boundary)
-    for mode, block, readers in ((0, 65536, 3), (0, 1 << 20, 2), (0, 16 << 20, 4), (1, 0, 4), (1, 16384, 5)):
+    # (mode -1: "ingest" 0 = host packers only, which takes the mapped form whatever file_mode says)
+    for mode, block, readers in ((0, 65536, 3), (0, 1 << 20, 2), (0, 16 << 20, 4), (1, 0, 4), (1, 16384, 5), (-1, 50_000, 2)):
         scr = hs.Screen(db)
-        scr.set_option("file_mode", mode)
+        if mode < 0:
+            scr.set_option("ingest", 0)
+        scr.set_option("file_mode", max(mode, 0))
         if mode == 0:
             scr.set_option("file_block_bytes", block)
             scr.set_option("file_readers", readers)

@@ -268,12 +268,13 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "strong" if kind == "c3" else "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        # same workload name and keys as the CUDA arm's line; the sample this arm timed is in cpu_baseline.sample
+        # the CUDA arm's workload, named and keyed the same way (a subset of its `config` with identical values);
+        # what this arm actually timed -- a bounded sample of it -- is described in cpu_baseline
         "config": {"workload": workload_name(args, kind), "k": k, "s": s,
-                   "sketches": n_sk, "mutation_rate": 0.01, "winner_take_all": bool(args.wta),
-                   "cpu_sample_mbp_per_step": args.cpu_mbp,
-                   "timing": "host wall clock around the CPU screen, all host threads"},
+                   "sketches": n_sk, "mutation_rate": 0.01, "winner_take_all": bool(args.wta)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": cpu.kind, "sample": sample,
+                         "sample_mbp_per_step": args.cpu_mbp, "real_genome_sketches_in_sample_table": n_real,
+                         "timing": "host wall clock around the CPU screen, all host threads",
                          "table_build_s": cpu.table_build_s, "note": cpu.note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

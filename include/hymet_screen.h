@@ -64,7 +64,7 @@ typedef struct {
     uint64_t n_positions;    /* packed positions streamed (bases + record separators + padding) */
     uint64_t n_valid_kmers;  /* K: k-mers hashed (S4) */
     uint64_t n_probes;       /* P: table probes issued (<= K when the range pre-filter is on) */
-    uint64_t n_bucket_reads; /* 32-byte bucket sectors read by those probes */
+    uint64_t n_bucket_reads; /* 128-byte bucket lines read by those probes */
     uint64_t n_hits;         /* H: probes that found a key (count updates) */
     uint64_t n_mix_inserts;  /* hashes offered to the mixture bottom-s set */
     uint64_t set_size;       /* S10, printed by mash as "Estimated distinct k-mers in mixture" */
